@@ -1,0 +1,157 @@
+/*
+ * sparsepoly_b200.h -- C ABI of the B200-native solver backend for sparsepoly.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the per-epoch solver loops
+ * (pcd / pbcd / psgd), the ANOVA / all-subsets kernels they are built on, the fused loss
+ * derivatives and the regularizers' proximal operators.  In the reference that boundary is the
+ * call from the Python fit drivers into numba @njit functions with numpy arrays mutated in
+ * place; here it is Python -> ctypes -> these entry points with DEVICE
+ * arrays mutated in place.  Each entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer unless its name ends in _host;
+ *   - fp64 values, int32 indices / indptr (reference dataset.py:60-66);
+ *   - `stream` is a cudaStream_t (0 = default stream); all calls are asynchronous;
+ *   - return value: SP_OK (0) or an error code; sp_last_error() gives the message
+ *     (thread-local).  Unsupported solver x regularizer x degree combinations return
+ *     SP_ERR_UNSUPPORTED with the reference's wording where it has one;
+ *   - calls sharing buffers must be issued on one stream; a handle-free API: all state lives
+ *     in caller-owned device buffers (PyTorch tensors in the Python host layer).
+ *   - loss ids : 0 squared, 1 logistic, 2 squared_hinge        (reference loss.py:13-71)
+ *   - reg ids  : 0 l1, 1 l21, 2 squaredl12, 3 squaredl21, 4 omegati, 5 omegacs
+ *                                                   (reference regularizer/__init__.py:8-15)
+ *   - degree == -1 selects the all-subsets kernel (reference pcd_all.py:41, omegati.py:53).
+ */
+#ifndef SPARSEPOLY_B200_H
+#define SPARSEPOLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+typedef void *sp_stream;
+
+enum { SP_STATUS_OK = 0, SP_STATUS_INVALID = 1, SP_STATUS_UNSUPPORTED = 2, SP_STATUS_CUDA = 3 };
+
+/* Device-resident design matrix in both layouts (replaces CSRDataset / CSCDataset,
+ * reference dataset.py:69-116).  Unused layouts may be NULL: psgd / predict need CSR,
+ * pcd / pbcd need CSC (sweeps) and CSR (cache precompute).  Within a row / column the indices
+ * must be strictly increasing. */
+typedef struct sp_dataset {
+    int32_t n_samples, n_features;
+    int64_t nnz;
+    const int32_t *csr_indptr, *csr_indices;
+    const double *csr_data;
+    const int32_t *csc_indptr, *csc_indices;
+    const double *csc_data;
+} sp_dataset;
+
+/* Coordinate-order plan for the sequential sweeps (built by sp_plan_partition + sp_plan_order).
+ * n_cta = width of the thread-block cluster; samples are range-partitioned over its CTAs. */
+typedef struct sp_plan {
+    int32_t n_cta;            /* power of two, 1..16 */
+    int32_t threads;          /* threads per CTA, multiple of 32, 32..256 */
+    const int32_t *pos_ptr;   /* [d*(n_cta+1)] CSC offsets of the per-CTA slices, by position */
+    const int32_t *flag_idx;  /* [nnz] CSC row index | 0x80000000 when the sample also occurs in
+                                 the column visited at the previous position */
+    const int32_t *idx_feat;  /* [d] coordinate order (indices_feature in the reference) */
+} sp_plan;
+
+int sp_abi_version(void);
+const char *sp_last_error(void);
+int sp_device_count(int *count_host);
+/* make `device` current for this thread's subsequent calls (cudaSetDevice) */
+int sp_set_device(int device);
+
+/* ------------------------------------------------------------------ dataset / plan helpers */
+/* out[j] = sum_i x_ij^2   (row_norms(X.T, squared=True), sparse_factorization_machines.py:409) */
+int sp_col_norm_sq(const sp_dataset *ds, double *out, sp_stream stream);
+/* col_part[j*(n_cta+1)+c]: CSC offset where CTA c's sample range starts in column j */
+int sp_plan_partition(const sp_dataset *ds, int n_cta, int32_t *col_part, sp_stream stream);
+/* position table + hazard flags for the order idx_feat (call again after every shuffle) */
+int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part, const int32_t *idx_feat,
+                  int32_t *pos_ptr, int32_t *flag_idx, sp_stream stream);
+/* out[c*rows+r] = in[r*cols+c] */
+int sp_transpose_f64(const double *in, double *out, int rows, int cols, sp_stream stream);
+/* doubles per sample record {y_pred, y, A^1..A^(m-1)} for a model of this top degree */
+int sp_rec_stride(int degree);
+
+/* ------------------------------------------------------------------------------ prediction */
+/* out[i*out_stride] (+)= <w,x_i> + sum_s lams[s] * K(P[:,s], x_i)    (kernels.poly_predict,
+ * reference kernels.py:140-153; K = ANOVA degree-m DP or all-subsets product).
+ * P_dk is feature-major [d,k]; w may be NULL; accumulate != 0 adds to out. */
+int sp_predict(const sp_dataset *ds, const double *P_dk, int k, const double *lams, int degree,
+               const double *w, double *out, int out_stride, int accumulate, sp_stream stream);
+
+/* K[i*k+s] = K(P[:,s], x_i): the Gram matrix of kernels.anova_kernel (kernels.py:71-115) /
+ * kernels.all_subsets_kernel (kernels.py:118-137, degree=-1). */
+int sp_kernel_matrix(const sp_dataset *ds, const double *P_dk, int k, int degree, double *K,
+                     sp_stream stream);
+
+/* --------------------------------------------------------------------------- pcd / linear */
+/* One pass of exact coordinate descent on w (cd_linear._cd_linear_epoch, cd_linear.py:8-33).
+ * rec is the per-sample record array (y_pred at +0, y at +1); *viol accumulates sum |update|. */
+int sp_cd_linear_epoch(const sp_dataset *ds, const sp_plan *plan, double *w,
+                       const double *col_norm_sq, double alpha, int loss, double *rec,
+                       int rec_stride, double *viol, sp_stream stream);
+
+/* One pcd epoch over all k components of one order (pcd.pcd_epoch, pcd.py:71-137; degree=-1:
+ * pcd_all.pcd_epoch, pcd_all.py:44-102).  P_kd is component-major [k,d] (the reference's
+ * P_[order]); lams [k]; regstate >= 8 doubles of scratch; idx_comp_host = indices_component. */
+int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P_kd, int k, const double *lams,
+                 int degree, double beta, double gamma, double eta, int reg, int loss, double *rec,
+                 int rec_stride, double *regstate, double *viol, const int32_t *idx_comp_host,
+                 sp_stream stream);
+
+/* ----------------------------------------------------------------------------------- pbcd */
+/* One pbcd epoch (pbcd.pbcd_epoch, pbcd.py:82-148; degree=-1: pbcd_all.pbcd_epoch,
+ * pbcd_all.py:68-132).  P_dk feature-major [d,k]; yrec [n,2] = {y_pred, y};
+ * A [n,(m-1),k] (ANOVA) or [n,k] (all-subsets) scratch; reg_norms [d] and regstate [>=16]
+ * regularizer scratch. */
+int sp_pbcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P_dk, int k, const double *lams,
+                  int degree, double beta, double gamma, double eta, int reg, int loss, double *yrec,
+                  double *A, double *reg_norms, double *regstate, double *viol, sp_stream stream);
+
+/* ----------------------------------------------------------------------------------- psgd */
+/* (eta_P, eta_w) of psgd._get_eta (psgd.py:9-22); host-side scalar helper. */
+int sp_get_eta(int learning_rate, double eta0, double alpha, double beta, double power_t,
+               int64_t it, double *eta_P_host, double *eta_w_host);
+
+/* Minibatch gradient: samples idx_samples[b0..b1) (psgd._pred + _update_grads,
+ * psgd.py:47-91).  P_odk [n_orders,d,k]; grad_P same shape and grad_w [d] are accumulated
+ * into (fp64 atomics); *loss_sum accumulates sum of losses at the pre-update parameters. */
+int sp_psgd_grad(const sp_dataset *ds, const double *y, const double *P_odk, int n_orders, int k,
+                 const double *w, const double *lams, int degree, int loss, int fit_linear,
+                 const int32_t *idx_samples, int b0, int b1, double *grad_P, double *grad_w,
+                 double *loss_sum, sp_stream stream);
+
+/* SGD step + zeroing of the gradients (psgd._update_params without the prox, psgd.py:94-117,
+ * :195-196):  P = (P - (eta_P/batch)*grad_P) / (1 + eta_P*beta), same for w with alpha. */
+int sp_psgd_step(double *P_odk, double *grad_P, double *w, double *grad_w, int n_orders, int d, int k,
+                 double eta_P, double eta_w, double alpha, double beta, int batch, int fit_linear,
+                 sp_stream stream);
+
+/* regularizer.prox on one order P_dk [d,k] (l1.py:50-51, l21.py:43-48, squaredl12.py:66-78,
+ * squaredl21.py:63-74, regularizer/utils.py:26-70).  work: >= d + 8*k + 64 doubles. */
+int sp_prox(double *P_dk, int d, int k, int reg, double strength, double *work, sp_stream stream);
+
+/* doubles of scratch sp_prox / sp_psgd_epoch need for a [d,k] matrix */
+size_t sp_prox_work_doubles(int d, int k);
+
+/* Whole single-GPU psgd epoch = psgd.psgd_epoch (psgd.py:125-199): loops the three calls
+ * above over the minibatches; *it_io_host is advanced once per parameter update. */
+int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_orders, int k, double *w,
+                  const double *lams, int degree, double alpha, double beta, double gamma, int reg,
+                  int loss, double *grad_P, double *grad_w, const int32_t *idx_samples,
+                  int fit_linear, double eta0, int learning_rate, double power_t, int batch_size,
+                  int64_t *it_io_host, double *loss_sum, double *work, sp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSEPOLY_B200_H */

@@ -1,0 +1,16 @@
+"""sparsepoly_b200 -- B200-native (sm_100a CUDA) solver backend behind sparsepoly's
+sklearn-style API.  See DESIGN.md; the C ABI is declared in include/sparsepoly_b200.h."""
+from .estimators import (
+    SparseAllSubsetsClassifier,
+    SparseAllSubsetsRegressor,
+    SparseFactorizationMachineClassifier,
+    SparseFactorizationMachineRegressor,
+)
+
+__all__ = [
+    "SparseAllSubsetsClassifier",
+    "SparseAllSubsetsRegressor",
+    "SparseFactorizationMachineClassifier",
+    "SparseFactorizationMachineRegressor",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,100 @@
+"""ctypes binding of libsparsepoly_b200.so (declared in include/sparsepoly_b200.h).
+
+There is no CPU fallback: if the shared library cannot be loaded (or built), importing the
+solvers fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsparsepoly_b200.so")
+
+LOSS_IDS = {"squared": 0, "logistic": 1, "squared_hinge": 2}
+REG_IDS = {"l1": 0, "l21": 1, "squaredl12": 2, "squaredl21": 3, "omegati": 4, "omegacs": 5}
+LEARNING_RATE = {"constant": 0, "optimal": 1, "pegasos": 2, "invscaling": 3}
+
+SP_OK, SP_ERR_INVALID, SP_ERR_UNSUPPORTED, SP_ERR_CUDA = 0, 1, 2, 3
+
+_vp = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+
+
+class SpDataset(C.Structure):
+    """struct sp_dataset (include/sparsepoly_b200.h)."""
+    _fields_ = [("n_samples", C.c_int32), ("n_features", C.c_int32), ("nnz", C.c_int64),
+                ("csr_indptr", _vp), ("csr_indices", _vp), ("csr_data", _vp),
+                ("csc_indptr", _vp), ("csc_indices", _vp), ("csc_data", _vp)]
+
+
+class SpPlan(C.Structure):
+    """struct sp_plan (include/sparsepoly_b200.h)."""
+    _fields_ = [("n_cta", C.c_int32), ("threads", C.c_int32), ("pos_ptr", _vp), ("flag_idx", _vp),
+                ("idx_feat", _vp)]
+
+
+_DSP = C.POINTER(SpDataset)
+_PLP = C.POINTER(SpPlan)
+
+# name -> (restype, argtypes); every symbol the header declares
+SIGNATURES = {
+    "sp_abi_version": (_i, []),
+    "sp_last_error": (C.c_char_p, []),
+    "sp_device_count": (_i, [C.POINTER(C.c_int)]),
+    "sp_set_device": (_i, [_i]),
+    "sp_col_norm_sq": (_i, [_DSP, _vp, _vp]),
+    "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
+    "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sp_transpose_f64": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sp_rec_stride": (_i, [_i]),
+    "sp_predict": (_i, [_DSP, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "sp_kernel_matrix": (_i, [_DSP, _vp, _i, _i, _vp, _vp]),
+    "sp_cd_linear_epoch": (_i, [_DSP, _PLP, _vp, _vp, _d, _i, _vp, _i, _vp, _vp]),
+    "sp_pcd_epoch": (_i, [_DSP, _PLP, _vp, _i, _vp, _i, _d, _d, _d, _i, _i, _vp, _i, _vp, _vp,
+                          C.POINTER(C.c_int32), _vp]),
+    "sp_pbcd_epoch": (_i, [_DSP, _PLP, _vp, _i, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                           _vp]),
+    "sp_get_eta": (_i, [_i, _d, _d, _d, _d, C.c_int64, C.POINTER(_d), C.POINTER(_d)]),
+    "sp_psgd_grad": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp,
+                          _vp]),
+    "sp_psgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _vp]),
+    "sp_prox_work_doubles": (C.c_size_t, [_i, _i]),
+    "sp_prox": (_i, [_vp, _i, _i, _i, _d, _vp, _vp]),
+    "sp_psgd_epoch": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp,
+                           _i, _d, _i, _d, _i, C.POINTER(C.c_int64), _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load (building first if the .so is missing and nvcc is available)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        import torch  # noqa: F401  (makes torch's libcudart.so.12 the shared runtime instance)
+    except Exception:
+        pass
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sp_abi_version() != 1:
+        raise ImportError("libsparsepoly_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    """Map a C status to the exception type the reference raises at the same spot."""
+    if rc == SP_OK:
+        return
+    msg = load().sp_last_error().decode("utf-8", "replace")
+    if rc in (SP_ERR_INVALID, SP_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)

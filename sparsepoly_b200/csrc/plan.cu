@@ -1,0 +1,150 @@
+// Dataset-side helpers for the sequential sweeps (device resident CSC; reference dataset.py:94-134
+// hands out column slices, here the column slices are additionally range-partitioned over the
+// CTAs of a thread-block cluster and tagged with intra-CTA read-after-write hazards).
+#include "common.cuh"
+#include "sparsepoly_b200.h"
+
+namespace {
+
+// out[j] = sum_i x_ij^2  (sparse_factorization_machines.py:409  row_norms(X.T, squared=True))
+__global__ void col_norm_sq_kernel(int d, const int32_t *__restrict__ indptr,
+                                   const double *__restrict__ data, double *out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < d; j += n_warps) {
+        double acc = 0.0;
+        for (int e = indptr[j] + lane; e < indptr[j + 1]; e += 32) acc += data[e] * data[e];
+        acc = sp_warp_allsum(acc);
+        if (lane == 0) out[j] = acc;
+    }
+}
+
+// col_part[j*(C+1)+c] = first CSC offset of column j whose row index >= c*chunk  (c=0..C)
+__global__ void partition_kernel(int d, int C, int chunk, const int32_t *__restrict__ indptr,
+                                 const int32_t *__restrict__ indices, int32_t *col_part) {
+    const long long total = (long long)d * (C + 1);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(g / (C + 1)), c = (int)(g % (C + 1));
+        int lo = indptr[j], hi = indptr[j + 1];
+        if (c == C) { col_part[g] = hi; continue; }
+        const long long bound = (long long)c * chunk;
+        while (lo < hi) {                       // lower_bound(rows, bound)
+            const int mid = (lo + hi) >> 1;
+            if (indices[mid] < bound) lo = mid + 1; else hi = mid;
+        }
+        col_part[g] = lo;
+    }
+}
+
+__global__ void order_ptr_kernel(int d, int C, const int32_t *__restrict__ idx_feat,
+                                 const int32_t *__restrict__ col_part, int32_t *pos_ptr) {
+    const long long total = (long long)d * (C + 1);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(g / (C + 1)), c = (int)(g % (C + 1));
+        pos_ptr[g] = col_part[(long long)idx_feat[t] * (C + 1) + c];
+    }
+}
+
+// flag_idx[e] = row | FLAG if the same sample also has a nonzero in the column visited
+// immediately before this one (position t-1): that sample's record is still being rewritten
+// when position t's prefetch is issued, so the sweep kernel must re-read it after the barrier.
+__global__ void order_flag_kernel(int d, const int32_t *__restrict__ idx_feat,
+                                  const int32_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ indices, int32_t *flag_idx) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = warp; t < d; t += n_warps) {
+        const int j = idx_feat[t];
+        int plo = 0, phi = 0;
+        if (t > 0) { const int jp = idx_feat[t - 1]; plo = indptr[jp]; phi = indptr[jp + 1]; }
+        for (int e = indptr[j] + lane; e < indptr[j + 1]; e += 32) {
+            const int row = indices[e];
+            int lo = plo, hi = phi;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (indices[mid] < row) lo = mid + 1; else hi = mid;
+            }
+            const bool hit = (lo < phi) && (indices[lo] == row);
+            flag_idx[e] = hit ? (int32_t)((uint32_t)row | SP_FLAG_BIT) : row;
+        }
+    }
+}
+
+__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows,
+                                 int cols) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int rr = by + r, cc = bx + threadIdx.x;
+        if (rr < rows && cc < cols) tile[r][threadIdx.x] = in[(size_t)rr * cols + cc];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int cc = bx + r, rr = by + threadIdx.x;
+        if (rr < rows && cc < cols) out[(size_t)cc * rows + rr] = tile[threadIdx.x][r];
+    }
+}
+
+int blocks_for(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" int sp_col_norm_sq(const sp_dataset *ds, double *out, sp_stream stream) {
+    if (!ds || !ds->csc_indptr || !out) { sp_set_error("sp_col_norm_sq: invalid argument"); return SP_ERR_INVALID; }
+    if (ds->n_features == 0) return SP_OK;
+    col_norm_sq_kernel<<<blocks_for((long long)ds->n_features * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        ds->n_features, ds->csc_indptr, ds->csc_data, out);
+    SP_LAUNCH_CHECK("col_norm_sq_kernel");
+    return SP_OK;
+}
+
+extern "C" int sp_plan_partition(const sp_dataset *ds, int n_cta, int32_t *col_part, sp_stream stream) {
+    if (!ds || !ds->csc_indptr || !col_part || n_cta < 1 || n_cta > 16) {
+        sp_set_error("sp_plan_partition: invalid argument (n_cta must be 1..16)");
+        return SP_ERR_INVALID;
+    }
+    if (ds->n_features == 0) return SP_OK;
+    const int chunk = (ds->n_samples + n_cta - 1) / n_cta;
+    partition_kernel<<<blocks_for((long long)ds->n_features * (n_cta + 1), 256), 256, 0,
+                       (cudaStream_t)stream>>>(ds->n_features, n_cta, chunk > 0 ? chunk : 1,
+                                               ds->csc_indptr, ds->csc_indices, col_part);
+    SP_LAUNCH_CHECK("partition_kernel");
+    return SP_OK;
+}
+
+extern "C" int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part,
+                             const int32_t *idx_feat, int32_t *pos_ptr, int32_t *flag_idx,
+                             sp_stream stream) {
+    if (!ds || !col_part || !idx_feat || !pos_ptr || !flag_idx || n_cta < 1 || n_cta > 16) {
+        sp_set_error("sp_plan_order: invalid argument");
+        return SP_ERR_INVALID;
+    }
+    if (ds->n_features == 0) return SP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    order_ptr_kernel<<<blocks_for((long long)ds->n_features * (n_cta + 1), 256), 256, 0, st>>>(
+        ds->n_features, n_cta, idx_feat, col_part, pos_ptr);
+    SP_LAUNCH_CHECK("order_ptr_kernel");
+    order_flag_kernel<<<blocks_for((long long)ds->n_features * 32, 256), 256, 0, st>>>(
+        ds->n_features, idx_feat, ds->csc_indptr, ds->csc_indices, flag_idx);
+    SP_LAUNCH_CHECK("order_flag_kernel");
+    return SP_OK;
+}
+
+extern "C" int sp_transpose_f64(const double *in, double *out, int rows, int cols, sp_stream stream) {
+    if (!in || !out || rows < 0 || cols < 0) { sp_set_error("sp_transpose_f64: invalid argument"); return SP_ERR_INVALID; }
+    if (rows == 0 || cols == 0) return SP_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    if (grid.y > 65535) { sp_set_error("sp_transpose_f64: too many rows (%d)", rows); return SP_ERR_INVALID; }
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+    SP_LAUNCH_CHECK("transpose_kernel");
+    return SP_OK;
+}

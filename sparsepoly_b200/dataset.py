@@ -1,0 +1,208 @@
+"""Device-resident design matrix (replaces reference sparsepoly/dataset.py).
+
+The reference wraps scipy CSR/CSC (or dense) arrays in numba jitclasses handing out row /
+column slices (dataset.py:69-116).  Here the matrix lives in HBM in BOTH layouts as int32 /
+fp64 torch tensors (PyTorch only holds the memory); kernels read coalesced row streams (CSR:
+prediction, cache precompute, psgd) and column streams (CSC: coordinate sweeps).  Dense input
+is stored with every entry, like the reference's ContiguousDataset / FortranDataset
+(dataset.py:18-57).
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("sparsepoly_b200 needs a CUDA device (there is no CPU fallback)")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _h2d(a, device, pin=False):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pin:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=pin)
+
+
+def host_csr(X):
+    """(indptr, indices, data) with sorted, duplicate-free rows; dense X keeps every entry."""
+    if sp.issparse(X):
+        Xr = sp.csr_matrix(X, dtype=np.float64, copy=False)
+        if not Xr.has_canonical_format:
+            Xr = Xr.copy()
+            Xr.sum_duplicates()
+        if Xr.nnz >= 2 ** 31:
+            raise ValueError("nnz >= 2^31 is not supported (int32 indptr, reference dataset.py:60-66)")
+        return (Xr.indptr.astype(np.int32, copy=False), Xr.indices.astype(np.int32, copy=False),
+                Xr.data.astype(np.float64, copy=False))
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    indptr = (np.arange(n + 1, dtype=np.int64) * d).astype(np.int32)
+    indices = np.tile(np.arange(d, dtype=np.int32), n)
+    return indptr, indices, np.ascontiguousarray(X).reshape(-1)
+
+
+def host_csc(X):
+    if sp.issparse(X):
+        Xc = sp.csc_matrix(X, dtype=np.float64, copy=False)
+        if not Xc.has_canonical_format:
+            Xc = Xc.copy()
+            Xc.sum_duplicates()
+        if Xc.nnz >= 2 ** 31:
+            raise ValueError("nnz >= 2^31 is not supported (int32 indptr, reference dataset.py:60-66)")
+        return (Xc.indptr.astype(np.int32, copy=False), Xc.indices.astype(np.int32, copy=False),
+                Xc.data.astype(np.float64, copy=False))
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    indptr = (np.arange(d + 1, dtype=np.int64) * n).astype(np.int32)
+    indices = np.tile(np.arange(n, dtype=np.int32), d)
+    return indptr, indices, np.ascontiguousarray(X.T).reshape(-1)
+
+
+class DeviceDataset:
+    """CSR and/or CSC copy of X in device memory + the sp_dataset struct handed to the C ABI."""
+
+    def __init__(self, X, need_csr=True, need_csc=True, device=None, pin=False):
+        self.device = _device(device)
+        self.n_samples, self.n_features = int(X.shape[0]), int(X.shape[1])
+        self.h2d_bytes = 0
+        self.csr = self.csc = None
+        if need_csr:
+            self.csr = tuple(_h2d(a, self.device, pin) for a in host_csr(X))
+            self.h2d_bytes += sum(t.numel() * t.element_size() for t in self.csr)
+        if need_csc:
+            self.csc = tuple(_h2d(a, self.device, pin) for a in host_csc(X))
+            self.h2d_bytes += sum(t.numel() * t.element_size() for t in self.csc)
+        ref = self.csr if self.csr is not None else self.csc
+        self.nnz = int(ref[2].numel())
+        s = _lib.SpDataset()
+        s.n_samples, s.n_features, s.nnz = self.n_samples, self.n_features, self.nnz
+        if self.csr is not None:
+            s.csr_indptr, s.csr_indices, s.csr_data = (t.data_ptr() for t in self.csr)
+        if self.csc is not None:
+            s.csc_indptr, s.csc_indices, s.csc_data = (t.data_ptr() for t in self.csc)
+        self.struct = s
+
+    @classmethod
+    def from_device_csr(cls, n_samples, n_features, indptr, indices, data):
+        """Wrap CSR tensors that already live on the device (no copy)."""
+        self = cls.__new__(cls)
+        self.device = data.device
+        self.n_samples, self.n_features = int(n_samples), int(n_features)
+        self.csr, self.csc = (indptr, indices, data), None
+        self.nnz = int(data.numel())
+        self.h2d_bytes = 0
+        s = _lib.SpDataset()
+        s.n_samples, s.n_features, s.nnz = self.n_samples, self.n_features, self.nnz
+        s.csr_indptr, s.csr_indices, s.csr_data = indptr.data_ptr(), indices.data_ptr(), data.data_ptr()
+        self.struct = s
+        return self
+
+    # reference accessor names (dataset.py:27-37, :78-86)
+    def get_n_samples(self):
+        return self.n_samples
+
+    def get_n_features(self):
+        return self.n_features
+
+    def count_nonzero(self):
+        return self.nnz
+
+    def ref(self):
+        return C.byref(self.struct)
+
+    def col_norm_sq(self):
+        out = torch.empty(self.n_features, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.load().sp_col_norm_sq(self.ref(), _ptr(out), _stream()))
+        return out
+
+
+def get_dataset(X, order="c", device=None):
+    """Same call shape as the reference factory (dataset.py:119-134): order="fortran" builds
+    what the column sweeps need (CSC + the CSR used for cache precompute), anything else the
+    row layout only."""
+    if order == "fortran":
+        return DeviceDataset(X, need_csr=True, need_csc=True, device=device)
+    return DeviceDataset(X, need_csr=True, need_csc=False, device=device)
+
+
+def _pow2_floor(v):
+    p = 1
+    while p * 2 <= v:
+        p *= 2
+    return p
+
+
+def choose_geometry(ds, solver, n_cta=None, threads=None):
+    """Cluster width / CTA size for the sequential sweeps from the mean column length."""
+    import os
+    env_c = os.environ.get("SPARSEPOLY_B200_NCTA")
+    env_t = os.environ.get("SPARSEPOLY_B200_THREADS")
+    if n_cta is None and env_c:
+        n_cta = int(env_c)
+    if threads is None and env_t:
+        threads = int(env_t)
+    avg = ds.nnz / max(ds.n_features, 1)
+    if n_cta is None:
+        if solver == "pbcd":
+            n_cta = _pow2_floor(max(1, min(16, int(avg // 16))))   # >= ~2 nonzeros per warp
+        else:
+            n_cta = _pow2_floor(max(1, min(16, int(avg // 32))))   # ~1 nonzero per thread
+    if threads is None:
+        if solver == "pbcd":
+            per_cta = avg / n_cta
+            threads = 32 * max(1, min(8, int(np.ceil(per_cta / 4))))
+        else:
+            per_cta = avg / n_cta
+            threads = 32 * max(1, min(8, int(np.ceil(per_cta / 32))))
+    return int(n_cta), int(threads)
+
+
+class SweepPlan:
+    """Coordinate-order plan (struct sp_plan): per-position column slices of every CTA and the
+    read-after-write hazard flags.  Rebuilt (cheaply, on device) whenever the order changes."""
+
+    def __init__(self, ds, solver="pcd", n_cta=None, threads=None):
+        self.ds = ds
+        self.n_cta, self.threads = choose_geometry(ds, solver, n_cta, threads)
+        dev = ds.device
+        d, C_ = ds.n_features, self.n_cta
+        self.col_part = torch.empty(max(d * (C_ + 1), 1), dtype=torch.int32, device=dev)
+        self.pos_ptr = torch.empty(max(d * (C_ + 1), 1), dtype=torch.int32, device=dev)
+        self.flag_idx = torch.empty(max(ds.nnz, 1), dtype=torch.int32, device=dev)
+        self.idx_feat = torch.empty(max(d, 1), dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().sp_plan_partition(ds.ref(), C_, _ptr(self.col_part), _stream()))
+        self._order_host = None
+        s = _lib.SpPlan()
+        s.n_cta, s.threads = C_, self.threads
+        s.pos_ptr, s.flag_idx, s.idx_feat = (self.pos_ptr.data_ptr(), self.flag_idx.data_ptr(),
+                                             self.idx_feat.data_ptr())
+        self.struct = s
+
+    def set_order(self, idx_feat_host):
+        idx = np.ascontiguousarray(idx_feat_host, dtype=np.int32)
+        if self._order_host is not None and np.array_equal(idx, self._order_host):
+            return
+        self._order_host = idx.copy()
+        self.idx_feat[: idx.size].copy_(torch.from_numpy(idx))
+        _lib.check(_lib.load().sp_plan_order(self.ds.ref(), self.n_cta, _ptr(self.col_part),
+                                             _ptr(self.idx_feat), _ptr(self.pos_ptr),
+                                             _ptr(self.flag_idx), _stream()))
+
+    def ref(self):
+        return C.byref(self.struct)

@@ -1,0 +1,651 @@
+"""sklearn-style estimators with the reference's public surface, fitted on the B200 backend.
+
+Drop-in for reference sparsepoly/{base,sparse_factorization_machines,sparse_all_subsets}.py:
+same class names, constructor parameters / defaults, fitted attributes (P_, w_, lams_,
+n_iter_, it_, label_binarizer_), warnings and verbose strings.  What changed is below the
+boundary: the Dataset / Loss / Regularizer jitclasses and the @njit epoch functions are
+replaced by device buffers and calls into libsparsepoly_b200.so (solvers.py).
+
+Differences from the reference that are deliberate and documented in DESIGN.md:
+  * unsupported solver x regularizer x degree combinations raise ValueError up front (the
+    reference fails with a numba TypingError when the epoch function is compiled);
+  * `callback(self)` sees the CURRENT P_ / w_ for every solver (the reference exposes a stale
+    pre-fit copy for pbcd / psgd, sparse_factorization_machines.py:285 vs :352);
+  * the initial predictions use the DP kernel instead of the power-sum identities
+    (kernels.py:91-114): same value up to ~1e-16 relative rounding.
+"""
+import warnings
+from abc import ABCMeta, abstractmethod
+
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.preprocessing import LabelBinarizer, add_dummy_feature
+from sklearn.utils import check_random_state
+from sklearn.utils.multiclass import type_of_target
+from sklearn.utils.validation import check_array, check_X_y
+
+from . import _lib, solvers
+from .dataset import DeviceDataset, SweepPlan, _device
+from .distributed import global_sum
+
+REGRESSION_LOSSES = ("squared",)
+CLASSIFICATION_LOSSES = ("squared", "squared_hinge", "logistic")
+FM_REGULARIZERS = ("squaredl12", "squaredl21", "l1", "l21", "omegati", "omegacs")
+ALL_SUBSETS_REGULARIZERS = ("l1", "l21", "omegacs", "omegati")
+LEARNING_RATE = _lib.LEARNING_RATE
+
+# which regularizers implement which solver protocol (reference README.md:25-31 and the
+# methods each jitclass defines, regularizer/*.py)
+_SOLVER_REGS = {
+    "pcd": ("l1", "squaredl12", "omegati"),
+    "pbcd": ("l1", "l21", "squaredl21", "omegacs"),
+    "psgd": ("l1", "l21", "squaredl12", "squaredl21"),
+}
+
+_f64 = torch.float64
+
+
+def _process_group():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.group.WORLD
+    return None
+
+
+class _SparsePolyBase(BaseEstimator, metaclass=ABCMeta):
+    """Shared validation (reference base.py:17-34)."""
+
+    def _get_loss(self, loss):
+        if loss not in self._LOSSES:
+            losses_str = '", "'.join(self._LOSSES)
+            raise ValueError(f"Loss function {loss} not supported. The available options are:"
+                             f' "{losses_str}".')
+        return loss
+
+    def _get_regularizer(self, regularizer):
+        if regularizer not in self._REGULARIZERS:
+            regularizers_str = '", "'.join(self._REGULARIZERS)
+            raise ValueError(f"Regularizer {regularizer} not supported. The available options are:"
+                             f' "{regularizers_str}".')
+        return regularizer
+
+    def _check_combination(self, solver, regularizer, degree):
+        if solver not in _SOLVER_REGS:
+            raise ValueError(f"Solver {solver} is not supported.")
+        if regularizer not in _SOLVER_REGS[solver]:
+            raise ValueError(f"Regularizer {regularizer} cannot be used with solver {solver}; "
+                             f"{solver} supports: {', '.join(_SOLVER_REGS[solver])}.")
+        if solver == "pcd" and regularizer == "squaredl12" and degree > 2:
+            raise ValueError("SquaredL12 supports only degree=2.")       # squaredl12.py:25-26
+        if solver == "pbcd" and regularizer == "squaredl21" and degree != 2:
+            raise ValueError("SquaredL21 supports only degree=2.")       # squaredl21.py:28-29
+
+    def _init_lambdas(self, rng):
+        if not (self.warm_start and hasattr(self, "lams_")):
+            if self.init_lambdas == "ones":
+                self.lams_ = np.ones(self.n_components)
+            elif self.init_lambdas == "random_signs":
+                self.lams_ = np.sign(rng.randn(self.n_components))
+            else:
+                raise ValueError("Lambdas must be initialized as ones (init_lambdas='ones') or as "
+                                 "random +/- 1 (init_lambdas='random_signs').")
+
+    def _after_epoch(self, it, value, what, sync):
+        """callback / verbose handling shared by the epoch loops; True = stop."""
+        if (self.callback is not None) and it % self.n_calls == 0:
+            sync()
+            if self.callback(self) is not None:
+                return True
+        if self.verbose:
+            print(what.format(it + 1, value))
+        return False
+
+
+class SparsePolyRegressorMixin(RegressorMixin):
+    """reference base.py:37-65."""
+    _LOSSES = REGRESSION_LOSSES
+
+    def _check_X_y(self, X, y):
+        X, y = check_X_y(X, y, accept_sparse=True, multi_output=False, dtype=np.double,
+                         y_numeric=True)
+        return X, y.astype(np.double).ravel()
+
+    def predict(self, X):
+        """Predict regression output for the samples in X ([n_samples] array)."""
+        return self._predict(X)
+
+
+class SparsePolyClassifierMixin(ClassifierMixin):
+    """reference base.py:68-142."""
+    _LOSSES = CLASSIFICATION_LOSSES
+
+    def decision_function(self, X):
+        """Model output before thresholding ([n_samples] array)."""
+        return self._predict(X)
+
+    def predict(self, X):
+        """Predicted class labels for the samples in X."""
+        y_pred = self.decision_function(X) > 0
+        return self.label_binarizer_.inverse_transform(y_pred)
+
+    def predict_proba(self, X):
+        """Probability of the positive class; only available if loss='logistic'."""
+        if self.loss == "logistic":
+            return 1 / (1 + np.exp(-self.decision_function(X)))
+        raise ValueError("Probability estimates only available for loss='logistic'. You may use "
+                         "probability calibration methods from scikit-learn instead.")
+
+    def _check_X_y(self, X, y):
+        is_2d = hasattr(y, "shape") and len(y.shape) > 1 and y.shape[1] >= 2
+        if is_2d or type_of_target(y) != "binary":
+            raise TypeError("Only binary targets supported. For training multiclass or multilabel "
+                            "models, you may use the OneVsRest or OneVsAll metaestimators in "
+                            "scikit-learn.")
+        X, Y = check_X_y(X, y, dtype=np.double, accept_sparse=True, multi_output=False)
+        self.label_binarizer_ = LabelBinarizer(pos_label=1, neg_label=-1)
+        y = self.label_binarizer_.fit_transform(Y).ravel().astype(np.double)
+        return X, y
+
+
+# =============================================================================================
+# Factorization machines
+# =============================================================================================
+class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
+    _REGULARIZERS = FM_REGULARIZERS
+
+    @abstractmethod
+    def __init__(self, degree=2, loss="squared", n_components=2, solver="pcd",
+                 regularizer="squaredl12", alpha=1, beta=1, gamma=1, mean=False, tol=1e-6,
+                 fit_lower="explicit", fit_linear=True, warm_start=False, init_lambdas="ones",
+                 max_iter=100, shuffle=False, batch_size="auto", eta0=1.0, learning_rate="optimal",
+                 power_t=1.0, n_iter_no_change=5, verbose=False, callback=None, n_calls=10,
+                 random_state=None):
+        self.degree = degree
+        self.loss = loss
+        self.n_components = n_components
+        self.solver = solver
+        self.regularizer = regularizer
+        self.alpha = alpha
+        self.beta = beta
+        self.gamma = gamma
+        self.mean = mean
+        self.tol = tol
+        self.fit_lower = fit_lower
+        self.fit_linear = fit_linear
+        self.warm_start = warm_start
+        self.init_lambdas = init_lambdas
+        self.max_iter = max_iter
+        self.shuffle = shuffle
+        self.batch_size = batch_size
+        self.eta0 = eta0
+        self.learning_rate = learning_rate
+        self.power_t = power_t
+        self.n_iter_no_change = n_iter_no_change
+        self.verbose = verbose
+        self.callback = callback
+        self.n_calls = n_calls
+        self.random_state = random_state
+
+    # ---------------------------------------------------------------- helpers
+    def _augment(self, X):
+        # one dummy all-ones column per missing lower order (sparse_factorization_machines.py:86-92)
+        if self.fit_lower == "augment":
+            k = 2 if self.fit_linear else 1
+            for _ in range(self.degree - k):
+                X = add_dummy_feature(X, value=1)
+        return X
+
+    def _scaled(self, n_samples):
+        if self.mean:
+            return self.alpha * n_samples, self.beta * n_samples, self.gamma * n_samples
+        return self.alpha, self.beta, self.gamma
+
+    def _output_orders(self):
+        """(order index, degree) pairs that enter the prediction (quirk kept: explicit lower
+        orders are only added for degree == 3, sparse_factorization_machines.py:445-449)."""
+        orders = [(0, self.degree)]
+        if self.fit_lower == "explicit" and self.degree == 3:
+            orders.append((1, 2))
+        return orders
+
+    def _device_output(self, ds, P_kd_orders, w_dev, lams_dev, out, stride):
+        """_get_output on device: writes the model output into out[::stride]."""
+        first = True
+        for o, deg in self._output_orders():
+            P_dk = solvers.transpose(P_kd_orders[o])
+            solvers.poly_predict(ds, P_dk, lams_dev, deg, w=w_dev if (first and self.fit_linear) else None,
+                                 out=out, out_stride=stride, accumulate=not first)
+            first = False
+        return out
+
+    # ---------------------------------------------------------------- pcd
+    def _fit_pcd(self, X, y, rng, dev):
+        n, d = X.shape
+        k, m = self.n_components, self.degree
+        alpha, beta, gamma = self._scaled(n)
+        ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
+        plan = SweepPlan(ds, "pcd")
+        self._h2d_bytes = ds.h2d_bytes
+        indices_feature = np.arange(d, dtype=np.int32)
+        indices_component = np.arange(k, dtype=np.int32)
+        plan.set_order(indices_feature)
+        stride = solvers.rec_stride(m)
+        rec = torch.zeros(n * stride, dtype=_f64, device=dev)
+        rec[1::stride] = torch.from_numpy(y).to(dev)
+        P = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)         # [n_orders, k, d]
+        w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        self._device_output(ds, P, w, lams, rec, stride)                     # y_pred -> rec[0::stride]
+        col_norm_sq = ds.col_norm_sq()
+        regstate = torch.zeros(16, dtype=_f64, device=dev)
+        viol_dev = torch.zeros(1, dtype=_f64, device=dev)
+
+        def sync():
+            self.P_[...] = P.cpu().numpy()
+            self.w_[...] = w.cpu().numpy()
+
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol_dev.zero_()
+            if self.shuffle:
+                rng.shuffle(indices_component)
+                rng.shuffle(indices_feature)
+                plan.set_order(indices_feature)
+            if self.fit_linear:
+                solvers.cd_linear_epoch(ds, plan, w, col_norm_sq, alpha, self.loss, rec, stride, viol_dev)
+            if self.fit_lower == "explicit":
+                for deg in range(2, m):
+                    solvers.pcd_epoch(ds, plan, P[m - deg], lams, deg, beta, gamma, self.eta0,
+                                      self.regularizer, self.loss, rec, stride, regstate, viol_dev,
+                                      indices_component)
+            solvers.pcd_epoch(ds, plan, P[0], lams, m, beta, gamma, self.eta0, self.regularizer,
+                              self.loss, rec, stride, regstate, viol_dev, indices_component)
+            viol = viol_dev.item()
+            if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
+                break
+            if viol < self.tol:
+                if self.verbose:
+                    print(f"Converged at iteration {it+1}")
+                converged = True
+                break
+        sync()
+        self._y_pred_train = rec[0::stride]
+        return converged, it
+
+    # ---------------------------------------------------------------- pbcd
+    def _fit_pbcd(self, X, y, rng, dev):
+        n, d = X.shape
+        k, m = self.n_components, self.degree
+        alpha, beta, gamma = self._scaled(n)
+        ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
+        plan = SweepPlan(ds, "pbcd")
+        plan_lin = SweepPlan(ds, "pcd") if self.fit_linear else None
+        self._h2d_bytes = ds.h2d_bytes
+        indices_feature = np.arange(d, dtype=np.int32)
+        plan.set_order(indices_feature)
+        if plan_lin is not None:
+            plan_lin.set_order(indices_feature)
+        yrec = torch.zeros(n * 2, dtype=_f64, device=dev)
+        yrec[1::2] = torch.from_numpy(y).to(dev)
+        P_kd = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)
+        w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        self._device_output(ds, P_kd, w, lams, yrec, 2)
+        # feature-major copy for training (sparse_factorization_machines.py:285)
+        P = torch.stack([solvers.transpose(P_kd[o]) for o in range(P_kd.shape[0])])   # [n_orders, d, k]
+        col_norm_sq = ds.col_norm_sq()
+        A = torch.empty(max(n * (m - 1) * k, 1), dtype=_f64, device=dev)
+        reg_norms = torch.zeros(max(d, 1), dtype=_f64, device=dev)
+        regstate = torch.zeros(16, dtype=_f64, device=dev)
+        viol_dev = torch.zeros(1, dtype=_f64, device=dev)
+
+        def sync():
+            for o in range(P.shape[0]):
+                self.P_[o] = solvers.transpose(P[o]).cpu().numpy()
+            self.w_[...] = w.cpu().numpy()
+
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol_dev.zero_()
+            if self.shuffle:
+                rng.shuffle(indices_feature)
+                plan.set_order(indices_feature)
+                if plan_lin is not None:
+                    plan_lin.set_order(indices_feature)
+            if self.fit_linear:
+                solvers.cd_linear_epoch(ds, plan_lin, w, col_norm_sq, alpha, self.loss, yrec, 2, viol_dev)
+            if self.fit_lower == "explicit":
+                for deg in range(2, m):
+                    solvers.pbcd_epoch(ds, plan, P[m - deg], lams, deg, beta, gamma, self.eta0,
+                                       self.regularizer, self.loss, yrec, A, reg_norms, regstate, viol_dev)
+            solvers.pbcd_epoch(ds, plan, P[0], lams, m, beta, gamma, self.eta0, self.regularizer,
+                               self.loss, yrec, A, reg_norms, regstate, viol_dev)
+            viol = viol_dev.item()
+            if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
+                break
+            if viol < self.tol:
+                if self.verbose:
+                    print(f"Converged at iteration {it+1}")
+                converged = True
+                break
+        sync()
+        self._y_pred_train = yrec[0::2]
+        return converged, it
+
+    # ---------------------------------------------------------------- psgd
+    def _fit_psgd(self, X, y, rng, dev):
+        n, d = X.shape
+        k = self.n_components
+        group = _process_group()
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev)
+        self._h2d_bytes = ds.h2d_bytes
+        if self.learning_rate not in LEARNING_RATE:
+            raise ValueError(f"learning_rate {self.learning_rate} is not supported."
+                             f" Choose from {LEARNING_RATE}.")
+        learning_rate = LEARNING_RATE[self.learning_rate]
+        n_glob, nnz_glob = (global_sum([n, ds.nnz], group) if group is not None else (n, ds.nnz))
+        if self.batch_size == "auto":
+            batch_size = int(n_glob * d / nnz_glob)                          # :101-102
+        else:
+            batch_size = self.batch_size
+        batch_size = max(int(batch_size), 1)
+        indices_samples = np.arange(n, dtype=np.int32)
+        idx_dev = torch.from_numpy(indices_samples).to(dev)
+        y_dev = torch.from_numpy(y).to(dev)
+        P_kd = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)
+        P = torch.stack([solvers.transpose(P_kd[o]) for o in range(P_kd.shape[0])])   # [n_orders, d, k]
+        w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        grad_P = torch.zeros_like(P)
+        grad_w = torch.zeros(d, dtype=_f64, device=dev)
+        loss_dev = torch.zeros(1, dtype=_f64, device=dev)
+        work = solvers.prox_work(d, k, dev)
+
+        def sync():
+            for o in range(P.shape[0]):
+                self.P_[o] = solvers.transpose(P[o]).cpu().numpy()
+            self.w_[...] = w.cpu().numpy()
+
+        converged, epoch = False, 0
+        no_improvement_count, best_loss = 0, np.inf
+        for epoch in range(self.max_iter):
+            if self.shuffle:
+                rng.shuffle(indices_samples)
+                idx_dev.copy_(torch.from_numpy(indices_samples))
+            loss_dev.zero_()
+            self.it_ = solvers.psgd_epoch(ds, y_dev, P, w, lams, self.degree, self.alpha, self.beta,
+                                          self.gamma, self.regularizer, self.loss, grad_P, grad_w,
+                                          idx_dev, self.fit_linear, self.eta0, learning_rate,
+                                          self.power_t, batch_size, self.it_, loss_dev, work, group)
+            sum_loss = loss_dev.item()
+            if group is not None:
+                sum_loss = global_sum([sum_loss], group)[0]
+            sum_loss /= n_glob
+            if (self.callback is not None) and epoch % self.n_calls == 0:
+                sync()
+                if self.callback(self) is not None:
+                    break
+            if self.verbose:
+                print(f"Epoch {epoch+1} loss {sum_loss}")
+            if sum_loss > (best_loss - self.tol):
+                no_improvement_count += 1
+            else:
+                no_improvement_count = 0
+            if sum_loss < best_loss:
+                best_loss = sum_loss
+            if no_improvement_count >= self.n_iter_no_change:
+                if self.verbose:
+                    print(f"Converged at iteration {epoch+1}")
+                converged = True
+                break
+        sync()
+        return converged, epoch
+
+    # ---------------------------------------------------------------- public
+    def fit(self, X, y):
+        """Fit the factorization machine to (X, y) on the current CUDA device; returns self."""
+        X, y = self._check_X_y(X, y)
+        X = self._augment(X)
+        n_features = X.shape[1]
+        rng = check_random_state(self.random_state)
+        self._get_loss(self.loss)
+        self._get_regularizer(self.regularizer)
+        if self.solver not in ("pcd", "pbcd", "psgd"):
+            raise ValueError(f"Solver {self.solver} is not supported.")
+        self._check_combination(self.solver, self.regularizer, self.degree)
+        dev = _device()
+        _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+
+        if not (self.warm_start and hasattr(self, "w_")):
+            self.w_ = np.zeros(n_features, dtype=np.double)
+        n_orders = self.degree - 1 if self.fit_lower == "explicit" else 1
+        if not (self.warm_start and hasattr(self, "P_")):
+            self.P_ = 0.01 * rng.randn(n_orders, self.n_components, n_features)
+        self._init_lambdas(rng)
+        if np.unique(np.abs(self.lams_)) != np.array([1.0]):
+            raise ValueError("Lambdas must be +1 or -1.")
+
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if self.solver == "pcd":
+            converged, self.n_iter_ = self._fit_pcd(X, y, rng, dev)
+        elif self.solver == "pbcd":
+            converged, self.n_iter_ = self._fit_pbcd(X, y, rng, dev)
+        else:
+            if not (self.warm_start and hasattr(self, "it_")):
+                self.it_ = 1
+            converged, self.n_iter_ = self._fit_psgd(X, y, rng, dev)
+        if not converged:
+            warnings.warn("Objective did not converge. Increase max_iter.")
+        return self
+
+    def _get_output(self, X):
+        dev = _device()
+        _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev)
+        P = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)
+        w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        out = torch.zeros(ds.n_samples, dtype=_f64, device=dev)
+        self._device_output(ds, P, w, lams, out, 1)
+        return out.cpu().numpy()
+
+    def _predict(self, X):
+        if not hasattr(self, "P_"):
+            raise NotFittedError("Estimator not fitted.")
+        X = check_array(X, accept_sparse=["csr", "csc"], dtype=np.double)
+        X = self._augment(X)
+        return self._get_output(X)
+
+
+class SparseFactorizationMachineRegressor(_BaseSparseFactorizationMachine, SparsePolyRegressorMixin):
+    """Sparse factorization machine for regression (squared loss) on the B200 backend.
+
+    Parameters, defaults, fitted attributes and semantics are those of the reference class of the
+    same name (sparse_factorization_machines.py:461-685): degree-m ANOVA model
+    y(x) = <w,x> + sum_orders sum_s lams_s * A^deg(P_[order,s], x) minimising
+    sum_i loss + alpha/2 |w|^2 + beta/2 |P|^2 + gamma * Omega(P) with solver in
+    {'pcd','pbcd','psgd'} and regularizer in {'squaredl12','squaredl21','omegati','omegacs',
+    'l1','l21'}.  fit_lower in {'explicit','augment',None}; see the reference docstring for the
+    meaning of every knob -- they are unchanged.
+
+    Attributes: P_ [n_orders, n_components, n_features], w_ [n_features], lams_ [n_components],
+    n_iter_, it_ (psgd).
+    """
+    _LOSSES = REGRESSION_LOSSES
+
+    def __init__(self, degree=2, n_components=2, solver="pcd", regularizer="squaredl12", alpha=1,
+                 beta=1, gamma=1, mean=False, tol=1e-6, fit_lower="explicit", fit_linear=True,
+                 warm_start=False, init_lambdas="ones", max_iter=100, shuffle=False,
+                 batch_size="auto", eta0=1.0, learning_rate="optimal", power_t=1.0,
+                 n_iter_no_change=5, verbose=False, callback=None, n_calls=10, random_state=None):
+        super().__init__(degree, "squared", n_components, solver, regularizer, alpha, beta, gamma,
+                         mean, tol, fit_lower, fit_linear, warm_start, init_lambdas, max_iter,
+                         shuffle, batch_size, eta0, learning_rate, power_t, n_iter_no_change,
+                         verbose, callback, n_calls, random_state)
+
+
+class SparseFactorizationMachineClassifier(_BaseSparseFactorizationMachine, SparsePolyClassifierMixin):
+    """Sparse factorization machine for binary classification on the B200 backend.
+
+    Same surface as the reference class (sparse_factorization_machines.py:688-920);
+    loss in {'squared_hinge','logistic','squared'}; targets are binarised to {-1,+1}.
+    """
+    _LOSSES = CLASSIFICATION_LOSSES
+
+    def __init__(self, degree=2, loss="squared_hinge", n_components=2, solver="pcd",
+                 regularizer="squaredl12", alpha=1, beta=1, gamma=1, mean=False, tol=1e-6,
+                 fit_lower="explicit", fit_linear=True, warm_start=False, init_lambdas="ones",
+                 max_iter=100, shuffle=False, batch_size="auto", eta0=1.0, learning_rate="optimal",
+                 power_t=1.0, n_iter_no_change=5, verbose=False, callback=None, n_calls=10,
+                 random_state=None):
+        super().__init__(degree, loss, n_components, solver, regularizer, alpha, beta, gamma, mean,
+                         tol, fit_lower, fit_linear, warm_start, init_lambdas, max_iter, shuffle,
+                         batch_size, eta0, learning_rate, power_t, n_iter_no_change, verbose,
+                         callback, n_calls, random_state)
+
+
+# =============================================================================================
+# All-subsets models
+# =============================================================================================
+class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
+    _REGULARIZERS = ALL_SUBSETS_REGULARIZERS
+
+    @abstractmethod
+    def __init__(self, loss="squared", n_components=2, solver="pcd", beta=1, gamma=1, eta0=0.1,
+                 mean=False, tol=1e-6, regularizer="omegati", warm_start=False, init_lambdas="ones",
+                 max_iter=100, shuffle=False, verbose=False, callback=None, n_calls=10,
+                 random_state=None):
+        self.loss = loss
+        self.n_components = n_components
+        self.solver = solver
+        self.beta = beta
+        self.gamma = gamma
+        self.eta0 = eta0
+        self.mean = mean
+        self.tol = tol
+        self.regularizer = regularizer
+        self.warm_start = warm_start
+        self.init_lambdas = init_lambdas
+        self.max_iter = max_iter
+        self.shuffle = shuffle
+        self.verbose = verbose
+        self.callback = callback
+        self.n_calls = n_calls
+        self.random_state = random_state
+
+    def fit(self, X, y):
+        """Fit the all-subsets model to (X, y) on the current CUDA device; returns self."""
+        X, y = self._check_X_y(X, y)
+        n, d = X.shape
+        k = self.n_components
+        rng = check_random_state(self.random_state)
+        self._get_loss(self.loss)
+        self._get_regularizer(self.regularizer)
+        if self.solver not in ("pcd", "pbcd"):
+            raise ValueError(f"Solver {self.solver} is not supported.")
+        self._check_combination(self.solver, self.regularizer, -1)
+        dev = _device()
+        _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+        if not (self.warm_start and hasattr(self, "P_")):
+            self.P_ = 0.01 * rng.randn(k, d)
+        self._init_lambdas(rng)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        beta, gamma = (n * self.beta, n * self.gamma) if self.mean else (self.beta, self.gamma)
+
+        ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
+        self._h2d_bytes = ds.h2d_bytes
+        plan = SweepPlan(ds, self.solver)
+        indices_feature = np.arange(d, dtype=np.int32)
+        indices_component = np.arange(k, dtype=np.int32)
+        plan.set_order(indices_feature)
+        P_kd = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        regstate = torch.zeros(16, dtype=_f64, device=dev)
+        viol_dev = torch.zeros(1, dtype=_f64, device=dev)
+        pcd = self.solver == "pcd"
+        stride = solvers.rec_stride(-1) if pcd else 2
+        rec = torch.zeros(n * stride, dtype=_f64, device=dev)
+        rec[1::stride] = torch.from_numpy(y).to(dev)
+        P_dk = solvers.transpose(P_kd)
+        solvers.poly_predict(ds, P_dk, lams, -1, out=rec, out_stride=stride)     # _get_output
+        if not pcd:
+            A = torch.empty(max(n * k, 1), dtype=_f64, device=dev)
+            reg_norms = torch.zeros(max(d, 1), dtype=_f64, device=dev)
+
+        def sync():
+            if pcd:
+                self.P_[...] = P_kd.cpu().numpy()
+            else:
+                self.P_[...] = solvers.transpose(P_dk).cpu().numpy()
+
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol_dev.zero_()
+            if self.shuffle:
+                if pcd:
+                    rng.shuffle(indices_component)
+                rng.shuffle(indices_feature)
+                plan.set_order(indices_feature)
+            if pcd:
+                solvers.pcd_epoch(ds, plan, P_kd, lams, -1, beta, gamma, self.eta0, self.regularizer,
+                                  self.loss, rec, stride, regstate, viol_dev, indices_component)
+            else:
+                solvers.pbcd_epoch(ds, plan, P_dk, lams, -1, beta, gamma, self.eta0, self.regularizer,
+                                   self.loss, rec, A, reg_norms, regstate, viol_dev)
+            viol = viol_dev.item()
+            if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
+                break
+            if viol < self.tol:
+                if self.verbose:
+                    print(f"Converged at iteration {it+1}")
+                converged = True
+                break
+        sync()
+        self._y_pred_train = rec[0::stride]
+        self.n_iter_ = it
+        if not converged:
+            warnings.warn("Objective did not converge. Increase max_iter.")
+        return self
+
+    def _get_output(self, X):
+        dev = _device()
+        _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev)
+        P_dk = solvers.transpose(torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev))
+        lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
+        return solvers.poly_predict(ds, P_dk, lams, -1).cpu().numpy()
+
+    def _predict(self, X):
+        if not hasattr(self, "P_"):
+            raise NotFittedError("Estimator not fitted.")
+        X = check_array(X, accept_sparse=["csr", "csc"], dtype=np.double)
+        return self._get_output(X)
+
+
+class SparseAllSubsetsRegressor(_BaseSparseAllSubsets, SparsePolyRegressorMixin):
+    """Sparse all-subsets model y(x) = sum_s lams_s * prod_j (1 + P_[s,j] x_j) for regression.
+    Same surface as the reference class (sparse_all_subsets.py:266-391)."""
+    _LOSSES = REGRESSION_LOSSES
+
+    def __init__(self, n_components=2, solver="pcd", beta=1, gamma=1, eta0=0.1, mean=False, tol=1e-6,
+                 regularizer="omegati", warm_start=False, init_lambdas="ones", max_iter=100,
+                 shuffle=False, verbose=False, callback=None, n_calls=10, random_state=None):
+        super().__init__("squared", n_components, solver, beta, gamma, eta0, mean, tol, regularizer,
+                         warm_start, init_lambdas, max_iter, shuffle, verbose, callback, n_calls,
+                         random_state)
+
+
+class SparseAllSubsetsClassifier(_BaseSparseAllSubsets, SparsePolyClassifierMixin):
+    """Sparse all-subsets model for binary classification.
+    Same surface as the reference class (sparse_all_subsets.py:394-519)."""
+    _LOSSES = CLASSIFICATION_LOSSES
+
+    def __init__(self, loss="squared_hinge", n_components=2, solver="pcd", beta=1, gamma=1, eta0=0.1,
+                 mean=False, regularizer="omegati", tol=1e-6, warm_start=False, init_lambdas="ones",
+                 max_iter=100, shuffle=False, verbose=False, callback=None, n_calls=10,
+                 random_state=None):
+        super().__init__(loss, n_components, solver, beta, gamma, eta0, mean, tol, regularizer,
+                         warm_start, init_lambdas, max_iter, shuffle, verbose, callback, n_calls,
+                         random_state)

@@ -1,0 +1,105 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol the
+header declares, and the host logic (validation, sharding helpers) behaves.  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "sparsepoly_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sparsepoly_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert lib.sp_abi_version() == 1
+
+
+def test_get_eta_matches_oracle():
+    # psgd.py:9-22 (host scalar helper of the ABI; no GPU needed)
+    import ctypes as C
+    from oracle import oracle as O
+    from sparsepoly_b200 import solvers
+    for lr in range(4):
+        for it in (1, 7, 1000):
+            a, b = C.c_double(), C.c_double()
+            O.lib().sp_oracle_get_eta(lr, 0.3, 0.2, 0.7, 0.8, it, C.byref(a), C.byref(b))
+            assert solvers.get_eta(lr, 0.3, 0.2, 0.7, 0.8, it) == (a.value, b.value)
+
+
+def test_rec_stride():
+    from sparsepoly_b200 import solvers
+    assert [solvers.rec_stride(m) for m in (-1, 2, 3, 4, 5)] == [4, 4, 4, 8, 8]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sparsepoly_b200 as S
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.SparseFactorizationMachineRegressor().fit(np.random.randn(10, 3), np.random.randn(10))
+
+
+def test_validation_errors_before_device_work():
+    import sparsepoly_b200 as S
+    X, y = np.random.randn(12, 3), np.random.randn(12)
+    with pytest.raises(ValueError, match="Regularizer foo not supported"):
+        S.SparseFactorizationMachineRegressor(regularizer="foo").fit(X, y)
+    with pytest.raises(ValueError, match="Solver sgd is not supported"):
+        S.SparseFactorizationMachineRegressor(solver="sgd").fit(X, y)
+    with pytest.raises(ValueError, match="cannot be used with solver pcd"):
+        S.SparseFactorizationMachineRegressor(solver="pcd", regularizer="l21").fit(X, y)
+    with pytest.raises(ValueError, match="SquaredL12 supports only degree=2"):
+        S.SparseFactorizationMachineRegressor(degree=3, regularizer="squaredl12").fit(X, y)
+    with pytest.raises(ValueError, match="SquaredL21 supports only degree=2"):
+        S.SparseFactorizationMachineRegressor(degree=3, solver="pbcd", regularizer="squaredl21").fit(X, y)
+    with pytest.raises(ValueError, match="Loss function hinge not supported"):
+        S.SparseFactorizationMachineClassifier(loss="hinge").fit(X, np.sign(y))
+    with pytest.raises(TypeError, match="Only binary targets supported"):
+        S.SparseFactorizationMachineClassifier().fit(X, np.arange(12) % 3)
+    with pytest.raises(ValueError, match="not supported"):
+        S.SparseAllSubsetsRegressor(regularizer="squaredl12").fit(X, y)
+
+
+def test_public_surface_matches_reference_signatures():
+    import inspect
+    import sparsepoly_b200 as S
+    fm = inspect.signature(S.SparseFactorizationMachineClassifier.__init__).parameters
+    assert list(fm)[1:] == ["degree", "loss", "n_components", "solver", "regularizer", "alpha", "beta",
+                            "gamma", "mean", "tol", "fit_lower", "fit_linear", "warm_start",
+                            "init_lambdas", "max_iter", "shuffle", "batch_size", "eta0",
+                            "learning_rate", "power_t", "n_iter_no_change", "verbose", "callback",
+                            "n_calls", "random_state"]
+    assert fm["loss"].default == "squared_hinge" and fm["regularizer"].default == "squaredl12"
+    al = inspect.signature(S.SparseAllSubsetsRegressor.__init__).parameters
+    assert list(al)[1:] == ["n_components", "solver", "beta", "gamma", "eta0", "mean", "tol",
+                            "regularizer", "warm_start", "init_lambdas", "max_iter", "shuffle",
+                            "verbose", "callback", "n_calls", "random_state"]
+    assert al["eta0"].default == 0.1 and al["regularizer"].default == "omegati"
+    est = S.SparseFactorizationMachineRegressor(degree=3, gamma=0.5)
+    assert est.get_params()["degree"] == 3 and est.set_params(gamma=2).gamma == 2
+
+
+def test_local_batches_cover_reference_minibatches():
+    from sparsepoly_b200.distributed import interleave_shards, local_batches
+    n_local, world, B = 23, 2, 8
+    bs = list(local_batches(n_local, B, world))
+    assert bs[0] == (0, 4, 8) and bs[-1] == (20, 23, 6)
+    assert sum(b1 - b0 for b0, b1, _ in bs) == n_local
+    shards = [np.arange(0, 23), np.arange(100, 123)]
+    order = interleave_shards(shards, B)
+    assert order[:8].tolist() == [0, 1, 2, 3, 100, 101, 102, 103]
+    assert sorted(order.tolist()) == sorted(np.concatenate(shards).tolist())

@@ -1,0 +1,230 @@
+"""Parity of the CUDA backend (through the C ABI) against
+  (1) the golden outputs of the unmodified reference (tests/golden, every solver x regularizer
+      x loss x degree combination the reference tests cover, plus sparse inputs, shuffle,
+      explicit / augmented lower orders, warm start), and
+  (2) the pinned C oracle on larger seeded sparse problems, for several cluster geometries.
+Tolerance: 1e-9 relative on coefficients / predictions (north_star), identical support sets."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from golden_util import case_names, load_case, rel_err, same_support
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _estimator(rec):
+    import sparsepoly_b200 as S
+    if rec["model"] == "fm":
+        cls = S.SparseFactorizationMachineClassifier if rec["clf"] else S.SparseFactorizationMachineRegressor
+    else:
+        cls = S.SparseAllSubsetsClassifier if rec["clf"] else S.SparseAllSubsetsRegressor
+    return cls(**rec["kw"])
+
+
+def _fit(est, X, y, P_init=None):
+    if P_init is not None:
+        est.warm_start = True
+        est.P_ = P_init.copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        est.fit(X, y)
+    return est
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_matches_reference_golden(name):
+    rec, X, arr = load_case(name)
+    est = _fit(_estimator(rec), X, arr["y"], arr.get("P_init"))
+    assert rel_err(est.P_, arr["P_"]) <= TOL
+    assert same_support(est.P_, arr["P_"])
+    if "w_" in arr:
+        assert rel_err(est.w_, arr["w_"]) <= TOL
+    assert est.n_iter_ == int(arr["n_iter_"])
+    if "it_" in arr:
+        assert est.it_ == int(arr["it_"])
+    pred = est.decision_function(arr["Xte"]) if rec["clf"] else est.predict(arr["Xte"])
+    assert rel_err(pred, arr["pred_te"]) <= TOL
+
+
+@pytest.mark.parametrize("n_cta,threads", [(2, 32), (4, 64), (8, 32), (16, 32), (1, 256), (2, 128)])
+@pytest.mark.parametrize("name", ["pcd_fm_d3_omegati_logistic", "pcd_fm_sql12_squared",
+                                  "pcd_all_omegati_squared_hinge", "pbcd_fm_d3_omegacs_logistic",
+                                  "pbcd_fm_sql21", "pbcd_all_l21", "pcd_fm_d3_shuffle"])
+def test_cluster_geometries_match_golden(name, n_cta, threads, monkeypatch):
+    monkeypatch.setenv("SPARSEPOLY_B200_NCTA", str(n_cta))
+    monkeypatch.setenv("SPARSEPOLY_B200_THREADS", str(threads))
+    rec, X, arr = load_case(name)
+    est = _fit(_estimator(rec), X, arr["y"], arr.get("P_init"))
+    assert rel_err(est.P_, arr["P_"]) <= TOL
+    assert same_support(est.P_, arr["P_"])
+    if "w_" in arr:
+        assert rel_err(est.w_, arr["w_"]) <= TOL
+
+
+# ----------------------------------------------------------------------------- vs the C oracle
+def _problem(n, d, r, seed, kernel, degree, clf):
+    from sparsepoly_b200 import synth
+    from oracle import oracle as O
+    X = synth.uniform_sparse(n, d, r, seed)
+    Pt = synth.planted_P(d, 3, seed + 1, frac_features=0.3, scale=0.5)
+    if kernel == "anova":
+        s = O.poly_predict(X, Pt, np.ones(3), "anova", degree)
+    else:
+        s = O.poly_predict(X, 0.3 * Pt, np.ones(3), "all-subsets")
+    return X, synth.targets_from_scores(s, seed + 2, clf)
+
+
+def _compare_fm(kw, X, y, tol=TOL):
+    import sparsepoly_b200 as S
+    from oracle import oracle as O
+    clf = kw.get("loss", "squared") != "squared"
+    cls = S.SparseFactorizationMachineClassifier if clf else S.SparseFactorizationMachineRegressor
+    ekw = dict(kw)
+    if not clf:
+        ekw.pop("loss", None)
+    est = _fit(cls(**ekw), X, y)
+    okw = dict(kw)
+    okw.setdefault("loss", "squared")
+    out = O.fit_fm(X, y, **okw)
+    assert rel_err(est.P_, out["P_"]) <= tol
+    assert same_support(est.P_, out["P_"])
+    assert rel_err(est.w_, out["w_"]) <= tol
+    frac = float(np.mean(out["P_"] != 0))
+    return est, out, frac
+
+
+CASES_ORACLE = [
+    # scaled versions of the BASELINE configs (C1 full size; C2-C5 shrunk so the oracle takes seconds)
+    ("C1", dict(n=10000, d=1000, r=50, seed=0, kernel="anova", degree=2, clf=False),
+     dict(degree=2, n_components=10, solver="pcd", regularizer="squaredl12", beta=1e-3, gamma=1e-4,
+          alpha=1e-3, max_iter=3, tol=-1.0, random_state=0, mean=True)),
+    ("C2s", dict(n=20000, d=2000, r=50, seed=1, kernel="anova", degree=3, clf=True),
+     dict(degree=3, loss="logistic", n_components=8, solver="pcd", regularizer="omegati", beta=1e-4,
+          gamma=1e-5, alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True)),
+    ("C3s", dict(n=20000, d=2000, r=50, seed=2, kernel="anova", degree=2, clf=False),
+     dict(degree=2, n_components=32, solver="pbcd", regularizer="omegacs", beta=1e-4, gamma=1e-5,
+          alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True)),
+    ("C5s", dict(n=20000, d=5000, r=39, seed=4, kernel="anova", degree=2, clf=True),
+     dict(degree=2, loss="logistic", n_components=32, solver="psgd", regularizer="squaredl12",
+          alpha=1e-5, beta=1e-5, gamma=1e-4, max_iter=2, tol=-1.0, random_state=0, eta0=0.1,
+          n_iter_no_change=10 ** 9)),
+]
+
+
+@pytest.mark.parametrize("tag,prob,kw", CASES_ORACLE, ids=[c[0] for c in CASES_ORACLE])
+def test_scaled_baseline_configs_match_oracle(tag, prob, kw):
+    X, y = _problem(**prob)
+    tol = 1e-8 if tag == "C5s" else TOL   # psgd sums gradients with fp64 atomics (order-free)
+    est, out, frac = _compare_fm(kw, X, y, tol)
+    print(tag, "nonzero fraction of P_", frac)
+
+
+def test_all_subsets_c4_scaled_matches_oracle():
+    import sparsepoly_b200 as S
+    from oracle import oracle as O
+    X, y = _problem(n=20000, d=800, r=20, seed=3, kernel="all", degree=2, clf=True)
+    kw = dict(loss="squared_hinge", n_components=8, solver="pcd", regularizer="omegati", beta=1e-4,
+              gamma=1e-5, mean=True, max_iter=2, tol=-1.0, random_state=0)
+    est = _fit(S.SparseAllSubsetsClassifier(**kw), X, y)
+    out = O.fit_all_subsets(X, y, **kw)
+    assert rel_err(est.P_, out["P_"]) <= TOL
+    assert same_support(est.P_, out["P_"])
+
+
+def test_predict_matches_oracle_and_kernels_module():
+    from sparsepoly_b200 import kernels, synth
+    from oracle import oracle as O
+    X = synth.uniform_sparse(3000, 400, 30, 7)
+    rng = np.random.RandomState(0)
+    P = 0.3 * rng.randn(7, 400)
+    lams = np.sign(rng.randn(7))
+    for deg in (2, 3, 4, 5):
+        K = kernels.anova_kernel(X, P, deg)
+        Kd = O.kernel_rows_dp(X, np.ascontiguousarray(P.T), deg)
+        assert rel_err(K, Kd) <= 1e-13
+        assert rel_err(kernels.poly_predict(X, P, lams, "anova", deg),
+                       O.poly_predict(X, P, lams, "anova", deg)) <= 1e-9
+    assert rel_err(kernels.all_subsets_kernel(X, 0.2 * P), O.all_subsets_kernel(X, 0.2 * P)) <= 1e-13
+    # empty rows / empty matrix edge cases
+    Xe = sp.csr_matrix((5, 400))
+    assert np.array_equal(kernels.anova_kernel(Xe, P, 2), np.zeros((5, 7)))
+    assert np.array_equal(kernels.all_subsets_kernel(Xe, P), np.ones((5, 7)))
+
+
+def test_ragged_and_dense_columns():
+    """empty columns, one dense column (slice longer than a CTA: slow path), 1-sample data."""
+    import sparsepoly_b200 as S
+    from oracle import oracle as O
+    rng = np.random.RandomState(3)
+    n, d = 700, 9
+    M = sp.random(n, d, density=0.05, format="lil", random_state=rng, data_rvs=rng.randn)
+    M[:, 4] = rng.randn(n, 1)          # dense column
+    M[:, 2] = 0                        # empty column
+    X = sp.csr_matrix(M)
+    y = rng.randn(n)
+    for solver, reg in (("pcd", "l1"), ("pcd", "omegati"), ("pbcd", "omegacs"), ("pbcd", "l21")):
+        kw = dict(degree=3, n_components=3, solver=solver, regularizer=reg, beta=0.1, gamma=0.01,
+                  alpha=0.1, max_iter=3, tol=-1.0, random_state=1, fit_lower="explicit")
+        est = _fit(S.SparseFactorizationMachineRegressor(**kw), X, y)
+        out = O.fit_fm(X, y, loss="squared", **kw)
+        assert rel_err(est.P_, out["P_"]) <= TOL, (solver, reg)
+        assert rel_err(est.w_, out["w_"]) <= TOL
+        assert same_support(est.P_, out["P_"])
+
+
+def test_prox_operators_match_reference_vectors():
+    import torch
+    from golden_util import GOLD
+    from sparsepoly_b200 import solvers
+    z = np.load(os.path.join(GOLD, "reference_prox.npz"))
+    for reg in ("l1", "l21", "squaredl12", "squaredl21"):
+        for t in range(4):
+            P = torch.from_numpy(np.ascontiguousarray(z[f"in_{t}"])).cuda()
+            work = solvers.prox_work(P.shape[0], P.shape[1], P.device)
+            solvers.prox(P, reg, float(z[f"strength_{t}"]), work)
+            got, want = P.cpu().numpy(), z[f"{reg}_{t}"]
+            assert rel_err(got, want) <= 1e-12, (reg, t)
+            assert np.array_equal(got != 0, want != 0), (reg, t)
+
+
+def test_squaredl12_prox_large_columns_vs_oracle():
+    """prox over d=200k rows x 32 columns (C5-shaped column length / 5): same theta, S."""
+    import torch
+    from oracle import oracle as O
+    from sparsepoly_b200 import solvers
+    rng = np.random.RandomState(11)
+    P = rng.randn(200000, 32) * (rng.rand(200000, 32) < 0.3)
+    for strength in (1e-6, 1e-4):
+        Pd = torch.from_numpy(P.copy()).cuda()
+        solvers.prox(Pd, "squaredl12", strength, solvers.prox_work(*P.shape, Pd.device))
+        Q = P.copy()
+        O.Reg("squaredl12", *P.shape).prox(Q, strength)
+        got = Pd.cpu().numpy()
+        assert rel_err(got, Q) <= 1e-12
+        assert np.array_equal(got != 0, Q != 0)
+        assert np.all(np.abs(got) <= np.abs(P))          # magnitudes never grow (test_prox.py:70-76)
+
+
+def test_callback_verbose_and_warm_start(capsys):
+    import sparsepoly_b200 as S
+    rec, X, arr = load_case("pcd_fm_sql12_squared")
+    seen = []
+    kw = dict(rec["kw"], max_iter=3, verbose=True, n_calls=1,
+              callback=lambda est: seen.append(est.P_.copy()) or None)
+    est = _fit(S.SparseFactorizationMachineRegressor(**kw), X, arr["y"])
+    out = capsys.readouterr().out
+    assert "Iteration 1 violation sum" in out and len(seen) == 3
+    assert np.array_equal(seen[-1], est.P_)
+    # warm start continues from the stored solution
+    est.set_params(warm_start=True, max_iter=1, callback=None, verbose=False)
+    P_before = est.P_.copy()
+    _fit(est, X, arr["y"])
+    assert not np.array_equal(P_before, est.P_)
+    with pytest.raises(Exception):
+        S.SparseFactorizationMachineRegressor().predict(X)
