@@ -68,6 +68,12 @@ int sp_device_count(int *count_host);
 /* make `device` current for this thread's subsequent calls (cudaSetDevice) */
 int sp_set_device(int device);
 
+/* Per-kernel-class CUDA-event timing (bench instrumentation).  Classes: 0 row DP kernels,
+ * 1 regularizer caches, 2 pcd/linear sweeps, 3 pbcd sweeps, 4 psgd gradient, 5 psgd dense step,
+ * 6 prox, 7 plan.  collect() synchronises and returns accumulated ms / launches since enable. */
+int sp_profile_enable(int on);
+int sp_profile_collect(double *ms_host /*[8]*/, long long *launches_host /*[8]*/);
+
 /* ------------------------------------------------------------------ dataset / plan helpers */
 /* out[j] = sum_i x_ij^2   (row_norms(X.T, squared=True), sparse_factorization_machines.py:409) */
 int sp_col_norm_sq(const sp_dataset *ds, double *out, sp_stream stream);

@@ -42,6 +42,8 @@ SIGNATURES = {
     "sp_last_error": (C.c_char_p, []),
     "sp_device_count": (_i, [C.POINTER(C.c_int)]),
     "sp_set_device": (_i, [_i]),
+    "sp_profile_enable": (_i, [_i]),
+    "sp_profile_collect": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "sp_col_norm_sq": (_i, [_DSP, _vp, _vp]),
     "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
     "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp]),

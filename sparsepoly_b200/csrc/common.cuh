@@ -15,6 +15,13 @@ enum { SP_REG_L1 = 0, SP_REG_L21 = 1, SP_REG_SQL12 = 2, SP_REG_SQL21 = 3, SP_REG
 
 enum { SP_OK = 0, SP_ERR_INVALID = 1, SP_ERR_UNSUPPORTED = 2, SP_ERR_CUDA = 3 };
 
+// kernel classes for sp_profile_* (see errors.cu)
+enum { SP_PROF_ROWS = 0, SP_PROF_REGCACHE = 1, SP_PROF_SWEEP_PCD = 2, SP_PROF_SWEEP_PBCD = 3,
+       SP_PROF_PSGD_GRAD = 4, SP_PROF_PSGD_STEP = 5, SP_PROF_PROX = 6, SP_PROF_PLAN = 7,
+       SP_PROF_CLASSES = 8 };
+void sp_prof_begin(int cls, cudaStream_t st);
+void sp_prof_end(cudaStream_t st);
+
 void sp_set_error(const char *fmt, ...);
 int sp_check_cuda(cudaError_t e, const char *what);
 

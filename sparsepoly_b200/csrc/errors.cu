@@ -30,3 +30,49 @@ extern "C" int sp_device_count(int *count_host) {
 extern "C" int sp_set_device(int device) {
     return sp_check_cuda(cudaSetDevice(device), "cudaSetDevice");
 }
+
+// ------------------------------------------------------------------------------------------
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's
+// roofline numbers).  Off by default; when on, every launch site brackets its kernel with an
+// event pair.  sp_profile_collect() synchronises the events and returns ms / launches per class.
+#include <vector>
+static bool g_prof_on = false;
+struct ProfPair { cudaEvent_t a, b; int cls; };
+static std::vector<ProfPair> g_prof_pairs;
+static double g_prof_ms[SP_PROF_CLASSES];
+static long long g_prof_n[SP_PROF_CLASSES];
+
+void sp_prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfPair p; p.cls = cls;
+    cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, st);
+    g_prof_pairs.push_back(p);
+}
+void sp_prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_pairs.empty()) return;
+    cudaEventRecord(g_prof_pairs.back().b, st);
+}
+extern "C" int sp_profile_enable(int on) {
+    g_prof_on = on != 0;
+    for (int c = 0; c < SP_PROF_CLASSES; c++) { g_prof_ms[c] = 0.0; g_prof_n[c] = 0; }
+    for (auto &p : g_prof_pairs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    g_prof_pairs.clear();
+    return SP_OK;
+}
+extern "C" int sp_profile_collect(double *ms_host, long long *launches_host) {
+    for (auto &p : g_prof_pairs) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(p.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, p.a, p.b);
+        if (e != cudaSuccess) return sp_check_cuda(e, "sp_profile_collect");
+        g_prof_ms[p.cls] += ms; g_prof_n[p.cls] += 1;
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    g_prof_pairs.clear();
+    for (int c = 0; c < SP_PROF_CLASSES; c++) {
+        if (ms_host) ms_host[c] = g_prof_ms[c];
+        if (launches_host) launches_host[c] = g_prof_n[c];
+    }
+    return SP_OK;
+}

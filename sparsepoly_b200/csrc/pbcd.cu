@@ -496,7 +496,10 @@ int launch_block(const BlockArgs &a, int threads, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return sp_check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "pbcd_sweep_kernel launch");
+    sp_prof_begin(SP_PROF_SWEEP_PBCD, st);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+    sp_prof_end(st);
+    return sp_check_cuda(le, "pbcd_sweep_kernel launch");
 }
 
 template <int KIND, int DEG>
@@ -546,7 +549,9 @@ extern "C" int sp_pbcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *
     if (rc) return rc;
     if (reg == SP_REG_SQL21 || reg == SP_REG_OMEGACS) {                         // pbcd.py:109
         int blocks = (d + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+        sp_prof_begin(SP_PROF_REGCACHE, st);
         row_norms_kernel<<<blocks, 256, 0, st>>>(d, k, P_dk, reg_norms);
+        sp_prof_end(st);
         SP_LAUNCH_CHECK("row_norms_kernel");
         const int mode = (reg == SP_REG_SQL21) ? 0 : (degree == -1 ? 2 : 1);
         rc = sp_launch_reg_cache(mode, degree, d, reg_norms, regstate, st);

@@ -315,7 +315,10 @@ int launch_sweep(const SweepArgs &a, int threads, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return sp_check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "sweep_kernel launch");
+    sp_prof_begin(SP_PROF_SWEEP_PCD, st);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+    sp_prof_end(st);
+    return sp_check_cuda(le, "sweep_kernel launch");
 }
 
 template <int KIND, int DEG>

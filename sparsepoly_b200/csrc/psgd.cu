@@ -369,12 +369,14 @@ static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, cons
 #define SP_GRAD(GG, KC)                                                                           \
     psgd_grad_kernel<DEG, NORD, GG, KC><<<(int)blocks, PG_THREADS, 0, st>>>(k, d, ds->csr_indptr, \
         ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls)
+    sp_prof_begin(SP_PROF_PSGD_GRAD, st);
     if (k <= 16) SP_GRAD(16, 1);
     else if (k <= 32) SP_GRAD(32, 1);
     else if (k <= 64) SP_GRAD(32, 2);
     else if (k <= 128) SP_GRAD(32, 4);
     else { sp_set_error("psgd: n_components=%d > 128 is not supported by the CUDA backend", k); return SP_ERR_UNSUPPORTED; }
 #undef SP_GRAD
+    sp_prof_end(st);
     SP_LAUNCH_CHECK("psgd_grad_kernel");
     return SP_OK;
 }
@@ -420,6 +422,7 @@ extern "C" int sp_psgd_step(double *P_odk, double *grad_P, double *w, double *gr
         return SP_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    sp_prof_begin(SP_PROF_PSGD_STEP, st);
     if (fit_linear && d > 0) {                                      // psgd.py:109-112
         psgd_step_kernel<<<ew_blocks((size_t)d / 2 + 1), 256, 0, st>>>(w, grad_w, (size_t)d, eta_w / batch,
                                                                         1 + eta_w * alpha);
@@ -431,6 +434,7 @@ extern "C" int sp_psgd_step(double *P_odk, double *grad_P, double *w, double *gr
                                                                 1.0 + eta_P * beta);
         SP_LAUNCH_CHECK("psgd_step_kernel(P)");
     }
+    sp_prof_end(st);
     return SP_OK;
 }
 
@@ -440,6 +444,7 @@ extern "C" int sp_prox(double *P_dk, int d, int k, int reg, double strength, dou
     if (d == 0) return SP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)d * k;
+    struct ProfScope { cudaStream_t s; ProfScope(cudaStream_t s_) : s(s_) { sp_prof_begin(SP_PROF_PROX, s); } ~ProfScope() { sp_prof_end(s); } } prof_scope(st);
     switch (reg) {
     case SP_REG_L1:
         prox_l1_kernel<<<ew_blocks(n), 256, 0, st>>>(P_dk, n, strength);

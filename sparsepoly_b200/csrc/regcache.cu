@@ -58,7 +58,9 @@ int sp_launch_reg_cache(int mode, int degree, int d, const double *v, double *re
         sp_set_error("regularizer cache: degree %d unsupported", degree);
         return SP_ERR_UNSUPPORTED;
     }
+    sp_prof_begin(SP_PROF_REGCACHE, st);
     reg_cache_kernel<<<1, RC_THREADS, 0, st>>>(mode, degree, d, v, regstate);
+    sp_prof_end(st);
     SP_LAUNCH_CHECK("reg_cache_kernel");
     return SP_OK;
 }

@@ -175,6 +175,7 @@ template <int DEG, int MODE, bool PX>
 int launch_all(int n, int k, const int32_t *indptr, const int32_t *indices, const double *data,
                const double *P_dk, const double *lams, const double *w, double *out, int out_stride,
                int accumulate, double *Aout, cudaStream_t st) {
+    sp_prof_begin(SP_PROF_ROWS, st);
     if (k <= 8) {
         rows_all_kernel<DEG, 8, MODE, PX><<<grid_for(n, ROWS_THREADS / 8), ROWS_THREADS, 0, st>>>(
             n, k, indptr, indices, data, P_dk, lams, w, out, out_stride, accumulate, Aout);
@@ -185,6 +186,7 @@ int launch_all(int n, int k, const int32_t *indptr, const int32_t *indices, cons
         rows_all_kernel<DEG, 32, MODE, PX><<<grid_for(n, ROWS_THREADS / 32), ROWS_THREADS, 0, st>>>(
             n, k, indptr, indices, data, P_dk, lams, w, out, out_stride, accumulate, Aout);
     }
+    sp_prof_end(st);
     SP_LAUNCH_CHECK("rows_all_kernel");
     return SP_OK;
 }
@@ -250,6 +252,7 @@ int sp_rows_precompute_one(const sp_dataset *ds, const double *p_s, int degree, 
 #define SP_ONE(D)                                                                                \
     rows_one_kernel<D><<<grid, ROWS_THREADS, 0, st>>>(n, ds->csr_indptr, ds->csr_indices,        \
                                                       ds->csr_data, p_s, rec, rec_stride)
+    sp_prof_begin(SP_PROF_ROWS, st);
     switch (degree) {
     case -1: SP_ONE(-1); break;
     case 2: SP_ONE(2); break;
@@ -261,6 +264,7 @@ int sp_rows_precompute_one(const sp_dataset *ds, const double *p_s, int degree, 
         return SP_ERR_UNSUPPORTED;
     }
 #undef SP_ONE
+    sp_prof_end(st);
     SP_LAUNCH_CHECK("rows_one_kernel");
     return SP_OK;
 }

@@ -221,13 +221,16 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         return out
 
     # ---------------------------------------------------------------- pcd
-    def _fit_pcd(self, X, y, rng, dev):
+    def _pcd_setup(self, X, y, rng, dev):
+        """Move everything to the device and return (epoch, sync): epoch() runs one iteration of
+        the reference driver loop (linear CD -> lower orders ascending -> top order,
+        sparse_factorization_machines.py:196-243) and returns the violation sum."""
         n, d = X.shape
         k, m = self.n_components, self.degree
         alpha, beta, gamma = self._scaled(n)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
         plan = SweepPlan(ds, "pcd")
-        self._h2d_bytes = ds.h2d_bytes
+        self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         indices_feature = np.arange(d, dtype=np.int32)
         indices_component = np.arange(k, dtype=np.int32)
         plan.set_order(indices_feature)
@@ -241,13 +244,13 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         col_norm_sq = ds.col_norm_sq()
         regstate = torch.zeros(16, dtype=_f64, device=dev)
         viol_dev = torch.zeros(1, dtype=_f64, device=dev)
+        self._dev_state = dict(ds=ds, plan=plan, rec=rec, stride=stride, P=P, w=w)
 
         def sync():
             self.P_[...] = P.cpu().numpy()
             self.w_[...] = w.cpu().numpy()
 
-        converged, it = False, 0
-        for it in range(self.max_iter):
+        def epoch(read_back=True):
             viol_dev.zero_()
             if self.shuffle:
                 rng.shuffle(indices_component)
@@ -262,7 +265,15 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                                       indices_component)
             solvers.pcd_epoch(ds, plan, P[0], lams, m, beta, gamma, self.eta0, self.regularizer,
                               self.loss, rec, stride, regstate, viol_dev, indices_component)
-            viol = viol_dev.item()
+            return viol_dev.item() if read_back else None
+
+        return epoch, sync
+
+    def _fit_pcd(self, X, y, rng, dev):
+        epoch, sync = self._pcd_setup(X, y, rng, dev)
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol = epoch()
             if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
                 break
             if viol < self.tol:
@@ -271,18 +282,18 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                 converged = True
                 break
         sync()
-        self._y_pred_train = rec[0::stride]
         return converged, it
 
     # ---------------------------------------------------------------- pbcd
-    def _fit_pbcd(self, X, y, rng, dev):
+    def _pbcd_setup(self, X, y, rng, dev):
+        """As _pcd_setup for the block solver (sparse_factorization_machines.py:260-337)."""
         n, d = X.shape
         k, m = self.n_components, self.degree
         alpha, beta, gamma = self._scaled(n)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
         plan = SweepPlan(ds, "pbcd")
         plan_lin = SweepPlan(ds, "pcd") if self.fit_linear else None
-        self._h2d_bytes = ds.h2d_bytes
+        self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         indices_feature = np.arange(d, dtype=np.int32)
         plan.set_order(indices_feature)
         if plan_lin is not None:
@@ -300,14 +311,14 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         reg_norms = torch.zeros(max(d, 1), dtype=_f64, device=dev)
         regstate = torch.zeros(16, dtype=_f64, device=dev)
         viol_dev = torch.zeros(1, dtype=_f64, device=dev)
+        self._dev_state = dict(ds=ds, plan=plan, rec=yrec, stride=2, P=P, w=w)
 
         def sync():
             for o in range(P.shape[0]):
                 self.P_[o] = solvers.transpose(P[o]).cpu().numpy()
             self.w_[...] = w.cpu().numpy()
 
-        converged, it = False, 0
-        for it in range(self.max_iter):
+        def epoch(read_back=True):
             viol_dev.zero_()
             if self.shuffle:
                 rng.shuffle(indices_feature)
@@ -322,7 +333,15 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                                        self.regularizer, self.loss, yrec, A, reg_norms, regstate, viol_dev)
             solvers.pbcd_epoch(ds, plan, P[0], lams, m, beta, gamma, self.eta0, self.regularizer,
                                self.loss, yrec, A, reg_norms, regstate, viol_dev)
-            viol = viol_dev.item()
+            return viol_dev.item() if read_back else None
+
+        return epoch, sync
+
+    def _fit_pbcd(self, X, y, rng, dev):
+        epoch, sync = self._pbcd_setup(X, y, rng, dev)
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol = epoch()
             if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
                 break
             if viol < self.tol:
@@ -331,7 +350,6 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                 converged = True
                 break
         sync()
-        self._y_pred_train = yrec[0::2]
         return converged, it
 
     # ---------------------------------------------------------------- psgd
