@@ -114,12 +114,15 @@ def dist_env():
     return rank, world, local
 
 
+ROWS_OVERRIDE = 0
+
+
 def make_problem(name, scale=1.0, rank=0):
     """Synthetic inputs of the named config (host numpy / scipy)."""
     from sparsepoly_b200 import synth
     wl = WORKLOADS[name]
     if name == "psgd":
-        n = max(1024, int(wl["n_per_gpu"] * scale))
+        n = max(1024, int((ROWS_OVERRIDE or wl["n_per_gpu"]) * scale))
         d = max(64, int(wl["d"] * scale))
         X = synth.criteo_like(n, d, wl["seed"] * 1000 + rank)
         rng = np.random.RandomState(99 + rank)
@@ -573,8 +576,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink n and d (debug only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rows-per-gpu", type=int, default=0, help="psgd: override the shard size (debug)")
     args = ap.parse_args()
     rank, world, local = dist_env()
+    global ROWS_OVERRIDE
+    ROWS_OVERRIDE = args.rows_per_gpu
     if args.workload == "auto":
         args.workload = "pcd" if max(world, args.gpus) == 1 else "psgd"
     if args.workload == "psgd" and args.steps == 3 and args.warmup == 3:
