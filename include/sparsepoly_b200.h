@@ -58,8 +58,10 @@ typedef struct sp_plan {
     int32_t threads;          /* threads per CTA, multiple of 32, 32..256 */
     const int32_t *pos_ptr;   /* [d*(n_cta+1)] CSC offsets of the per-CTA slices, by position */
     const int32_t *flag_idx;  /* [nnz] CSC row index | 0x80000000 when the sample also occurs in
-                                 the column visited at the previous position */
+                                 the column visited at the previous position, | 0x40000000 when
+                                 it occurs in the one before that */
     const int32_t *idx_feat;  /* [d] coordinate order (indices_feature in the reference) */
+    const int32_t *pos_conf;  /* [d] 1 when the columns at positions t-1 and t share a sample */
 } sp_plan;
 
 int sp_abi_version(void);
@@ -81,7 +83,7 @@ int sp_col_norm_sq(const sp_dataset *ds, double *out, sp_stream stream);
 int sp_plan_partition(const sp_dataset *ds, int n_cta, int32_t *col_part, sp_stream stream);
 /* position table + hazard flags for the order idx_feat (call again after every shuffle) */
 int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part, const int32_t *idx_feat,
-                  int32_t *pos_ptr, int32_t *flag_idx, sp_stream stream);
+                  int32_t *pos_ptr, int32_t *flag_idx, int32_t *pos_conf, sp_stream stream);
 /* out[c*rows+r] = in[r*cols+c] */
 int sp_transpose_f64(const double *in, double *out, int rows, int cols, sp_stream stream);
 /* doubles per sample record {y_pred, y, A^1..A^(m-1)} for a model of this top degree */

@@ -30,7 +30,7 @@ class SpDataset(C.Structure):
 class SpPlan(C.Structure):
     """struct sp_plan (include/sparsepoly_b200.h)."""
     _fields_ = [("n_cta", C.c_int32), ("threads", C.c_int32), ("pos_ptr", _vp), ("flag_idx", _vp),
-                ("idx_feat", _vp)]
+                ("idx_feat", _vp), ("pos_conf", _vp)]
 
 
 _DSP = C.POINTER(SpDataset)
@@ -46,7 +46,7 @@ SIGNATURES = {
     "sp_profile_collect": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "sp_col_norm_sq": (_i, [_DSP, _vp, _vp]),
     "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
-    "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sp_transpose_f64": (_i, [_vp, _vp, _i, _i, _vp]),
     "sp_rec_stride": (_i, [_i]),
     "sp_predict": (_i, [_DSP, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),

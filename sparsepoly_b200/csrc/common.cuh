@@ -7,7 +7,9 @@
 #include <stdio.h>
 
 #define SP_MAXDEG 5           // highest ANOVA degree with a compiled sweep kernel
-#define SP_FLAG_BIT 0x80000000u
+#define SP_FLAG_BIT 0x80000000u    // sample also occurs at position t-1
+#define SP_FLAG2_BIT 0x40000000u   // sample also occurs at position t-2
+#define SP_ROW_MASK 0x3fffffff
 
 enum { SP_LOSS_SQUARED = 0, SP_LOSS_LOGISTIC = 1, SP_LOSS_SQHINGE = 2 };
 enum { SP_REG_L1 = 0, SP_REG_L21 = 1, SP_REG_SQL12 = 2, SP_REG_SQL21 = 3, SP_REG_OMEGATI = 4,

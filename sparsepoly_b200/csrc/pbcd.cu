@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(PB_MAX_THREADS) pbcd_sweep_kernel(const BlockA
             double x_l = 0.0;
             if (ql < nq) {
                 const int e = s0 + warp + W * ql;
-                idx_l = a.flag_idx[e] & 0x7fffffff;
+                idx_l = a.flag_idx[e] & SP_ROW_MASK;
                 x_l = a.data[e];
             }
             const int nloc = min(32, nq - qb);
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(PB_MAX_THREADS) pbcd_sweep_kernel(const BlockA
                 double x_l = 0.0;
                 if (ql < nq) {
                     const int e = s0 + warp + W * ql;
-                    idx_l = a.flag_idx[e] & 0x7fffffff;
+                    idx_l = a.flag_idx[e] & SP_ROW_MASK;
                     x_l = a.data[e];
                 }
                 const int nloc = min(32, nq - qb);

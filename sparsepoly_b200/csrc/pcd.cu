@@ -3,19 +3,22 @@
 //   * pcd.pcd_epoch  (_update + synchronize loop)    (reference optimizer/pcd.py:33-137)
 //   * pcd_all.pcd_epoch                              (reference optimizer/pcd_all.py:21-102)
 //
-// Design (see DESIGN.md "pcd sweep"):  coordinate order is a true dependency chain, so a sweep
-// is latency-bound, not bandwidth-bound.  One cluster of C CTAs walks the d coordinates in order.
-// Samples are range-partitioned over the CTAs (CTA c owns rows [c*chunk,(c+1)*chunk)), so a
-// sample's record {y_pred, y, A^1..A^{m-1}} is only ever touched by one SM: no inter-SM memory
-// hazards, only an all-to-all exchange of the per-CTA partial sums (g_c, h_c) through
-// distributed shared memory (st.async + mbarrier complete_tx), one hop (~DSMEM latency) per
-// coordinate.  Every thread then runs the ~20-flop scalar chain (step, prox, regularizer
-// cache) redundantly, so no broadcast is needed.  Column slices, records and P entries of the
-// next positions are software-pipelined through registers (distance 1-3 positions); records
-// of samples that the previous position is still rewriting are tagged by the plan
-// (SP_FLAG_BIT in flag_idx) and re-read after the end-of-step barrier.
-#include <stdarg.h>
-
+// Design.  Coordinate order is a true dependency chain, so a sweep is bound by the
+// latency of one coordinate step, not by bandwidth.  One cluster of C CTAs walks the d coordinates
+// of one component in order:
+//   * samples are range-partitioned over the CTAs, so a sample's record {y_pred, y, A^1..A^{m-1}}
+//     is only ever touched by one SM; the only inter-SM traffic is the all-to-all exchange of the
+//     per-warp partial sums (g, h) through distributed shared memory (st.async + mbarrier
+//     complete_tx, 4-deep mailboxes);
+//   * every thread runs the ~20-flop scalar chain (step, prox_cd, regularizer cache) redundantly;
+//   * column slices and records of the coming positions are staged through shared memory with
+//     cp.async (no scoreboard coupling with the step's own loads); the per-position table lives in
+//     registers, 32 positions per warp, broadcast by shuffles;
+//   * the partial sums of position t+1 are computed and pushed BEFORE the scalar chain of position
+//     t whenever the plan marks the two columns sample-disjoint (pos_conf == 0), which hides the
+//     DSMEM hop behind the scalar chain; otherwise they are recomputed after the write-back;
+//   * records the previous two positions may still be rewriting are tagged by the plan (bits
+//     31/30 of flag_idx) and re-read from global memory after the barrier.
 #include "common.cuh"
 #include "cluster.cuh"
 #include "sparsepoly_b200.h"
@@ -29,6 +32,7 @@ namespace {
 enum { KIND_LINEAR = 0, KIND_FM = 1, KIND_ALL = 2 };
 constexpr int SWEEP_MAX_THREADS = 256;
 constexpr int SWEEP_MAX_CTAS = 16;
+constexpr int MBOX_DEPTH = 4;
 
 struct SweepArgs {
     int d, C;
@@ -36,6 +40,7 @@ struct SweepArgs {
     const int32_t *flag_idx;   // [nnz]
     const double *data;        // [nnz] CSC values
     const int32_t *idx_feat;   // [d]
+    const int32_t *pos_conf;   // [d]
     double *prow;              // P[s, :] (or w)
     const double *cns;         // col_norm_sq (linear only)
     const double *lam_ptr;     // &lams[s] (FM / all-subsets)
@@ -48,7 +53,18 @@ struct SweepArgs {
     double *viol;              // in/out running sum of |updates|
 };
 
-// ------------------------------------------------------------------------- record access
+__device__ __forceinline__ void cp_async4(void *smem, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int R> __device__ __forceinline__ void load_rec(const double *p, double (&r)[R]) {
     const double2 *q = reinterpret_cast<const double2 *>(p);
 #pragma unroll
@@ -56,12 +72,13 @@ template <int R> __device__ __forceinline__ void load_rec(const double *p, doubl
     if (R & 1) r[R - 1] = p[R - 1];
 }
 
-// per-nonzero gradient terms.  r = {y_pred, y, A^1.. }.  dA[] keeps the chain for the scatter.
+// per-nonzero gradient terms.  r = {y_pred, y, A^1.. }.  dA[] keeps the chain for the write-back.
 template <int KIND, int DEG, int LOSS, int R, int ND>
 __device__ __forceinline__ void nz_terms(const double (&r)[R], double x, double pold, double (&dA)[ND],
                                          double &tg, double &th) {
     const double dl = sp_dloss<LOSS>(r[0], r[1]);
     if (KIND == KIND_LINEAR) {
+        dA[0] = x;
         tg += dl * x;                                        // cd_linear.py:18
     } else if (KIND == KIND_FM) {
         dA[0] = x;                                           // pcd.py:8-12
@@ -78,7 +95,7 @@ __device__ __forceinline__ void nz_terms(const double (&r)[R], double x, double 
 
 // write-back of one sample after the coordinate moved by upd = p_old - p_new
 template <int KIND, int DEG, int R, int ND>
-__device__ __forceinline__ void nz_scatter(double *p, double (&r)[R], const double (&dA)[ND], double x,
+__device__ __forceinline__ void nz_scatter(double *p, const double (&r)[R], const double (&dA)[ND], double x,
                                            double lam, double upd, double pold, double pnew) {
     if (KIND == KIND_LINEAR) {
         p[0] = r[0] - upd * x;                               // cd_linear.py:31
@@ -96,108 +113,236 @@ __device__ __forceinline__ void nz_scatter(double *p, double (&r)[R], const doub
     }
 }
 
-template <int KIND, int DEG, int LOSS>
+// 32 positions of the per-position table, one per lane
+struct MetaChunk {
+    int s, e, jf;        // slice [s,e) of this CTA, feature id | conflict << 31
+    double pold, cn;     // P[s_comp, j] (or w_j), col_norm_sq[j]
+};
+
+__device__ __forceinline__ void meta_load_ptr(MetaChunk &m, const SweepArgs &a, int base, int c, int lane) {
+    const int q = base + lane;
+    m.s = 0; m.e = 0; m.jf = 0;
+    if (q < a.d) {
+        m.s = a.pos_ptr[(size_t)q * (a.C + 1) + c];
+        m.e = a.pos_ptr[(size_t)q * (a.C + 1) + c + 1];
+        m.jf = a.idx_feat[q] | (a.pos_conf[q] ? (int)SP_FLAG_BIT : 0);
+    }
+}
+template <int KIND>
+__device__ __forceinline__ void meta_load_val(MetaChunk &m, const SweepArgs &a, int base, int lane) {
+    m.pold = 0.0; m.cn = 0.0;
+    if (base + lane < a.d) {
+        const int j = m.jf & 0x7fffffff;
+        m.pold = a.prow[j];
+        if (KIND == KIND_LINEAR) m.cn = a.cns[j];
+    }
+}
+
+template <int KIND, int DEG, int LOSS, int NZ>
 __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArgs a) {
     constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
-    constexpr int R = 2 + NA;
+    constexpr int R = 2 + NA;                                // doubles used per record
+    constexpr int NCH = (R + 1) / 2;                         // 16-byte chunks staged per record
     constexpr int ND = (KIND == KIND_FM) ? DEG : 1;
     constexpr int NC = (KIND == KIND_FM) ? DEG : 1;          // regularizer cache scalars
 
-    __shared__ double2 red[SWEEP_MAX_THREADS / 32];
-    __shared__ __align__(16) double2 mbox[2][SWEEP_MAX_CTAS];
-    __shared__ __align__(8) unsigned long long mbar[2];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[MBOX_DEPTH];
 
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
-    const int C = a.C, PS = C + 1, d = a.d;
+    const int C = a.C, d = a.d;
     const int c = (C > 1) ? (int)cluster_ctarank() : 0;
+    const int NP = C * W;                                    // partials per position
     const int stride = a.stride;
     const double mu = sp_mu<LOSS>();
     const double lam = (KIND == KIND_LINEAR) ? 1.0 : *a.lam_ptr;
     const double ab = a.ab, gamma = a.gamma, eta = a.eta;
     const int reg = a.reg;
 
+    // dynamic smem carve-up
+    double2 *recbuf = reinterpret_cast<double2 *>(smem_raw);                 // [2][NZ][NCH][T]
+    double *xbuf = reinterpret_cast<double *>(recbuf + (size_t)2 * NZ * NCH * T);   // [3][NZ][T]
+    double2 *mbox = reinterpret_cast<double2 *>(xbuf + (size_t)3 * NZ * T);  // [MBOX_DEPTH][NP]
+    int *idxbuf = reinterpret_cast<int *>(mbox + (size_t)MBOX_DEPTH * NP);   // [3][NZ][T]
+
     double viol = *a.viol;
     double cache[NC];
 #pragma unroll
     for (int t = 0; t < NC; t++) cache[t] = a.regstate[t];
 
-    if (C > 1) {
-        if (tid == 0) {
-            mbar_init(smem_u32(&mbar[0]), 1);
-            mbar_init(smem_u32(&mbar[1]), 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        cluster_sync_all();
-    }
-
-    // ---- pipeline registers: position t (0), t+1 (1), t+2 (2), t+3 (3)
-    int s0 = 0, e0 = 0, j0 = 0, s1 = 0, e1 = 0, j1 = 0, s2 = 0, e2 = 0, j2 = 0, s3 = 0, e3 = 0, j3 = 0;
-    int fi0 = 0, fi1 = 0, fi2 = 0;
-    double x0 = 0.0, x1 = 0.0, x2 = 0.0, pold0 = 0.0, pold1 = 0.0, cn0 = 0.0, cn1 = 0.0;
-    double r0[R], r1[R];
+    if (tid == 0) {
 #pragma unroll
-    for (int u = 0; u < R; u++) { r0[u] = 0.0; r1[u] = 0.0; }
-
-    if (0 < d) { s0 = a.pos_ptr[c]; e0 = a.pos_ptr[c + 1]; j0 = a.idx_feat[0]; }
-    if (1 < d) { s1 = a.pos_ptr[PS + c]; e1 = a.pos_ptr[PS + c + 1]; j1 = a.idx_feat[1]; }
-    if (2 < d) { s2 = a.pos_ptr[2 * PS + c]; e2 = a.pos_ptr[2 * PS + c + 1]; j2 = a.idx_feat[2]; }
-    if (s0 + tid < e0) {
-        fi0 = a.flag_idx[s0 + tid];
-        x0 = a.data[s0 + tid];
-        load_rec<R>(a.rec + (size_t)(fi0 & 0x7fffffff) * stride, r0);
+        for (int b = 0; b < MBOX_DEPTH; b++) mbar_init(smem_u32(&mbar[b]), 1);
+        fence_mbar_init();
     }
-    if (s1 + tid < e1) { fi1 = a.flag_idx[s1 + tid]; x1 = a.data[s1 + tid]; }
-    if (0 < d) { pold0 = a.prow[j0]; if (KIND == KIND_LINEAR) cn0 = a.cns[j0]; }
+    __syncthreads();
+    if (C > 1) cluster_sync_all();
 
-    for (int t = 0; t < d; t++) {
-        // ------------------------------------------------ issue the loads of future positions
-        if (t + 3 < d) {
-            s3 = a.pos_ptr[(size_t)(t + 3) * PS + c];
-            e3 = a.pos_ptr[(size_t)(t + 3) * PS + c + 1];
-            j3 = a.idx_feat[t + 3];
-        } else { s3 = 0; e3 = 0; j3 = 0; }
-        if (s2 + tid < e2) { fi2 = a.flag_idx[s2 + tid]; x2 = a.data[s2 + tid]; }
-        const bool has1 = s1 + tid < e1;
-        if (has1 && fi1 >= 0) load_rec<R>(a.rec + (size_t)fi1 * stride, r1);
-        if (t + 1 < d) { pold1 = a.prow[j1]; if (KIND == KIND_LINEAR) cn1 = a.cns[j1]; }
-        if (C > 1 && tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[t & 1]), 16u * (uint32_t)C);
+    // ------------------------------------------------------------------ per-position table
+    MetaChunk mcur, mnxt, mnx2;
+    meta_load_ptr(mcur, a, 0, c, lane);
+    meta_load_ptr(mnxt, a, 32, c, lane);
+    meta_load_ptr(mnx2, a, 64, c, lane);
+    meta_load_val<KIND>(mcur, a, 0, lane);
+    meta_load_val<KIND>(mnxt, a, 32, lane);
+    int chunk_base = 0;
+    auto meta_se = [&](int q, int &s, int &e) {
+        const int l = q & 31;
+        const int s1 = __shfl_sync(0xffffffffu, mcur.s, l), e1 = __shfl_sync(0xffffffffu, mcur.e, l);
+        const int s2 = __shfl_sync(0xffffffffu, mnxt.s, l), e2 = __shfl_sync(0xffffffffu, mnxt.e, l);
+        const bool in_cur = (q - chunk_base) < 32;
+        s = in_cur ? s1 : s2; e = in_cur ? e1 : e2;
+        if (q >= d) { s = 0; e = 0; }
+    };
+    auto meta_val = [&](int q, int &jf, double &pold, double &cn) {
+        const int l = q & 31;
+        const bool in_cur = (q - chunk_base) < 32;
+        const int j1 = __shfl_sync(0xffffffffu, mcur.jf, l), j2 = __shfl_sync(0xffffffffu, mnxt.jf, l);
+        const double p1 = sp_shfl(mcur.pold, l), p2 = sp_shfl(mnxt.pold, l);
+        jf = in_cur ? j1 : j2; pold = in_cur ? p1 : p2;
+        if (KIND == KIND_LINEAR) {
+            const double c1 = sp_shfl(mcur.cn, l), c2 = sp_shfl(mnxt.cn, l);
+            cn = in_cur ? c1 : c2;
+        } else cn = 0.0;
+    };
 
-        // ------------------------------------------------ gradient / curvature partial sums
-        const bool has0 = s0 + tid < e0;
-        const int i0 = fi0 & 0x7fffffff;
-        double tg = 0.0, th = 0.0;
-        double dA0[ND];
+    // ------------------------------------------------------------------ staging helpers
+    auto issue_idxval = [&](int q, int s, int e) {            // idx / value of position q -> stage q%3
+        const int st3 = q % 3;
 #pragma unroll
-        for (int u = 0; u < ND; u++) dA0[u] = 0.0;
-        if (has0) {
-            if (fi0 < 0) load_rec<R>(a.rec + (size_t)i0 * stride, r0);   // hazard: re-read
-            nz_terms<KIND, DEG, LOSS, R, ND>(r0, x0, pold0, dA0, tg, th);
+        for (int z = 0; z < NZ; z++) {
+            const int g = s + z * T + tid;
+            if (g < e) {
+                cp_async4(&idxbuf[(st3 * NZ + z) * T + tid], a.flag_idx + g);
+                cp_async8(&xbuf[(st3 * NZ + z) * T + tid], a.data + g);
+            }
         }
-        for (int e = s0 + T + tid; e < e0; e += T) {          // slices longer than the CTA
+    };
+    auto issue_rec = [&](int q, int s, int e) {               // records of position q -> stage q%2
+        const int st3 = q % 3, st2 = q & 1;
+#pragma unroll
+        for (int z = 0; z < NZ; z++) {
+            if (s + z * T + tid < e) {
+                const int i = idxbuf[(st3 * NZ + z) * T + tid] & SP_ROW_MASK;
+                const double *src = a.rec + (size_t)i * stride;
+#pragma unroll
+                for (int h = 0; h < NCH; h++)
+                    cp_async16(&recbuf[((st2 * NZ + z) * NCH + h) * T + tid], src + 2 * h);
+            }
+        }
+    };
+
+    // pending position (terms computed, waiting for its scalar chain + write-back)
+    int pi[NZ];
+    double px[NZ], pr[NZ][R], pdA[NZ][ND];
+#pragma unroll
+    for (int z = 0; z < NZ; z++) pi[z] = -1;
+    // gradient / curvature terms of position q (slice [s,e), coefficient pold); `late` = after the
+    // write-back of position q-1 (then bit31-tagged records are re-read as well)
+    auto terms = [&](int q, int s, int e, double pold, bool late, double &tg, double &th) {
+        const int st3 = q % 3, st2 = q & 1;
+        tg = 0.0; th = 0.0;
+#pragma unroll
+        for (int z = 0; z < NZ; z++) {
+            pi[z] = -1;
+            if (s + z * T + tid < e) {
+                const int fi = idxbuf[(st3 * NZ + z) * T + tid];
+                const int i = fi & SP_ROW_MASK;
+                const unsigned stale = (unsigned)fi & (late ? (SP_FLAG_BIT | SP_FLAG2_BIT) : SP_FLAG2_BIT);
+                pi[z] = i;
+                px[z] = xbuf[(st3 * NZ + z) * T + tid];
+                if (stale) {
+                    load_rec<R>(a.rec + (size_t)i * stride, pr[z]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NCH; h++) {
+                        const double2 v = recbuf[((st2 * NZ + z) * NCH + h) * T + tid];
+                        pr[z][2 * h] = v.x;
+                        if (2 * h + 1 < R) pr[z][2 * h + 1] = v.y;
+                    }
+                }
+                nz_terms<KIND, DEG, LOSS, R, ND>(pr[z], px[z], pold, pdA[z], tg, th);
+            }
+        }
+        for (int g = s + NZ * T + tid; g < e; g += T) {       // slices longer than NZ*T (rare)
             double rr[R], dd[ND];
-            load_rec<R>(a.rec + (size_t)(a.flag_idx[e] & 0x7fffffff) * stride, rr);
-            nz_terms<KIND, DEG, LOSS, R, ND>(rr, a.data[e], pold0, dd, tg, th);
+            load_rec<R>(a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride, rr);
+            nz_terms<KIND, DEG, LOSS, R, ND>(rr, a.data[g], pold, dd, tg, th);
         }
         tg = sp_warp_allsum(tg);
         if (KIND != KIND_LINEAR) th = sp_warp_allsum(th);
-        if (W > 1) {
-            if (lane == 0) red[warp] = make_double2(tg, th);
-            __syncthreads();
-            tg = 0.0; th = 0.0;
-            for (int w = 0; w < W; w++) { const double2 v = red[w]; tg += v.x; th += v.y; }
-        }
+    };
+    // all-to-all: every warp writes its partial into every CTA's mailbox q%4
+    auto push = [&](int q, double tg, double th) {
+        const int b = q & (MBOX_DEPTH - 1);
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[b]), 16u * (uint32_t)NP);
         if (C > 1) {
-            const int par = t & 1;
-            if (tid < C)
-                st_async_2f64(mapa_u32(smem_u32(&mbox[par][c]), (uint32_t)tid), tg, th,
-                              mapa_u32(smem_u32(&mbar[par]), (uint32_t)tid));
-            mbar_wait(smem_u32(&mbar[par]), (uint32_t)((t >> 1) & 1));
-            tg = 0.0; th = 0.0;
-            for (int r = 0; r < C; r++) { const double2 v = mbox[par][r]; tg += v.x; th += v.y; }
+            if (lane < C)
+                st_async_2f64(mapa_u32(smem_u32(&mbox[b * NP + c * W + warp]), (uint32_t)lane), tg, th,
+                              mapa_u32(smem_u32(&mbar[b]), (uint32_t)lane));
+        } else if (lane == 0) {
+            st_async_2f64(smem_u32(&mbox[b * NP + warp]), tg, th, smem_u32(&mbar[b]));
         }
+    };
 
-        // ------------------------------------------------ scalar chain (redundant in every thread)
+    // ------------------------------------------------------------------ prologue
+    int s0, e0, s1, e1, s2, e2, s3 = 0, e3 = 0;
+    meta_se(0, s0, e0); meta_se(1, s1, e1); meta_se(2, s2, e2);
+    int jf0, jf1 = 0;
+    double pold0, cn0, pold1 = 0.0, cn1 = 0.0;
+    meta_val(0, jf0, pold0, cn0);
+    issue_idxval(0, s0, e0); issue_idxval(1, s1, e1); issue_idxval(2, s2, e2);
+    cp_async_commit(); cp_async_wait_all();
+    issue_rec(0, s0, e0); issue_rec(1, s1, e1);
+    cp_async_commit(); cp_async_wait_all();
+    if (d > 0) {
+        double tg, th;
+        terms(0, s0, e0, pold0, false, tg, th);
+        push(0, tg, th);
+    }
+
+    for (int t = 0; t < d; t++) {
+        // ---- a/b: staged data of t+1 (records) and t+2 (indices) has landed; stage the next ones
+        cp_async_wait_all();
+        meta_se(t + 3, s3, e3);
+        issue_rec(t + 2, s2, e2);
+        issue_idxval(t + 3, s3, e3);
+        cp_async_commit();
+        // ---- c: early partial sums of t+1 (columns t and t+1 sample-disjoint)
+        meta_val(t + 1, jf1, pold1, cn1);
+        const bool have_next = t + 1 < d;
+        const bool conf1 = jf1 < 0;
+        // keep position t's pending registers: the terms of t+1 overwrite pi/px/pr/pdA
+        int ci[NZ];
+        double cx[NZ], cr[NZ][R], cdA[NZ][ND];
+#pragma unroll
+        for (int z = 0; z < NZ; z++) {
+            ci[z] = pi[z]; cx[z] = px[z];
+#pragma unroll
+            for (int u = 0; u < R; u++) cr[z][u] = pr[z][u];
+#pragma unroll
+            for (int u = 0; u < ND; u++) cdA[z][u] = pdA[z][u];
+        }
+        if (have_next && !conf1) {
+            double tg, th;
+            terms(t + 1, s1, e1, pold1, false, tg, th);
+            push(t + 1, tg, th);
+        }
+        // ---- d: position t: collect the partials, scalar chain, write-back
+        mbar_wait(smem_u32(&mbar[t & (MBOX_DEPTH - 1)]), (uint32_t)((t >> 2) & 1));
+        double g0 = 0.0, h0 = 0.0, g1 = 0.0, h1 = 0.0;
+        {
+            const double2 *box = mbox + (t & (MBOX_DEPTH - 1)) * NP;
+            int r = 0;
+            for (; r + 1 < NP; r += 2) {
+                const double2 v = box[r], u = box[r + 1];
+                g0 += v.x; h0 += v.y; g1 += u.x; h1 += u.y;
+            }
+            if (r < NP) { const double2 v = box[r]; g0 += v.x; h0 += v.y; }
+        }
+        const double tg = g0 + g1, th = h0 + h1;
+        const int j0 = jf0 & 0x7fffffff;
+
         double pnew, upd;
         if (KIND == KIND_LINEAR) {
             double u = tg + ab * pold0;                       // cd_linear.py:19-22
@@ -258,32 +403,43 @@ __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArg
         viol += fabs(upd);
         if (c == 0 && tid == 0) a.prow[j0] = pnew;
 
-        // ------------------------------------------------ synchronize predictions and caches
         if (KIND == KIND_ALL || upd != 0.0) {
-            if (has0) nz_scatter<KIND, DEG, R, ND>(a.rec + (size_t)i0 * stride, r0, dA0, x0, lam, upd, pold0, pnew);
-            for (int e = s0 + T + tid; e < e0; e += T) {
+#pragma unroll
+            for (int z = 0; z < NZ; z++)
+                if (ci[z] >= 0)
+                    nz_scatter<KIND, DEG, R, ND>(a.rec + (size_t)ci[z] * stride, cr[z], cdA[z], cx[z], lam, upd,
+                                                 pold0, pnew);
+            for (int g = s0 + NZ * T + tid; g < e0; g += T) {
                 double rr[R], dd[ND];
-                double *p = a.rec + (size_t)(a.flag_idx[e] & 0x7fffffff) * stride;
-                const double x = a.data[e];
+                double *p = a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride;
+                const double x = a.data[g];
                 load_rec<R>(p, rr);
+                dd[0] = x;
                 if (KIND == KIND_FM) {
-                    dd[0] = x;
 #pragma unroll
                     for (int u = 1; u < ND; u++) dd[u] = x * (rr[1 + u] - pold0 * dd[u - 1]);
-                } else {
-                    dd[0] = 0.0;
                 }
                 nz_scatter<KIND, DEG, R, ND>(p, rr, dd, x, lam, upd, pold0, pnew);
             }
         }
+        // ---- e: the write-back must be visible before tagged records are re-read / re-staged
         if (W > 1) __syncthreads(); else __syncwarp();
-
-        // ------------------------------------------------ rotate the pipeline
-        s0 = s1; e0 = e1; j0 = j1; pold0 = pold1; cn0 = cn1; fi0 = fi1; x0 = x1;
-#pragma unroll
-        for (int u = 0; u < R; u++) r0[u] = r1[u];
-        s1 = s2; e1 = e2; j1 = j2; fi1 = fi2; x1 = x2;
-        s2 = s3; e2 = e3; j2 = j3;
+        // ---- f: late partial sums of t+1 (the columns share samples)
+        if (have_next && conf1) {
+            double tg2, th2;
+            terms(t + 1, s1, e1, pold1, true, tg2, th2);
+            push(t + 1, tg2, th2);
+        }
+        // ---- g: rotate
+        s0 = s1; e0 = e1; s1 = s2; e1 = e2; s2 = s3; e2 = e3;
+        jf0 = jf1; pold0 = pold1; cn0 = cn1;
+        if (((t + 1) & 31) == 0) {                            // entering the next chunk of positions
+            chunk_base = t + 1;
+            mcur = mnxt;
+            mnxt = mnx2;
+            meta_load_val<KIND>(mnxt, a, chunk_base + 32, lane);
+            meta_load_ptr(mnx2, a, chunk_base + 64, c, lane);
+        }
     }
 
     if (c == 0 && tid == 0) {
@@ -293,20 +449,28 @@ __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArg
             for (int t = 0; t < NC; t++) a.regstate[t] = cache[t];
         }
     }
+    cp_async_wait_all();
     if (C > 1) cluster_sync_all();   // no CTA may exit while peers can still write its smem
 }
 
-template <int KIND, int DEG, int LOSS>
+template <int KIND, int DEG, int LOSS, int NZ>
 int launch_sweep(const SweepArgs &a, int threads, cudaStream_t st) {
-    auto kern = sweep_kernel<KIND, DEG, LOSS>;
+    constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
+    constexpr int NCH = (2 + NA + 1) / 2;
+    auto kern = sweep_kernel<KIND, DEG, LOSS, NZ>;
+    const int W = threads / 32;
+    const size_t smem = (size_t)2 * NZ * NCH * threads * 16 + (size_t)3 * NZ * threads * 8 +
+                        (size_t)MBOX_DEPTH * a.C * W * 16 + (size_t)3 * NZ * threads * 4;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return sp_check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     if (a.C > 8) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return sp_check_cuda(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)");
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.C, 1, 1);
     cfg.blockDim = dim3((unsigned)threads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -322,17 +486,22 @@ int launch_sweep(const SweepArgs &a, int threads, cudaStream_t st) {
 }
 
 template <int KIND, int DEG>
-int dispatch_loss(int loss, const SweepArgs &a, int threads, cudaStream_t st) {
+int dispatch_loss(int loss, const SweepArgs &a, int threads, int nz, cudaStream_t st) {
+#define SP_DISPATCH_NZ(L)                                                    \
+    return nz >= 2 ? launch_sweep<KIND, DEG, L, 2>(a, threads, st)           \
+                   : launch_sweep<KIND, DEG, L, 1>(a, threads, st)
     switch (loss) {
-    case SP_LOSS_SQUARED: return launch_sweep<KIND, DEG, SP_LOSS_SQUARED>(a, threads, st);
-    case SP_LOSS_LOGISTIC: return launch_sweep<KIND, DEG, SP_LOSS_LOGISTIC>(a, threads, st);
-    case SP_LOSS_SQHINGE: return launch_sweep<KIND, DEG, SP_LOSS_SQHINGE>(a, threads, st);
+    case SP_LOSS_SQUARED: SP_DISPATCH_NZ(SP_LOSS_SQUARED);
+    case SP_LOSS_LOGISTIC: SP_DISPATCH_NZ(SP_LOSS_LOGISTIC);
+    case SP_LOSS_SQHINGE: SP_DISPATCH_NZ(SP_LOSS_SQHINGE);
     default: sp_set_error("unknown loss id %d", loss); return SP_ERR_INVALID;
     }
+#undef SP_DISPATCH_NZ
 }
 
 int check_plan(const sp_dataset *ds, const sp_plan *plan, const char *who) {
-    if (!ds || !plan || !ds->csc_data || !plan->pos_ptr || !plan->flag_idx || !plan->idx_feat) {
+    if (!ds || !plan || !ds->csc_data || !plan->pos_ptr || !plan->flag_idx || !plan->idx_feat ||
+        !plan->pos_conf) {
         sp_set_error("%s: dataset/plan pointers missing", who);
         return SP_ERR_INVALID;
     }
@@ -347,9 +516,15 @@ int check_plan(const sp_dataset *ds, const sp_plan *plan, const char *who) {
     return SP_OK;
 }
 
+// nonzeros per thread staged through shared memory: 2 when the mean slice exceeds the CTA
+int pick_nz(const sp_dataset *ds, const sp_plan *plan) {
+    const double avg = (double)ds->nnz / (ds->n_features > 0 ? ds->n_features : 1);
+    return (avg / plan->n_cta > 0.8 * plan->threads) ? 2 : 1;
+}
+
 }  // namespace
 
-int sp_min_rec_stride(int degree) {   // record = {y_pred, y, A^1..A^{m-1}}, even number of doubles
+int sp_min_rec_stride(int degree) {   // record = {y_pred, y, A^1..A^{m-1}}, multiple of 4 doubles
     const int r = (degree == -1) ? 3 : (degree < 1 ? 2 : degree + 1);
     return (r + 3) & ~3;
 }
@@ -369,10 +544,10 @@ extern "C" int sp_cd_linear_epoch(const sp_dataset *ds, const sp_plan *plan, dou
     SweepArgs a = {};
     a.d = ds->n_features; a.C = plan->n_cta;
     a.pos_ptr = plan->pos_ptr; a.flag_idx = plan->flag_idx; a.data = ds->csc_data;
-    a.idx_feat = plan->idx_feat;
+    a.idx_feat = plan->idx_feat; a.pos_conf = plan->pos_conf;
     a.prow = w; a.cns = col_norm_sq; a.lam_ptr = nullptr; a.ab = alpha; a.gamma = 0.0; a.eta = 1.0;
     a.reg = SP_REG_L1; a.rec = rec; a.stride = rec_stride; a.regstate = viol; a.viol = viol;
-    return dispatch_loss<KIND_LINEAR, 1>(loss, a, plan->threads, (cudaStream_t)stream);
+    return dispatch_loss<KIND_LINEAR, 1>(loss, a, plan->threads, pick_nz(ds, plan), (cudaStream_t)stream);
 }
 
 extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P_kd, int k,
@@ -407,6 +582,7 @@ extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P
     const int d = ds->n_features;
     if (d == 0) return SP_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const int nz = pick_nz(ds, plan);
     for (int ss = 0; ss < k; ss++) {
         const int s = idx_comp_host[ss];
         if (s < 0 || s >= k) { sp_set_error("sp_pcd_epoch: bad component index %d", s); return SP_ERR_INVALID; }
@@ -421,15 +597,15 @@ extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P
         SweepArgs a = {};
         a.d = d; a.C = plan->n_cta;
         a.pos_ptr = plan->pos_ptr; a.flag_idx = plan->flag_idx; a.data = ds->csc_data;
-        a.idx_feat = plan->idx_feat;
+        a.idx_feat = plan->idx_feat; a.pos_conf = plan->pos_conf;
         a.prow = prow; a.cns = nullptr; a.lam_ptr = lams + s; a.ab = beta; a.gamma = gamma; a.eta = eta;
         a.reg = reg; a.rec = rec; a.stride = rec_stride; a.regstate = regstate; a.viol = viol;
         switch (degree) {
-        case -1: rc = dispatch_loss<KIND_ALL, 1>(loss, a, plan->threads, st); break;
-        case 2: rc = dispatch_loss<KIND_FM, 2>(loss, a, plan->threads, st); break;
-        case 3: rc = dispatch_loss<KIND_FM, 3>(loss, a, plan->threads, st); break;
-        case 4: rc = dispatch_loss<KIND_FM, 4>(loss, a, plan->threads, st); break;
-        case 5: rc = dispatch_loss<KIND_FM, 5>(loss, a, plan->threads, st); break;
+        case -1: rc = dispatch_loss<KIND_ALL, 1>(loss, a, plan->threads, nz, st); break;
+        case 2: rc = dispatch_loss<KIND_FM, 2>(loss, a, plan->threads, nz, st); break;
+        case 3: rc = dispatch_loss<KIND_FM, 3>(loss, a, plan->threads, nz, st); break;
+        case 4: rc = dispatch_loss<KIND_FM, 4>(loss, a, plan->threads, nz, st); break;
+        case 5: rc = dispatch_loss<KIND_FM, 5>(loss, a, plan->threads, nz, st); break;
         }
         if (rc) return rc;
     }

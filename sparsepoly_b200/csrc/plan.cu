@@ -48,29 +48,42 @@ __global__ void order_ptr_kernel(int d, int C, const int32_t *__restrict__ idx_f
     }
 }
 
-// flag_idx[e] = row | FLAG if the same sample also has a nonzero in the column visited
-// immediately before this one (position t-1): that sample's record is still being rewritten
-// when position t's prefetch is issued, so the sweep kernel must re-read it after the barrier.
+// flag_idx[e] = row | bit31 if the same sample also has a nonzero in the column visited at
+// position t-1, | bit30 if it has one in the column visited at position t-2: records of those
+// samples are (possibly) still being rewritten when position t's asynchronous prefetch is
+// issued, so the sweep kernel re-reads them after the barrier.  pos_conf[t] = 1 when ANY sample
+// of column t carries bit31 (columns t-1 and t are not sample-disjoint).
+__device__ __forceinline__ bool col_has_row(const int32_t *__restrict__ indices, int lo, int hi, int row) {
+    const int end = hi;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (indices[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end) && (indices[lo] == row);
+}
+
 __global__ void order_flag_kernel(int d, const int32_t *__restrict__ idx_feat,
                                   const int32_t *__restrict__ indptr,
-                                  const int32_t *__restrict__ indices, int32_t *flag_idx) {
+                                  const int32_t *__restrict__ indices, int32_t *flag_idx,
+                                  int32_t *pos_conf) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int t = warp; t < d; t += n_warps) {
         const int j = idx_feat[t];
-        int plo = 0, phi = 0;
-        if (t > 0) { const int jp = idx_feat[t - 1]; plo = indptr[jp]; phi = indptr[jp + 1]; }
+        int p1lo = 0, p1hi = 0, p2lo = 0, p2hi = 0;
+        if (t > 0) { const int jp = idx_feat[t - 1]; p1lo = indptr[jp]; p1hi = indptr[jp + 1]; }
+        if (t > 1) { const int jp = idx_feat[t - 2]; p2lo = indptr[jp]; p2hi = indptr[jp + 1]; }
+        bool any1 = false;
         for (int e = indptr[j] + lane; e < indptr[j + 1]; e += 32) {
             const int row = indices[e];
-            int lo = plo, hi = phi;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (indices[mid] < row) lo = mid + 1; else hi = mid;
-            }
-            const bool hit = (lo < phi) && (indices[lo] == row);
-            flag_idx[e] = hit ? (int32_t)((uint32_t)row | SP_FLAG_BIT) : row;
+            const bool h1 = col_has_row(indices, p1lo, p1hi, row);
+            const bool h2 = col_has_row(indices, p2lo, p2hi, row);
+            any1 = any1 || h1;
+            flag_idx[e] = (int32_t)((uint32_t)row | (h1 ? SP_FLAG_BIT : 0u) | (h2 ? SP_FLAG2_BIT : 0u));
         }
+        any1 = __any_sync(0xffffffffu, any1);
+        if (lane == 0) pos_conf[t] = any1 ? 1 : 0;
     }
 }
 
@@ -123,18 +136,22 @@ extern "C" int sp_plan_partition(const sp_dataset *ds, int n_cta, int32_t *col_p
 
 extern "C" int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part,
                              const int32_t *idx_feat, int32_t *pos_ptr, int32_t *flag_idx,
-                             sp_stream stream) {
-    if (!ds || !col_part || !idx_feat || !pos_ptr || !flag_idx || n_cta < 1 || n_cta > 16) {
+                             int32_t *pos_conf, sp_stream stream) {
+    if (!ds || !col_part || !idx_feat || !pos_ptr || !flag_idx || !pos_conf || n_cta < 1 || n_cta > 16) {
         sp_set_error("sp_plan_order: invalid argument");
         return SP_ERR_INVALID;
     }
     if (ds->n_features == 0) return SP_OK;
+    if (ds->n_samples >= (1 << 30)) {
+        sp_set_error("sp_plan_order: n_samples >= 2^30 is not supported (two flag bits in the row index)");
+        return SP_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     order_ptr_kernel<<<blocks_for((long long)ds->n_features * (n_cta + 1), 256), 256, 0, st>>>(
         ds->n_features, n_cta, idx_feat, col_part, pos_ptr);
     SP_LAUNCH_CHECK("order_ptr_kernel");
     order_flag_kernel<<<blocks_for((long long)ds->n_features * 32, 256), 256, 0, st>>>(
-        ds->n_features, idx_feat, ds->csc_indptr, ds->csc_indices, flag_idx);
+        ds->n_features, idx_feat, ds->csc_indptr, ds->csc_indices, flag_idx, pos_conf);
     SP_LAUNCH_CHECK("order_flag_kernel");
     return SP_OK;
 }

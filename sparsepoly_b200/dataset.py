@@ -159,17 +159,15 @@ def choose_geometry(ds, solver, n_cta=None, threads=None):
         threads = int(env_t)
     avg = ds.nnz / max(ds.n_features, 1)
     if n_cta is None:
-        if solver == "pbcd":
-            n_cta = _pow2_floor(max(1, min(16, int(avg // 16))))   # >= ~2 nonzeros per warp
-        else:
-            n_cta = _pow2_floor(max(1, min(16, int(avg // 32))))   # ~1 nonzero per thread
+        # widest cluster that still leaves ~16 nonzeros of a column per CTA (measured on B200:
+        # the step time is flat in the geometry once every nonzero has its own thread)
+        n_cta = _pow2_floor(max(1, min(16, int(avg // 16))))
     if threads is None:
+        per_cta = avg / n_cta
         if solver == "pbcd":
-            per_cta = avg / n_cta
-            threads = 32 * max(1, min(8, int(np.ceil(per_cta / 4))))
+            threads = 32 * max(1, min(8, int(np.ceil(per_cta / 4))))      # ~4 nonzero rows per warp
         else:
-            per_cta = avg / n_cta
-            threads = 32 * max(1, min(8, int(np.ceil(per_cta / 32))))
+            threads = 32 * max(1, min(8, int(np.ceil(1.5 * per_cta / 32))))   # 1.5 slots per nonzero
     return int(n_cta), int(threads)
 
 
@@ -186,12 +184,14 @@ class SweepPlan:
         self.pos_ptr = torch.empty(max(d * (C_ + 1), 1), dtype=torch.int32, device=dev)
         self.flag_idx = torch.empty(max(ds.nnz, 1), dtype=torch.int32, device=dev)
         self.idx_feat = torch.empty(max(d, 1), dtype=torch.int32, device=dev)
+        self.pos_conf = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
         _lib.check(_lib.load().sp_plan_partition(ds.ref(), C_, _ptr(self.col_part), _stream()))
         self._order_host = None
         s = _lib.SpPlan()
         s.n_cta, s.threads = C_, self.threads
         s.pos_ptr, s.flag_idx, s.idx_feat = (self.pos_ptr.data_ptr(), self.flag_idx.data_ptr(),
                                              self.idx_feat.data_ptr())
+        s.pos_conf = self.pos_conf.data_ptr()
         self.struct = s
 
     def set_order(self, idx_feat_host):
@@ -202,7 +202,7 @@ class SweepPlan:
         self.idx_feat[: idx.size].copy_(torch.from_numpy(idx))
         _lib.check(_lib.load().sp_plan_order(self.ds.ref(), self.n_cta, _ptr(self.col_part),
                                              _ptr(self.idx_feat), _ptr(self.pos_ptr),
-                                             _ptr(self.flag_idx), _stream()))
+                                             _ptr(self.flag_idx), _ptr(self.pos_conf), _stream()))
 
     def ref(self):
         return C.byref(self.struct)
