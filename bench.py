@@ -404,16 +404,13 @@ def run_psgd_workload(args, rank, world, local):
     loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     work = solvers.prox_work(d, k, dev)
     it = [1]
+    state = solvers.PsgdLazyState(P, kw["regularizer"])
 
     def minibatch(m):
         b0, b1 = m * b_loc, (m + 1) * b_loc
-        solvers.psgd_grad(ds, y_dev, P, w, lams, 2, kw["loss"], True, idx, b0, b1, gP, gw, loss_dev)
-        if group is not None:
-            dist.all_reduce(gP, group=group)
-            dist.all_reduce(gw, group=group)
-        eta_P, eta_w = solvers.get_eta(1, kw["eta0"], kw["alpha"], kw["beta"], kw["power_t"], it[0])
-        solvers.psgd_step(P, gP, w, gw, eta_P, eta_w, kw["alpha"], kw["beta"], b_loc * world, True)
-        solvers.prox(P[0], kw["regularizer"], kw["gamma"] * eta_P / (1 + eta_P * kw["beta"]), work)
+        solvers.psgd_minibatch(ds, y_dev, P, w, lams, 2, kw["alpha"], kw["beta"], kw["gamma"],
+                               kw["regularizer"], kw["loss"], gP, gw, idx, True, kw["eta0"], 1,
+                               kw["power_t"], b0, b1, b_loc * world, it[0], loss_dev, work, state, group)
         it[0] += 1
 
     for m in range(args.warmup):
@@ -462,7 +459,7 @@ def run_psgd_workload(args, rank, world, local):
                      "whole_step_gbs_per_gpu": step_bytes / (ms_total / 1e3) / 1e9,
                      "whole_step_frac": step_bytes / (ms_total / 1e3) / 1e9 / peak},
         "gpu_launches": int(sum(cnt)),
-        "kernel_ms": {"psgd_grad": ms[4], "psgd_step": ms[5], "prox": ms[6]},
+        "kernel_ms": {"psgd_grad": ms[4], "psgd_step_w": ms[5], "fused_update_prox": ms[6]},
         "clocks": clocks,
     }
     result["roofline"]["frac"] = result["roofline"]["achieved"] / peak
@@ -474,6 +471,7 @@ def run_psgd_workload(args, rank, world, local):
     y_h = torch.from_numpy(y[:need].copy()).pin_memory()
     P.copy_(torch.from_numpy(np.ascontiguousarray(0.01 * rng.randn(1, d, k))))
     w.zero_(); it[0] = 1
+    state = solvers.PsgdLazyState(P, kw["regularizer"])
     max_nnz = int(np.max(Xr.indptr[b_loc::b_loc] - Xr.indptr[:-b_loc:b_loc])) if need >= b_loc else Xr.nnz
     ip_d = torch.empty(b_loc + 1, dtype=torch.int32, device=dev)
     ix_d = torch.empty(max_nnz, dtype=torch.int32, device=dev)
@@ -492,13 +490,9 @@ def run_psgd_workload(args, rank, world, local):
         yb_d.copy_(y_h[r0:r1], non_blocking=True)
         h2d[0] += (b_loc + 1) * 4 + (p1 - p0) * 12 + b_loc * 8
         dsb = DeviceDataset.from_device_csr(b_loc, d, ip_d, ix_d, dt_d)
-        solvers.psgd_grad(dsb, yb_d, P, w, lams, 2, kw["loss"], True, idx_b, 0, b_loc, gP, gw, loss_dev)
-        if group is not None:
-            dist.all_reduce(gP, group=group)
-            dist.all_reduce(gw, group=group)
-        eta_P, eta_w = solvers.get_eta(1, kw["eta0"], kw["alpha"], kw["beta"], kw["power_t"], it[0])
-        solvers.psgd_step(P, gP, w, gw, eta_P, eta_w, kw["alpha"], kw["beta"], b_loc * world, True)
-        solvers.prox(P[0], kw["regularizer"], kw["gamma"] * eta_P / (1 + eta_P * kw["beta"]), work)
+        solvers.psgd_minibatch(dsb, yb_d, P, w, lams, 2, kw["alpha"], kw["beta"], kw["gamma"],
+                               kw["regularizer"], kw["loss"], gP, gw, idx_b, True, kw["eta0"], 1,
+                               kw["power_t"], 0, b_loc, b_loc * world, it[0], loss_dev, work, state, group)
         it[0] += 1
         return loss_dev.item()                           # D2H read of the step's metric
 

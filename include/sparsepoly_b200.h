@@ -132,11 +132,13 @@ int sp_get_eta(int learning_rate, double eta0, double alpha, double beta, double
 
 /* Minibatch gradient: samples idx_samples[b0..b1) (psgd._pred + _update_grads,
  * psgd.py:47-91).  P_odk [n_orders,d,k]; grad_P same shape and grad_w [d] are accumulated
- * into (fp64 atomics); *loss_sum accumulates sum of losses at the pre-update parameters. */
+ * into (fp64 atomics); *loss_sum accumulates sum of losses at the pre-update parameters.
+ * col_thresh (may be NULL): [n_orders*k] thresholds of a lazily applied prox -- the model is
+ * soft_threshold(P_odk[o,:,s], col_thresh[o*k+s]) (see sp_psgd_update_prox). */
 int sp_psgd_grad(const sp_dataset *ds, const double *y, const double *P_odk, int n_orders, int k,
                  const double *w, const double *lams, int degree, int loss, int fit_linear,
                  const int32_t *idx_samples, int b0, int b1, double *grad_P, double *grad_w,
-                 double *loss_sum, sp_stream stream);
+                 double *loss_sum, const double *col_thresh, sp_stream stream);
 
 /* SGD step + zeroing of the gradients (psgd._update_params without the prox, psgd.py:94-117,
  * :195-196):  P = (P - (eta_P/batch)*grad_P) / (1 + eta_P*beta), same for w with alpha. */
@@ -147,6 +149,18 @@ int sp_psgd_step(double *P_odk, double *grad_P, double *w, double *grad_w, int n
 /* regularizer.prox on one order P_dk [d,k] (l1.py:50-51, l21.py:43-48, squaredl12.py:66-78,
  * squaredl21.py:63-74, regularizer/utils.py:26-70).  work: >= d + 8*k + 64 doubles. */
 int sp_prox(double *P_dk, int d, int k, int reg, double strength, double *work, sp_stream stream);
+
+/* Fused dense update + prox for l1 / squaredl12, one cooperative launch per minibatch:
+ * P_raw = (soft_threshold(P_raw, col_thresh) - (eta_P/batch)*grad_P)/(1+eta_P*beta), grad_P = 0,
+ * then col_thresh = the new prox thresholds (l1: strength; squaredl12: 2*strength*S_s of
+ * regularizer/utils.py:26-70, found by a warm-started fixed-point selection).  The soft threshold
+ * is applied lazily by the readers; sp_psgd_finalize materialises it (P = model, col_thresh = 0).
+ * col_thresh: [n_orders*k], zero-initialised before the first call; work: sp_psgd_lazy_work_doubles. */
+int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
+                        double beta, int batch, int reg, double strength, double *col_thresh,
+                        double *work, sp_stream stream);
+int sp_psgd_finalize(double *P_odk, int n_orders, int d, int k, double *col_thresh, sp_stream stream);
+size_t sp_psgd_lazy_work_doubles(int n_orders, int k);
 
 /* doubles of scratch sp_prox / sp_psgd_epoch need for a [d,k] matrix */
 size_t sp_prox_work_doubles(int d, int k);

@@ -87,13 +87,14 @@ def prox(P_dk, reg, strength, work):
 
 
 def psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-              loss_sum):
-    """psgd._pred + _update_grads for samples idx_samples[b0:b1] (psgd.py:47-91)."""
+              loss_sum, col_thresh=None):
+    """psgd._pred + _update_grads for samples idx_samples[b0:b1] (psgd.py:47-91).  col_thresh:
+    thresholds of a lazily applied prox (see psgd_update_prox)."""
     n_orders, _, k = P_odk.shape
     _lib.check(_L().sp_psgd_grad(ds.ref(), _ptr(y), _ptr(P_odk), int(n_orders), int(k), _ptr(w),
                                  _ptr(lams), int(degree), _lib.LOSS_IDS[loss], int(bool(fit_linear)),
                                  _ptr(idx_samples), int(b0), int(b1), _ptr(grad_P), _ptr(grad_w),
-                                 _ptr(loss_sum), _stream()))
+                                 _ptr(loss_sum), _ptr(col_thresh), _stream()))
 
 
 def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_linear):
@@ -102,6 +103,32 @@ def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_li
     _lib.check(_L().sp_psgd_step(_ptr(P_odk), _ptr(grad_P), _ptr(w), _ptr(grad_w), int(n_orders), int(d),
                                  int(k), float(eta_P), float(eta_w), float(alpha), float(beta),
                                  int(batch), int(bool(fit_linear)), _stream()))
+
+
+LAZY_REGS = ("l1", "squaredl12")
+
+
+def lazy_work(n_orders, k, device):
+    return torch.empty(int(_L().sp_psgd_lazy_work_doubles(int(n_orders), int(k))), dtype=_f64, device=device)
+
+
+def psgd_step_w(w, grad_w, eta_w, alpha, batch, fit_linear):
+    """The linear half of psgd._update_params (psgd.py:109-112) + zeroing of grad_w."""
+    _lib.check(_L().sp_psgd_step(None, None, _ptr(w), _ptr(grad_w), 0, int(w.shape[0]), 1, 0.0,
+                                 float(eta_w), float(alpha), 0.0, int(batch), int(bool(fit_linear)), _stream()))
+
+
+def psgd_update_prox(P_odk, grad_P, eta_P, beta, batch, reg, strength, col_thresh, work):
+    """Fused P update + prox with a lazily applied soft threshold (l1 / squaredl12 only)."""
+    n_orders, d, k = P_odk.shape
+    _lib.check(_L().sp_psgd_update_prox(_ptr(P_odk), _ptr(grad_P), int(n_orders), int(d), int(k),
+                                        float(eta_P), float(beta), int(batch), _lib.REG_IDS[reg],
+                                        float(strength), _ptr(col_thresh), _ptr(work), _stream()))
+
+
+def psgd_finalize(P_odk, col_thresh):
+    n_orders, d, k = P_odk.shape
+    _lib.check(_L().sp_psgd_finalize(_ptr(P_odk), int(n_orders), int(d), int(k), _ptr(col_thresh), _stream()))
 
 
 def psgd_epoch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
@@ -127,15 +154,52 @@ def psgd_epoch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, gra
     import torch.distributed as dist
     from .distributed import local_batches
     world = dist.get_world_size(group)
+    state = PsgdLazyState(P_odk, reg)
     for b0, b1, b_global in local_batches(ds.n_samples, batch_size, world):
-        psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-                  loss_sum)
+        psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
+                       idx_samples, fit_linear, eta0, learning_rate, power_t, b0, b1, b_global, it,
+                       loss_sum, work, state, group)
+        it += 1
+    state.finalize(P_odk)
+    return it
+
+
+class PsgdLazyState:
+    """Thresholds of the lazily applied prox (l1 / squaredl12) + scratch of the fused kernel."""
+
+    def __init__(self, P_odk, reg):
+        n_orders, _, k = P_odk.shape
+        self.lazy = reg in LAZY_REGS
+        if self.lazy:
+            self.thr = torch.zeros(n_orders * k, dtype=_f64, device=P_odk.device)
+            self.work = lazy_work(n_orders, k, P_odk.device)
+        else:
+            self.thr = None
+
+    def finalize(self, P_odk):
+        if self.lazy:
+            psgd_finalize(P_odk, self.thr)
+
+
+def psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
+                   idx_samples, fit_linear, eta0, learning_rate, power_t, b0, b1, b_global, it, loss_sum,
+                   work, state, group=None):
+    """One parameter update of psgd.psgd_epoch (psgd.py:153-198) on samples idx_samples[b0:b1] of this
+    rank; b_global = number of samples in the minibatch over all ranks."""
+    n_orders = P_odk.shape[0]
+    psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
+              loss_sum, state.thr)
+    if group is not None:
+        import torch.distributed as dist
         dist.all_reduce(grad_P, group=group)
         if fit_linear:
             dist.all_reduce(grad_w, group=group)
-        eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
+    eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
+    strength = gamma * eta_P / (1 + eta_P * beta)
+    if state.lazy:
+        psgd_step_w(w, grad_w, eta_w, alpha, b_global, fit_linear)
+        psgd_update_prox(P_odk, grad_P, eta_P, beta, b_global, reg, strength, state.thr, state.work)
+    else:
         psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, b_global, fit_linear)
         for o in range(n_orders):
-            prox(P_odk[o], reg, gamma * eta_P / (1 + eta_P * beta), work)
-        it += 1
-    return it
+            prox(P_odk[o], reg, strength, work)

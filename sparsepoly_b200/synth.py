@@ -29,9 +29,11 @@ def criteo_like(n, d, seed, n_numeric=13, n_categorical=26, zipf_a=1.1):
     width = (d - n_numeric) // n_categorical
     if width < 1:
         raise ValueError("d too small for the Criteo-shaped layout")
-    for g in range(n_categorical):
-        z = rng.zipf(zipf_a, size=n)
-        cols[:, n_numeric + g] = n_numeric + g * width + ((z - 1) % width).astype(np.int32)
+    cdf = np.cumsum(np.arange(1, width + 1, dtype=np.float64) ** (-zipf_a))
+    cdf /= cdf[-1]
+    for g in range(n_categorical):           # truncated Zipf(a) over the slice, inverse-CDF sampling
+        ids = np.searchsorted(cdf, rng.rand(n), side="left").astype(np.int32)
+        cols[:, n_numeric + g] = n_numeric + g * width + np.minimum(ids, width - 1)
     vals[:, n_numeric:] = 1.0
     indptr = np.arange(0, n * r + 1, r, dtype=np.int64)
     X = sp.csr_matrix((vals.ravel(), cols.ravel(), indptr), shape=(n, d))
