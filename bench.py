@@ -12,6 +12,9 @@ Workloads (BASELINE.json configs / SURVEY.md 8d):
              sample-sharded, 6.25M rows per GPU (= n=50M at 8 GPUs)               [N>1 default]
 A "step" is one epoch (pcd / pbcd / allsub) or one minibatch of batch_size="auto" (psgd).
 pcd / pbcd do not shard (sequential coordinate order): with N>1 they run N independent replicas.
+With --workload auto (default) the headline line is the pcd workload (replicas for N>1) and the
+"also" list carries the psgd numbers (sample-sharded over the N ranks, NCCL all-reduce) and, at
+N=1, the pbcd epoch time.
 
 `--impl reference` times the reference algorithm on the host CPU (the pinned C oracle port of the
 numba path; the numba package itself cannot travel to the GPU box) on a bounded sample.
@@ -385,11 +388,18 @@ def run_psgd_workload(args, rank, world, local):
     if world > 1:
         import torch.distributed as dist
         group = dist.group.WORLD
+    global ROWS_OVERRIDE
+    ROWS_OVERRIDE = args.rows_per_gpu
     X, y = make_problem("psgd", args.scale, rank)
     n, d = X.shape
     k = wl["k"]
-    batch = int(n * d / X.nnz)                        # batch_size="auto" (global)
-    b_loc = max(1, batch // world)
+    batch = int(n * d / X.nnz)                        # batch_size="auto" = d / nnz_row (independent of n)
+    if args.psgd_batch == "auto":
+        b_loc = max(1, batch // world)                # the reference's global minibatch, split over ranks
+    elif args.psgd_batch == "weak":
+        b_loc = batch                                 # every rank contributes one auto-sized batch
+    else:
+        b_loc = max(1, int(args.psgd_batch) // world)
     need = (args.warmup + args.steps) * b_loc
     if need > n:
         raise SystemExit(f"psgd bench needs {need} rows per GPU, shard has {n}")
@@ -518,7 +528,8 @@ def run_psgd_workload(args, rank, world, local):
         v, desc = cpu_reference_psgd_samples_per_s(X, y, args.cpu_budget)
         result["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port", "sample": desc}
     result["config"] = {"workload": "C5 psgd: " + json.dumps(kw), "rows_per_gpu": n, "n_features": d,
-                        "nnz_per_row": r, "global_batch": b_loc * world, "scale": args.scale,
+                        "nnz_per_row": r, "global_batch": b_loc * world, "batch_mode": args.psgd_batch,
+                        "batch_size_auto": batch, "scale": args.scale,
                         "l2": "inputs_exceed_l2 (P and grad_P are 256 MB each)" if d * k * 8 > 1.3e8 else "P fits L2",
                         "parallelism": "single GPU" if world == 1 else f"dp{world}: samples sharded, dense gradient all-reduced (NCCL) per minibatch"}
     return result
@@ -571,14 +582,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="psgd: override the shard size (debug)")
+    ap.add_argument("--psgd-batch", default="weak",
+                    help="psgd global minibatch: 'auto' (= d/nnz_row split over the ranks), 'weak' "
+                         "(auto x n_gpus: per-GPU work fixed) or an integer")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()
     rank, world, local = dist_env()
     global ROWS_OVERRIDE
     ROWS_OVERRIDE = args.rows_per_gpu
-    if args.workload == "auto":
-        args.workload = "pcd" if max(world, args.gpus) == 1 else "psgd"
-    if args.workload == "psgd" and args.steps == 3 and args.warmup == 3:
-        pass
+    auto = args.workload == "auto"
+    if auto:
+        args.workload = "pcd"
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -599,6 +613,28 @@ def main():
         res = run_psgd_workload(args, rank, world, local)
     else:
         res = run_sweep_workload(name, args, rank, world, local)
+    also = []
+    if auto and not args.no_also:
+        # secondary measurements of the same path (north_star: pbcd epoch time and psgd samples/s,
+        # psgd sharded over the ranks); short runs, no CPU leg
+        import copy
+        a2 = copy.copy(args)
+        a2.no_cpu = True
+        a2.steps, a2.warmup = 20, 3
+        if a2.rows_per_gpu == 0:
+            a2.rows_per_gpu = 1_000_000          # >= 23 auto-sized minibatches; batch "auto" is n-independent
+        for mode in (["auto"] if world == 1 else ["weak", "auto"]):
+            a2.psgd_batch = mode
+            r2 = run_psgd_workload(a2, rank, world, local)
+            r2.update(metric=metric_name("psgd"), unit="samples/s", n_gpus=world)
+            also.append(r2)
+        if world == 1:
+            a3 = copy.copy(args)
+            a3.no_cpu = True
+            a3.steps, a3.warmup = 2, 3
+            r3 = run_sweep_workload("pbcd", a3, rank, world, local)
+            r3.update(metric=metric_name("pbcd"), unit="s/epoch", n_gpus=1)
+            also.append(r3)
     if rank == 0:
         line = {"metric": metric_name(name), "value": res.pop("value"),
                 "unit": "samples/s" if name == "psgd" else "s/epoch", "n_gpus": world, "steps": args.steps,
@@ -606,6 +642,8 @@ def main():
                 "higher_is_better": name == "psgd", "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic"}
         line.update(res)
+        if also:
+            line["also"] = also
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
