@@ -10,7 +10,9 @@
 //     is only ever touched by one SM; the only inter-SM traffic is the all-to-all exchange of the
 //     per-warp partial sums (g, h) through distributed shared memory (st.async + mbarrier
 //     complete_tx, 4-deep mailboxes);
-//   * every thread runs the ~20-flop scalar chain (step, prox_cd, regularizer cache) redundantly;
+//   * warps are specialised: W gather warps (stage, gradient terms, push, write-back) and one
+//     scalar-chain warp per CTA that sums the partials and runs the ~20-flop chain (step, prox_cd,
+//     regularizer cache) redundantly in every CTA, handing (upd, p_new) back through shared memory;
 //   * column slices and records of the coming positions are staged through shared memory with
 //     cp.async (no scoreboard coupling with the step's own loads); the per-position table lives in
 //     registers, 32 positions per warp, broadcast by shuffles;
@@ -139,7 +141,7 @@ __device__ __forceinline__ void meta_load_val(MetaChunk &m, const SweepArgs &a, 
 }
 
 template <int KIND, int DEG, int LOSS, int NZ>
-__global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArgs a) {
+__global__ void __launch_bounds__(SWEEP_MAX_THREADS + 32) sweep_kernel(const SweepArgs a) {
     constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
     constexpr int R = 2 + NA;                                // doubles used per record
     constexpr int NCH = (R + 1) / 2;                         // 16-byte chunks staged per record
@@ -147,17 +149,18 @@ __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArg
     constexpr int NC = (KIND == KIND_FM) ? DEG : 1;          // regularizer cache scalars
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long mbar[MBOX_DEPTH];
+    __shared__ __align__(8) unsigned long long mbar[MBOX_DEPTH];   // partials of position q have landed
+    __shared__ __align__(8) unsigned long long rbar[MBOX_DEPTH];   // result of position q is published
+    __shared__ double2 res[MBOX_DEPTH];                             // (upd, pnew) of position q
 
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    // warp roles: warps 0..W-1 gather (stage, terms, push, write-back); warp W runs the scalar chain
+    const int T = blockDim.x - 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const bool scalar_role = warp == W;
     const int C = a.C, d = a.d;
     const int c = (C > 1) ? (int)cluster_ctarank() : 0;
     const int NP = C * W;                                    // partials per position
     const int stride = a.stride;
-    const double mu = sp_mu<LOSS>();
     const double lam = (KIND == KIND_LINEAR) ? 1.0 : *a.lam_ptr;
-    const double ab = a.ab, gamma = a.gamma, eta = a.eta;
-    const int reg = a.reg;
 
     // dynamic smem carve-up
     double2 *recbuf = reinterpret_cast<double2 *>(smem_raw);                 // [2][NZ][NCH][T]
@@ -165,14 +168,12 @@ __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArg
     double2 *mbox = reinterpret_cast<double2 *>(xbuf + (size_t)3 * NZ * T);  // [MBOX_DEPTH][NP]
     int *idxbuf = reinterpret_cast<int *>(mbox + (size_t)MBOX_DEPTH * NP);   // [3][NZ][T]
 
-    double viol = *a.viol;
-    double cache[NC];
-#pragma unroll
-    for (int t = 0; t < NC; t++) cache[t] = a.regstate[t];
-
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < MBOX_DEPTH; b++) mbar_init(smem_u32(&mbar[b]), 1);
+        for (int b = 0; b < MBOX_DEPTH; b++) {
+            mbar_init(smem_u32(&mbar[b]), 1);
+            mbar_init(smem_u32(&rbar[b]), 1);
+        }
         fence_mbar_init();
     }
     __syncthreads();
@@ -205,251 +206,287 @@ __global__ void __launch_bounds__(SWEEP_MAX_THREADS) sweep_kernel(const SweepArg
             cn = in_cur ? c1 : c2;
         } else cn = 0.0;
     };
-
-    // ------------------------------------------------------------------ staging helpers
-    auto issue_idxval = [&](int q, int s, int e) {            // idx / value of position q -> stage q%3
-        const int st3 = q % 3;
-#pragma unroll
-        for (int z = 0; z < NZ; z++) {
-            const int g = s + z * T + tid;
-            if (g < e) {
-                cp_async4(&idxbuf[(st3 * NZ + z) * T + tid], a.flag_idx + g);
-                cp_async8(&xbuf[(st3 * NZ + z) * T + tid], a.data + g);
-            }
-        }
-    };
-    auto issue_rec = [&](int q, int s, int e) {               // records of position q -> stage q%2
-        const int st3 = q % 3, st2 = q & 1;
-#pragma unroll
-        for (int z = 0; z < NZ; z++) {
-            if (s + z * T + tid < e) {
-                const int i = idxbuf[(st3 * NZ + z) * T + tid] & SP_ROW_MASK;
-                const double *src = a.rec + (size_t)i * stride;
-#pragma unroll
-                for (int h = 0; h < NCH; h++)
-                    cp_async16(&recbuf[((st2 * NZ + z) * NCH + h) * T + tid], src + 2 * h);
-            }
-        }
-    };
-
-    // pending position (terms computed, waiting for its scalar chain + write-back)
-    int pi[NZ];
-    double px[NZ], pr[NZ][R], pdA[NZ][ND];
-#pragma unroll
-    for (int z = 0; z < NZ; z++) pi[z] = -1;
-    // gradient / curvature terms of position q (slice [s,e), coefficient pold); `late` = after the
-    // write-back of position q-1 (then bit31-tagged records are re-read as well)
-    auto terms = [&](int q, int s, int e, double pold, bool late, double &tg, double &th) {
-        const int st3 = q % 3, st2 = q & 1;
-        tg = 0.0; th = 0.0;
-#pragma unroll
-        for (int z = 0; z < NZ; z++) {
-            pi[z] = -1;
-            if (s + z * T + tid < e) {
-                const int fi = idxbuf[(st3 * NZ + z) * T + tid];
-                const int i = fi & SP_ROW_MASK;
-                const unsigned stale = (unsigned)fi & (late ? (SP_FLAG_BIT | SP_FLAG2_BIT) : SP_FLAG2_BIT);
-                pi[z] = i;
-                px[z] = xbuf[(st3 * NZ + z) * T + tid];
-                if (stale) {
-                    load_rec<R>(a.rec + (size_t)i * stride, pr[z]);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < NCH; h++) {
-                        const double2 v = recbuf[((st2 * NZ + z) * NCH + h) * T + tid];
-                        pr[z][2 * h] = v.x;
-                        if (2 * h + 1 < R) pr[z][2 * h + 1] = v.y;
-                    }
-                }
-                nz_terms<KIND, DEG, LOSS, R, ND>(pr[z], px[z], pold, pdA[z], tg, th);
-            }
-        }
-        for (int g = s + NZ * T + tid; g < e; g += T) {       // slices longer than NZ*T (rare)
-            double rr[R], dd[ND];
-            load_rec<R>(a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride, rr);
-            nz_terms<KIND, DEG, LOSS, R, ND>(rr, a.data[g], pold, dd, tg, th);
-        }
-        tg = sp_warp_allsum(tg);
-        if (KIND != KIND_LINEAR) th = sp_warp_allsum(th);
-    };
-    // all-to-all: every warp writes its partial into every CTA's mailbox q%4
-    auto push = [&](int q, double tg, double th) {
-        const int b = q & (MBOX_DEPTH - 1);
-        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[b]), 16u * (uint32_t)NP);
-        if (C > 1) {
-            if (lane < C)
-                st_async_2f64(mapa_u32(smem_u32(&mbox[b * NP + c * W + warp]), (uint32_t)lane), tg, th,
-                              mapa_u32(smem_u32(&mbar[b]), (uint32_t)lane));
-        } else if (lane == 0) {
-            st_async_2f64(smem_u32(&mbox[b * NP + warp]), tg, th, smem_u32(&mbar[b]));
-        }
-    };
-
-    // ------------------------------------------------------------------ prologue
-    int s0, e0, s1, e1, s2, e2, s3 = 0, e3 = 0;
-    meta_se(0, s0, e0); meta_se(1, s1, e1); meta_se(2, s2, e2);
-    int jf0, jf1 = 0;
-    double pold0, cn0, pold1 = 0.0, cn1 = 0.0;
-    meta_val(0, jf0, pold0, cn0);
-    issue_idxval(0, s0, e0); issue_idxval(1, s1, e1); issue_idxval(2, s2, e2);
-    cp_async_commit(); cp_async_wait_all();
-    issue_rec(0, s0, e0); issue_rec(1, s1, e1);
-    cp_async_commit(); cp_async_wait_all();
-    if (d > 0) {
-        double tg, th;
-        terms(0, s0, e0, pold0, false, tg, th);
-        push(0, tg, th);
-    }
-
-    for (int t = 0; t < d; t++) {
-        // ---- a/b: staged data of t+1 (records) and t+2 (indices) has landed; stage the next ones
-        cp_async_wait_all();
-        meta_se(t + 3, s3, e3);
-        issue_rec(t + 2, s2, e2);
-        issue_idxval(t + 3, s3, e3);
-        cp_async_commit();
-        // ---- c: early partial sums of t+1 (columns t and t+1 sample-disjoint)
-        meta_val(t + 1, jf1, pold1, cn1);
-        const bool have_next = t + 1 < d;
-        const bool conf1 = jf1 < 0;
-        // keep position t's pending registers: the terms of t+1 overwrite pi/px/pr/pdA
-        int ci[NZ];
-        double cx[NZ], cr[NZ][R], cdA[NZ][ND];
-#pragma unroll
-        for (int z = 0; z < NZ; z++) {
-            ci[z] = pi[z]; cx[z] = px[z];
-#pragma unroll
-            for (int u = 0; u < R; u++) cr[z][u] = pr[z][u];
-#pragma unroll
-            for (int u = 0; u < ND; u++) cdA[z][u] = pdA[z][u];
-        }
-        if (have_next && !conf1) {
-            double tg, th;
-            terms(t + 1, s1, e1, pold1, false, tg, th);
-            push(t + 1, tg, th);
-        }
-        // ---- d: position t: collect the partials, scalar chain, write-back
-        mbar_wait(smem_u32(&mbar[t & (MBOX_DEPTH - 1)]), (uint32_t)((t >> 2) & 1));
-        double g0 = 0.0, h0 = 0.0, g1 = 0.0, h1 = 0.0;
-        {
-            const double2 *box = mbox + (t & (MBOX_DEPTH - 1)) * NP;
-            int r = 0;
-            for (; r + 1 < NP; r += 2) {
-                const double2 v = box[r], u = box[r + 1];
-                g0 += v.x; h0 += v.y; g1 += u.x; h1 += u.y;
-            }
-            if (r < NP) { const double2 v = box[r]; g0 += v.x; h0 += v.y; }
-        }
-        const double tg = g0 + g1, th = h0 + h1;
-        const int j0 = jf0 & 0x7fffffff;
-
-        double pnew, upd;
-        if (KIND == KIND_LINEAR) {
-            double u = tg + ab * pold0;                       // cd_linear.py:19-22
-            const double inv = mu * cn0 + ab;
-            u = u / inv;
-            pnew = pold0 - u;
-            upd = u;
-        } else {
-            double inv = th * mu;                             // pcd.py:59-68 / pcd_all.py:34-41
-            inv = inv + ab;
-            double u = tg * lam;
-            u = u + ab * pold0;
-            u = u / inv;
-            double p = pold0 - eta * u;
-            double strength = eta * gamma / inv;
-            const double a_old = fabs(pold0);
-            if (reg == SP_REG_L1) {                           // l1.py:32-33
-                pnew = sp_soft_threshold(p, strength);
-            } else if (reg == SP_REG_SQL12) {                 // squaredl12.py:52-57, :47-50
-                const double dcache = cache[0] - a_old;
-                p = p / (1.0 + 2.0 * strength);
-                const double sign = p > 0.0 ? 1.0 : -1.0;
-                double m = fabs(p) - 2.0 * strength * dcache / (1.0 + 2.0 * strength);
-                if (!(m > 0.0)) m = 0.0;
-                pnew = sign * m;
-                cache[0] = cache[0] - a_old;
-                cache[0] = cache[0] + fabs(pnew);
-            } else {                                          // omegati.py:82-104
-                const double sign = p > 0.0 ? 1.0 : -1.0;
-                if (KIND == KIND_FM) {
-                    double dc[DEG + 1];
-                    dc[0] = 0.0; dc[1] = 1.0;
-#pragma unroll
-                    for (int deg = 2; deg <= DEG; deg++) {
-                        double v = cache[deg - 1];
-                        v = v - dc[deg - 1] * a_old;
-                        if (v < 0.0) v = 0.0;
-                        dc[deg] = v;
-                    }
-                    strength = strength * dc[DEG];
-                    double m = fabs(p) - strength;
-                    if (!(m > 0.0)) m = 0.0;
-                    pnew = sign * m;
-                    const double a_new = fabs(pnew);
-#pragma unroll
-                    for (int deg = 1; deg < DEG; deg++) cache[deg] = dc[deg + 1] + dc[deg] * a_new;
-                } else {
-                    cache[0] = cache[0] / (1.0 + a_old);
-                    strength = strength * cache[0];
-                    double m = fabs(p) - strength;
-                    if (!(m > 0.0)) m = 0.0;
-                    pnew = sign * m;
-                    cache[0] = cache[0] * (1.0 + fabs(pnew));
-                }
-            }
-            upd = pold0 - pnew;
-        }
-        viol += fabs(upd);
-        if (c == 0 && tid == 0) a.prow[j0] = pnew;
-
-        if (KIND == KIND_ALL || upd != 0.0) {
-#pragma unroll
-            for (int z = 0; z < NZ; z++)
-                if (ci[z] >= 0)
-                    nz_scatter<KIND, DEG, R, ND>(a.rec + (size_t)ci[z] * stride, cr[z], cdA[z], cx[z], lam, upd,
-                                                 pold0, pnew);
-            for (int g = s0 + NZ * T + tid; g < e0; g += T) {
-                double rr[R], dd[ND];
-                double *p = a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride;
-                const double x = a.data[g];
-                load_rec<R>(p, rr);
-                dd[0] = x;
-                if (KIND == KIND_FM) {
-#pragma unroll
-                    for (int u = 1; u < ND; u++) dd[u] = x * (rr[1 + u] - pold0 * dd[u - 1]);
-                }
-                nz_scatter<KIND, DEG, R, ND>(p, rr, dd, x, lam, upd, pold0, pnew);
-            }
-        }
-        // ---- e: the write-back must be visible before tagged records are re-read / re-staged
-        if (W > 1) __syncthreads(); else __syncwarp();
-        // ---- f: late partial sums of t+1 (the columns share samples)
-        if (have_next && conf1) {
-            double tg2, th2;
-            terms(t + 1, s1, e1, pold1, true, tg2, th2);
-            push(t + 1, tg2, th2);
-        }
-        // ---- g: rotate
-        s0 = s1; e0 = e1; s1 = s2; e1 = e2; s2 = s3; e2 = e3;
-        jf0 = jf1; pold0 = pold1; cn0 = cn1;
-        if (((t + 1) & 31) == 0) {                            // entering the next chunk of positions
-            chunk_base = t + 1;
+    auto meta_advance = [&](int t_next) {                     // entering the next chunk of positions
+        if ((t_next & 31) == 0) {
+            chunk_base = t_next;
             mcur = mnxt;
             mnxt = mnx2;
             meta_load_val<KIND>(mnxt, a, chunk_base + 32, lane);
             meta_load_ptr(mnx2, a, chunk_base + 64, c, lane);
         }
-    }
+    };
 
-    if (c == 0 && tid == 0) {
-        *a.viol = viol;
-        if (KIND != KIND_LINEAR) {
+    if (scalar_role) {
+        // =============================================================== scalar-chain warp
+        const double mu = sp_mu<LOSS>();
+        const double ab = a.ab, gamma = a.gamma, eta = a.eta;
+        const int reg = a.reg;
+        double viol = *a.viol;
+        double cache[NC];
 #pragma unroll
-            for (int t = 0; t < NC; t++) a.regstate[t] = cache[t];
+        for (int t = 0; t < NC; t++) cache[t] = a.regstate[t];
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < MBOX_DEPTH; b++)
+                if (b < d) mbar_arrive_expect_tx(smem_u32(&mbar[b]), 16u * (uint32_t)NP);
         }
+        for (int t = 0; t < d; t++) {
+            int jf0;
+            double pold0, cn0;
+            meta_val(t, jf0, pold0, cn0);
+            const int b = t & (MBOX_DEPTH - 1);
+            mbar_wait(smem_u32(&mbar[b]), (uint32_t)((t >> 2) & 1));
+            double g0 = 0.0, h0 = 0.0, g1 = 0.0, h1 = 0.0;
+            {
+                const double2 *box = mbox + b * NP;
+                int r = 0;
+                for (; r + 1 < NP; r += 2) {
+                    const double2 v = box[r], u = box[r + 1];
+                    g0 += v.x; h0 += v.y; g1 += u.x; h1 += u.y;
+                }
+                if (r < NP) { const double2 v = box[r]; g0 += v.x; h0 += v.y; }
+            }
+            __syncwarp();
+            // the mailbox has been read by every lane: re-arm it for position t+4
+            if (lane == 0 && t + MBOX_DEPTH < d) mbar_arrive_expect_tx(smem_u32(&mbar[b]), 16u * (uint32_t)NP);
+            const double tg = g0 + g1, th = h0 + h1;
+            const int j0 = jf0 & 0x7fffffff;
+
+            double pnew, upd;
+            if (KIND == KIND_LINEAR) {
+                double u = tg + ab * pold0;                       // cd_linear.py:19-22
+                const double inv = mu * cn0 + ab;
+                u = u / inv;
+                pnew = pold0 - u;
+                upd = u;
+            } else {
+                double inv = th * mu;                             // pcd.py:59-68 / pcd_all.py:34-41
+                inv = inv + ab;
+                double u = tg * lam;
+                u = u + ab * pold0;
+                u = u / inv;
+                double p = pold0 - eta * u;
+                double strength = eta * gamma / inv;
+                const double a_old = fabs(pold0);
+                if (reg == SP_REG_L1) {                           // l1.py:32-33
+                    pnew = sp_soft_threshold(p, strength);
+                } else if (reg == SP_REG_SQL12) {                 // squaredl12.py:52-57, :47-50
+                    const double dcache = cache[0] - a_old;
+                    p = p / (1.0 + 2.0 * strength);
+                    const double sign = p > 0.0 ? 1.0 : -1.0;
+                    double m = fabs(p) - 2.0 * strength * dcache / (1.0 + 2.0 * strength);
+                    if (!(m > 0.0)) m = 0.0;
+                    pnew = sign * m;
+                    cache[0] = cache[0] - a_old;
+                    cache[0] = cache[0] + fabs(pnew);
+                } else {                                          // omegati.py:82-104
+                    const double sign = p > 0.0 ? 1.0 : -1.0;
+                    if (KIND == KIND_FM) {
+                        double dc[DEG + 1];
+                        dc[0] = 0.0; dc[1] = 1.0;
+#pragma unroll
+                        for (int deg = 2; deg <= DEG; deg++) {
+                            double v = cache[deg - 1];
+                            v = v - dc[deg - 1] * a_old;
+                            if (v < 0.0) v = 0.0;
+                            dc[deg] = v;
+                        }
+                        strength = strength * dc[DEG];
+                        double m = fabs(p) - strength;
+                        if (!(m > 0.0)) m = 0.0;
+                        pnew = sign * m;
+                        const double a_new = fabs(pnew);
+#pragma unroll
+                        for (int deg = 1; deg < DEG; deg++) cache[deg] = dc[deg + 1] + dc[deg] * a_new;
+                    } else {
+                        cache[0] = cache[0] / (1.0 + a_old);
+                        strength = strength * cache[0];
+                        double m = fabs(p) - strength;
+                        if (!(m > 0.0)) m = 0.0;
+                        pnew = sign * m;
+                        cache[0] = cache[0] * (1.0 + fabs(pnew));
+                    }
+                }
+                upd = pold0 - pnew;
+            }
+            viol += fabs(upd);
+            if (lane == 0) {
+                res[b] = make_double2(upd, pnew);
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rbar[b])) : "memory");
+                if (c == 0) a.prow[j0] = pnew;
+            }
+            meta_advance(t + 1);
+        }
+        if (c == 0 && lane == 0) {
+            *a.viol = viol;
+            if (KIND != KIND_LINEAR) {
+#pragma unroll
+                for (int t = 0; t < NC; t++) a.regstate[t] = cache[t];
+            }
+        }
+    } else {
+        // =============================================================== gather warps
+        auto issue_idxval = [&](int q, int s, int e) {            // idx / value of position q -> stage q%3
+            const int st3 = q % 3;
+#pragma unroll
+            for (int z = 0; z < NZ; z++) {
+                const int g = s + z * T + tid;
+                if (g < e) {
+                    cp_async4(&idxbuf[(st3 * NZ + z) * T + tid], a.flag_idx + g);
+                    cp_async8(&xbuf[(st3 * NZ + z) * T + tid], a.data + g);
+                }
+            }
+        };
+        auto issue_rec = [&](int q, int s, int e) {               // records of position q -> stage q%2
+            const int st3 = q % 3, st2 = q & 1;
+#pragma unroll
+            for (int z = 0; z < NZ; z++) {
+                if (s + z * T + tid < e) {
+                    const int i = idxbuf[(st3 * NZ + z) * T + tid] & SP_ROW_MASK;
+                    const double *src = a.rec + (size_t)i * stride;
+#pragma unroll
+                    for (int h = 0; h < NCH; h++)
+                        cp_async16(&recbuf[((st2 * NZ + z) * NCH + h) * T + tid], src + 2 * h);
+                }
+            }
+        };
+        // pending position (terms computed, waiting for its scalar chain + write-back)
+        int pi[NZ];
+        double px[NZ], pr[NZ][R], pdA[NZ][ND];
+#pragma unroll
+        for (int z = 0; z < NZ; z++) pi[z] = -1;
+        // gradient / curvature terms of position q; `late` = after the write-back of position q-1
+        // (then bit31-tagged records are re-read as well)
+        auto terms = [&](int q, int s, int e, double pold, bool late, double &tg, double &th) {
+            const int st3 = q % 3, st2 = q & 1;
+            tg = 0.0; th = 0.0;
+#pragma unroll
+            for (int z = 0; z < NZ; z++) {
+                pi[z] = -1;
+                if (s + z * T + tid < e) {
+                    const int fi = idxbuf[(st3 * NZ + z) * T + tid];
+                    const int i = fi & SP_ROW_MASK;
+                    const unsigned stale = (unsigned)fi & (late ? (SP_FLAG_BIT | SP_FLAG2_BIT) : SP_FLAG2_BIT);
+                    pi[z] = i;
+                    px[z] = xbuf[(st3 * NZ + z) * T + tid];
+                    if (stale) {
+                        load_rec<R>(a.rec + (size_t)i * stride, pr[z]);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < NCH; h++) {
+                            const double2 v = recbuf[((st2 * NZ + z) * NCH + h) * T + tid];
+                            pr[z][2 * h] = v.x;
+                            if (2 * h + 1 < R) pr[z][2 * h + 1] = v.y;
+                        }
+                    }
+                    nz_terms<KIND, DEG, LOSS, R, ND>(pr[z], px[z], pold, pdA[z], tg, th);
+                }
+            }
+            for (int g = s + NZ * T + tid; g < e; g += T) {       // slices longer than NZ*T (rare)
+                double rr[R], dd[ND];
+                load_rec<R>(a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride, rr);
+                nz_terms<KIND, DEG, LOSS, R, ND>(rr, a.data[g], pold, dd, tg, th);
+            }
+            tg = sp_warp_allsum(tg);
+            if (KIND != KIND_LINEAR) th = sp_warp_allsum(th);
+        };
+        // all-to-all: every gather warp writes its partial into every CTA's mailbox q%4
+        auto push = [&](int q, double tg, double th) {
+            const int b = q & (MBOX_DEPTH - 1);
+            if (C > 1) {
+                if (lane < C)
+                    st_async_2f64(mapa_u32(smem_u32(&mbox[b * NP + c * W + warp]), (uint32_t)lane), tg, th,
+                                  mapa_u32(smem_u32(&mbar[b]), (uint32_t)lane));
+            } else if (lane == 0) {
+                st_async_2f64(smem_u32(&mbox[b * NP + warp]), tg, th, smem_u32(&mbar[b]));
+            }
+        };
+        auto gather_barrier = [&]() {
+            if (W > 1) asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+            else __syncwarp();
+        };
+
+        // ---- prologue
+        int s0, e0, s1, e1, s2, e2, s3 = 0, e3 = 0;
+        meta_se(0, s0, e0); meta_se(1, s1, e1); meta_se(2, s2, e2);
+        int jf0, jf1 = 0;
+        double pold0, cn0, pold1 = 0.0, cn1 = 0.0;
+        meta_val(0, jf0, pold0, cn0);
+        issue_idxval(0, s0, e0); issue_idxval(1, s1, e1); issue_idxval(2, s2, e2);
+        cp_async_commit(); cp_async_wait_all();
+        issue_rec(0, s0, e0); issue_rec(1, s1, e1);
+        cp_async_commit(); cp_async_wait_all();
+        if (d > 0) {
+            double tg, th;
+            terms(0, s0, e0, pold0, false, tg, th);
+            push(0, tg, th);
+        }
+        for (int t = 0; t < d; t++) {
+            // ---- staged data of t+1 (records) and t+2 (indices) has landed; stage the next ones
+            cp_async_wait_all();
+            meta_se(t + 3, s3, e3);
+            issue_rec(t + 2, s2, e2);
+            issue_idxval(t + 3, s3, e3);
+            cp_async_commit();
+            meta_val(t + 1, jf1, pold1, cn1);
+            const bool have_next = t + 1 < d;
+            const bool conf1 = jf1 < 0;
+            // keep position t's pending registers: the terms of t+1 overwrite pi/px/pr/pdA
+            int ci[NZ];
+            double cx[NZ], cr[NZ][R], cdA[NZ][ND];
+#pragma unroll
+            for (int z = 0; z < NZ; z++) {
+                ci[z] = pi[z]; cx[z] = px[z];
+#pragma unroll
+                for (int u = 0; u < R; u++) cr[z][u] = pr[z][u];
+#pragma unroll
+                for (int u = 0; u < ND; u++) cdA[z][u] = pdA[z][u];
+            }
+            // ---- early partial sums of t+1 (columns t and t+1 sample-disjoint)
+            if (have_next && !conf1) {
+                double tg, th;
+                terms(t + 1, s1, e1, pold1, false, tg, th);
+                push(t + 1, tg, th);
+            }
+            // ---- result of position t from the scalar warp, write-back
+            const int b = t & (MBOX_DEPTH - 1);
+            mbar_wait(smem_u32(&rbar[b]), (uint32_t)((t >> 2) & 1));
+            const double2 rs = res[b];
+            const double upd = rs.x, pnew = rs.y;
+            if (KIND == KIND_ALL || upd != 0.0) {
+#pragma unroll
+                for (int z = 0; z < NZ; z++)
+                    if (ci[z] >= 0)
+                        nz_scatter<KIND, DEG, R, ND>(a.rec + (size_t)ci[z] * stride, cr[z], cdA[z], cx[z], lam, upd,
+                                                     pold0, pnew);
+                for (int g = s0 + NZ * T + tid; g < e0; g += T) {
+                    double rr[R], dd[ND];
+                    double *p = a.rec + (size_t)(a.flag_idx[g] & SP_ROW_MASK) * stride;
+                    const double x = a.data[g];
+                    load_rec<R>(p, rr);
+                    dd[0] = x;
+                    if (KIND == KIND_FM) {
+#pragma unroll
+                        for (int u = 1; u < ND; u++) dd[u] = x * (rr[1 + u] - pold0 * dd[u - 1]);
+                    }
+                    nz_scatter<KIND, DEG, R, ND>(p, rr, dd, x, lam, upd, pold0, pnew);
+                }
+            }
+            // ---- the write-back must be visible before tagged records are re-read / re-staged
+            gather_barrier();
+            // ---- late partial sums of t+1 (the columns share samples)
+            if (have_next && conf1) {
+                double tg2, th2;
+                terms(t + 1, s1, e1, pold1, true, tg2, th2);
+                push(t + 1, tg2, th2);
+            }
+            s0 = s1; e0 = e1; s1 = s2; e1 = e2; s2 = s3; e2 = e3;
+            jf0 = jf1; pold0 = pold1; cn0 = cn1;
+            meta_advance(t + 1);
+        }
+        cp_async_wait_all();
     }
-    cp_async_wait_all();
+    __syncthreads();
     if (C > 1) cluster_sync_all();   // no CTA may exit while peers can still write its smem
 }
 
@@ -469,7 +506,7 @@ int launch_sweep(const SweepArgs &a, int threads, cudaStream_t st) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.C, 1, 1);
-    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads + 32, 1, 1);      // gather warps + the scalar-chain warp
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
