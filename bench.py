@@ -342,8 +342,13 @@ def run_sweep_workload(name, args, rank, world, local):
         "gpu_launches": int(sum(cnt)),
         "kernel_ms": {"rows": ms[0], "regcache": ms[1], "sweep_pcd": ms[2], "sweep_pbcd": ms[3]},
         "clocks": clocks, "p_nonzero_frac": nz_frac,
-        "geometry": {"n_cta": est._dev_state["plan"].n_cta, "threads": est._dev_state["plan"].threads},
+        "geometry": ({"sweep": "window", **est._dev_state["plan"].wplan.stats}
+                     if getattr(est._dev_state["plan"], "mode", "cluster") == "window" else
+                     {"sweep": "cluster", "n_cta": est._dev_state["plan"].n_cta,
+                      "threads": est._dev_state["plan"].threads}),
     }
+    if result["geometry"]["sweep"] == "window" and name == "pcd":
+        result["roofline"]["kernel"] = "wsweep_kernel (pcd_window.cu)"
     del est, epoch, sync
     torch.cuda.empty_cache()
 

@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 1
+#define SP_ABI_VERSION 2
+#define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
 
 typedef void *sp_stream;
 
@@ -62,7 +63,28 @@ typedef struct sp_plan {
                                  it occurs in the one before that */
     const int32_t *idx_feat;  /* [d] coordinate order (indices_feature in the reference) */
     const int32_t *pos_conf;  /* [d] 1 when the columns at positions t-1 and t share a sample */
+    const struct sp_wplan *win; /* non-NULL: run sp_pcd_epoch / sp_cd_linear_epoch as the
+                                 pipelined window sweep (the cluster fields above are ignored) */
 } sp_plan;
+
+/* Window plan of the pipelined sweep (built by sp_wplan_flag + sp_wplan_fill; wplan.cu).  The
+ * coordinate order is cut into windows of `window` positions.  A nonzero is HOT when its sample
+ * has another nonzero in a column visited within `horizon` windows; hot nonzeros are handled by
+ * one engine CTA that keeps the window's hot sample records in shared memory slots, cold ones by
+ * all other CTAs in bulk. */
+typedef struct sp_wplan {
+    int32_t window, horizon, n_windows, slot_cap;
+    const int32_t *cflag;     /* [nnz] CSC row index | 0x80000000 when the nonzero is hot */
+    const int32_t *ht_ptr;    /* [d+1] offsets of the hot nonzeros of position t */
+    const int32_t *h_slot;    /* [n_hot] slot of the sample within its window */
+    const int32_t *h_dep;     /* [n_hot] window-local position that last touched the slot, or -1 */
+    const double *h_x;        /* [n_hot] value */
+    const int32_t *n_slots;   /* [n_windows] distinct hot samples */
+    const int32_t *slot_row;  /* [n_windows*slot_cap] sample index of every slot */
+    int32_t *sync;            /* [2*(n_windows+2)+2] scratch counters (zeroed by every sweep) */
+    double *res;              /* [2*d] scratch: (update, new value) per position */
+    double *base;             /* [2*d] scratch: cold partial sums (g, h) per position */
+} sp_wplan;
 
 int sp_abi_version(void);
 const char *sp_last_error(void);
@@ -84,6 +106,24 @@ int sp_plan_partition(const sp_dataset *ds, int n_cta, int32_t *col_part, sp_str
 /* position table + hazard flags for the order idx_feat (call again after every shuffle) */
 int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part, const int32_t *idx_feat,
                   int32_t *pos_ptr, int32_t *flag_idx, int32_t *pos_conf, sp_stream stream);
+/* Window plan, step 1: pos_scratch [d]; cflag [nnz] and hot_count [d] (hot nonzeros per position)
+ * are written.  The caller turns hot_count into ht_ptr (exclusive prefix sum, d+1 entries). */
+int sp_wplan_flag(const sp_dataset *ds, const int32_t *idx_feat, int window, int horizon,
+                  int32_t *pos_scratch, int32_t *cflag, int32_t *hot_count, sp_stream stream);
+/* Window plan, step 2: fills h_slot / h_dep / h_x [ht_ptr[d]], n_slots [n_windows], slot_row
+ * [n_windows*slot_cap]; *overflow is set to 1 when a window has more than slot_cap distinct hot
+ * samples (retry with a smaller window). */
+int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap,
+                  const int32_t *cflag, const int32_t *ht_ptr, int32_t *h_slot, int32_t *h_dep,
+                  double *h_x, int32_t *n_slots, int32_t *slot_row, int32_t *overflow,
+                  sp_stream stream);
+/* debug: cycle counters of the window sweep's roles (zeros unless the library was built with
+ * -DSP_WPROF); out_host [16] */
+int sp_wprof_read(unsigned long long *out_host);
+/* debug: per-position timestamps of window 100 of the last sweep; out_host [SP_WINDOW_MAX*8] */
+int sp_wtrace_read(long long *out_host);
+/* slots (hot sample records) the engine CTA can hold in shared memory for records of this stride */
+int sp_wplan_slot_cap(int rec_stride);
 /* out[c*rows+r] = in[r*cols+c] */
 int sp_transpose_f64(const double *in, double *out, int rows, int cols, sp_stream stream);
 /* doubles per sample record {y_pred, y, A^1..A^(m-1)} for a model of this top degree */

@@ -27,10 +27,18 @@ class SpDataset(C.Structure):
                 ("csc_indptr", _vp), ("csc_indices", _vp), ("csc_data", _vp)]
 
 
+class SpWPlan(C.Structure):
+    """struct sp_wplan (include/sparsepoly_b200.h)."""
+    _fields_ = [("window", C.c_int32), ("horizon", C.c_int32), ("n_windows", C.c_int32),
+                ("slot_cap", C.c_int32), ("cflag", _vp), ("ht_ptr", _vp), ("h_slot", _vp), ("h_dep", _vp),
+                ("h_x", _vp), ("n_slots", _vp), ("slot_row", _vp), ("sync", _vp), ("res", _vp),
+                ("base", _vp)]
+
+
 class SpPlan(C.Structure):
     """struct sp_plan (include/sparsepoly_b200.h)."""
     _fields_ = [("n_cta", C.c_int32), ("threads", C.c_int32), ("pos_ptr", _vp), ("flag_idx", _vp),
-                ("idx_feat", _vp), ("pos_conf", _vp)]
+                ("idx_feat", _vp), ("pos_conf", _vp), ("win", C.POINTER(SpWPlan))]
 
 
 _DSP = C.POINTER(SpDataset)
@@ -47,6 +55,11 @@ SIGNATURES = {
     "sp_col_norm_sq": (_i, [_DSP, _vp, _vp]),
     "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
     "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sp_wplan_flag": (_i, [_DSP, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sp_wplan_fill": (_i, [_DSP, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sp_wplan_slot_cap": (_i, [_i]),
+    "sp_wprof_read": (_i, [C.POINTER(C.c_ulonglong)]),
+    "sp_wtrace_read": (_i, [C.POINTER(C.c_longlong)]),
     "sp_transpose_f64": (_i, [_vp, _vp, _i, _i, _vp]),
     "sp_rec_stride": (_i, [_i]),
     "sp_predict": (_i, [_DSP, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
@@ -89,7 +102,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sp_abi_version() != 1:
+    if lib.sp_abi_version() != 2:
         raise ImportError("libsparsepoly_b200.so ABI version mismatch")
     _LIB = lib
     return lib

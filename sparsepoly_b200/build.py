@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INC = os.path.join(HERE, "..", "include")
 OUT = os.path.join(HERE, "libsparsepoly_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["errors.cu", "rows.cu", "plan.cu", "regcache.cu", "pcd.cu", "pbcd.cu", "psgd.cu"]
+SOURCES = ["errors.cu", "rows.cu", "plan.cu", "regcache.cu", "wplan.cu", "pcd.cu", "pcd_window.cu", "pbcd.cu", "psgd.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC]
 
@@ -44,10 +44,13 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
+    extra = ["-DSP_WPROF=" + os.environ["SP_WPROF"]] if os.environ.get("SP_WPROF") else []     # debug: engine cycle accounting
+    if os.environ.get("SP_BACKOFF_NS"):
+        extra.append("-DSP_BACKOFF_NS=" + os.environ["SP_BACKOFF_NS"])
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -25,6 +25,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t addr, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
     asm volatile(
         "{\n"

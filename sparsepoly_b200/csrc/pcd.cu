@@ -23,15 +23,18 @@
 //     31/30 of flag_idx) and re-read from global memory after the barrier.
 #include "common.cuh"
 #include "cluster.cuh"
+#include "pcd_common.cuh"
 #include "sparsepoly_b200.h"
 
 int sp_rows_precompute_one(const sp_dataset *ds, const double *p_s, int degree, double *rec,
                            int rec_stride, cudaStream_t st);
 int sp_launch_reg_cache(int mode, int degree, int d, const double *v, double *regstate, cudaStream_t st);
+int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat, int degree, double *prow,
+              const double *cns, const double *lam_ptr, double ab, double gamma, double eta, int reg,
+              int loss, double *rec, int rec_stride, double *regstate, double *viol, cudaStream_t st);
 
 namespace {
 
-enum { KIND_LINEAR = 0, KIND_FM = 1, KIND_ALL = 2 };
 constexpr int SWEEP_MAX_THREADS = 256;
 constexpr int SWEEP_MAX_CTAS = 16;
 constexpr int MBOX_DEPTH = 4;
@@ -66,54 +69,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *g) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int R> __device__ __forceinline__ void load_rec(const double *p, double (&r)[R]) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-#pragma unroll
-    for (int u = 0; u < R / 2; u++) { double2 v = q[u]; r[2 * u] = v.x; r[2 * u + 1] = v.y; }
-    if (R & 1) r[R - 1] = p[R - 1];
-}
-
-// per-nonzero gradient terms.  r = {y_pred, y, A^1.. }.  dA[] keeps the chain for the write-back.
-template <int KIND, int DEG, int LOSS, int R, int ND>
-__device__ __forceinline__ void nz_terms(const double (&r)[R], double x, double pold, double (&dA)[ND],
-                                         double &tg, double &th) {
-    const double dl = sp_dloss<LOSS>(r[0], r[1]);
-    if (KIND == KIND_LINEAR) {
-        dA[0] = x;
-        tg += dl * x;                                        // cd_linear.py:18
-    } else if (KIND == KIND_FM) {
-        dA[0] = x;                                           // pcd.py:8-12
-#pragma unroll
-        for (int t = 1; t < DEG; t++) dA[t] = x * (r[1 + t] - pold * dA[t - 1]);
-        tg += dl * dA[DEG - 1];                              // pcd.py:56-57
-        th += dA[DEG - 1] * dA[DEG - 1];
-    } else {
-        dA[0] = x * r[2] / (1.0 + x * pold);                 // pcd_all.py:29-31
-        tg += dl * dA[0];
-        th += dA[0] * dA[0];
-    }
-}
-
-// write-back of one sample after the coordinate moved by upd = p_old - p_new
-template <int KIND, int DEG, int R, int ND>
-__device__ __forceinline__ void nz_scatter(double *p, const double (&r)[R], const double (&dA)[ND], double x,
-                                           double lam, double upd, double pold, double pnew) {
-    if (KIND == KIND_LINEAR) {
-        p[0] = r[0] - upd * x;                               // cd_linear.py:31
-    } else if (KIND == KIND_FM) {
-#pragma unroll
-        for (int t = 1; t < DEG; t++) p[1 + t] = r[1 + t] - upd * dA[t - 1];   // pcd.py:129-130
-        p[0] = r[0] - (lam * upd) * dA[DEG - 1];             // pcd.py:133
-    } else {
-        double yp = r[0] - lam * r[2];                       // pcd_all.py:95-98
-        double A = r[2] / (1.0 + x * pold);
-        A = A * (1.0 + x * pnew);
-        yp = yp + lam * A;
-        p[2] = A;
-        p[0] = yp;
-    }
-}
 
 // 32 positions of the per-position table, one per lane
 struct MetaChunk {
@@ -537,6 +492,13 @@ int dispatch_loss(int loss, const SweepArgs &a, int threads, int nz, cudaStream_
 }
 
 int check_plan(const sp_dataset *ds, const sp_plan *plan, const char *who) {
+    if (ds && plan && plan->win) {                      // window sweep: only the order is needed
+        if (!ds->csc_data || !ds->csc_indptr || !plan->idx_feat) {
+            sp_set_error("%s: dataset/plan pointers missing", who);
+            return SP_ERR_INVALID;
+        }
+        return SP_OK;
+    }
     if (!ds || !plan || !ds->csc_data || !plan->pos_ptr || !plan->flag_idx || !plan->idx_feat ||
         !plan->pos_conf) {
         sp_set_error("%s: dataset/plan pointers missing", who);
@@ -578,6 +540,9 @@ extern "C" int sp_cd_linear_epoch(const sp_dataset *ds, const sp_plan *plan, dou
         return SP_ERR_INVALID;
     }
     if (ds->n_features == 0) return SP_OK;
+    if (plan->win)
+        return sp_wsweep(ds, plan->win, plan->idx_feat, 1, w, col_norm_sq, nullptr, alpha, 0.0, 1.0, SP_REG_L1,
+                         loss, rec, rec_stride, viol, viol, (cudaStream_t)stream);
     SweepArgs a = {};
     a.d = ds->n_features; a.C = plan->n_cta;
     a.pos_ptr = plan->pos_ptr; a.flag_idx = plan->flag_idx; a.data = ds->csc_data;
@@ -619,7 +584,7 @@ extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P
     const int d = ds->n_features;
     if (d == 0) return SP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nz = pick_nz(ds, plan);
+    const int nz = plan->win ? 1 : pick_nz(ds, plan);
     for (int ss = 0; ss < k; ss++) {
         const int s = idx_comp_host[ss];
         if (s < 0 || s >= k) { sp_set_error("sp_pcd_epoch: bad component index %d", s); return SP_ERR_INVALID; }
@@ -630,6 +595,12 @@ extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P
             const int mode = (reg == SP_REG_SQL12) ? 0 : (degree == -1 ? 2 : 1);
             rc = sp_launch_reg_cache(mode, degree, d, prow, regstate, st);
             if (rc) return rc;
+        }
+        if (plan->win) {
+            rc = sp_wsweep(ds, plan->win, plan->idx_feat, degree, prow, nullptr, lams + s, beta, gamma, eta, reg,
+                           loss, rec, rec_stride, regstate, viol, st);
+            if (rc) return rc;
+            continue;
         }
         SweepArgs a = {};
         a.d = d; a.C = plan->n_cta;

@@ -1,0 +1,615 @@
+// Pipelined window sweep: the same coordinate descent as pcd.cu (reference optimizer/pcd.py:33-137,
+// pcd_all.py:21-102, cd_linear.py:8-33), organised so that the only strictly sequential work per
+// coordinate is the ~10-flop regularizer chain.
+//
+// One persistent cooperative launch per sweep (one CTA per SM):
+//   * CTA 0 is the ENGINE.  Per window of B positions it holds the records of the window's hot
+//     samples in shared-memory slots (wplan.cu).  Warp 0 runs the scalar chain (prox_cd + cache,
+//     in coordinate order, state in registers); warps 1.. are workers, worker k owning positions
+//     k, k+W, ... : gradient terms of the position's hot nonzeros (waiting, per nonzero, on the
+//     write-back flag of the position that last touched its slot), + the cold partial sums, the
+//     Newton step and the two divisions, handed to the chain warp through a 16-byte {value, tag}
+//     cell; then the write-back of the hot records once the chain warp has published the update.
+//   * CTAs 1.. are BULK workers: BASE(w) reduces the cold nonzeros of window w's columns to
+//     (g, h) per position; WB(w) applies the published updates to the cold records.  With horizon
+//     H = 1 a cold record is untouched for a whole window on either side, so BASE(w) runs while
+//     the engine is still in window w-1 and the engine never waits for the bulk CTAs.
+//   * windows are handed over through three counters in global memory (release / acquire).
+// Per-sample terms are computed exactly as the reference does; only the order in which a column's
+// terms are summed differs (as in any parallel reduction).
+#include "common.cuh"
+#include "cluster.cuh"
+#include "pcd_common.cuh"
+#include "sparsepoly_b200.h"
+
+namespace {
+
+constexpr int WT = 512;                        // threads per CTA: chain warp + 15 worker warps
+constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 3 * 4 + 2 * 8) + 64;
+constexpr int W_REC_BYTES = 196608;            // shared memory reserved for the hot record slots
+
+struct WArgs {
+    int d, B, H, nwin, slot_cap, stride, reg;
+    const int32_t *indptr;       // CSC
+    const int32_t *cflag;
+    const double *data;
+    const int32_t *idx_feat;
+    const int32_t *ht_ptr, *h_slot, *h_dep;
+    const double *h_x;
+    const int32_t *n_slots, *slot_row;
+    const double *prow;          // P[s, :] (or w): read-only during the sweep
+    const double *cns;
+    const double *lam_ptr;
+    double ab, gamma, eta;
+    double *rec;
+    double *regstate, *viol;
+    double2 *res, *base;
+    int *base_cnt, *wb_cnt, *eng_done;
+};
+
+struct __align__(16) Cell { double v; long long tag; };
+#ifndef SP_BACKOFF_NS
+#define SP_BACKOFF_NS 0
+#endif
+#define SP_BACKOFF if (SP_BACKOFF_NS) __nanosleep(SP_BACKOFF_NS);
+
+// Optional cycle accounting of the engine roles (build with -DSP_WPROF; read with sp_wprof_read).
+enum { TP_ENG_WAIT = 0, TP_ENG_STAGE, TP_ENG_ROLE, TP_ENG_FLUSH, TP_CH_WAIT, TP_CH_COMP, TP_WK_LOAD, TP_WK_DEP,
+       TP_WK_TERMS, TP_WK_RED, TP_WK_RESWAIT, TP_WK_WB, TP_BULK_WAITB, TP_BULK_BASE, TP_BULK_WAITW, TP_BULK_WB,
+       TP_N };
+__device__ unsigned long long g_wprof[TP_N];
+__device__ long long g_wtrace[SP_WINDOW_MAX * 8];   // per-position timestamps of window 100 (SP_WPROF)
+#if defined(SP_WPROF) && SP_WPROF >= 2
+#define TP_DECL unsigned long long tp_acc[TP_N] = {}; long long tp_t0 = clock64();
+#define TP_MARK(id) { const long long tp_t1 = clock64(); tp_acc[id] += (unsigned long long)(tp_t1 - tp_t0); tp_t0 = tp_t1; }
+#define TP_FLUSH(cond) if (cond) { for (int i_ = 0; i_ < TP_N; i_++) if (tp_acc[i_]) atomicAdd(&g_wprof[i_], tp_acc[i_]); }
+#else
+#define TP_DECL
+#define TP_MARK(id) {}
+#define TP_FLUSH(cond) {}
+#endif
+#ifdef SP_WPROF
+#define TR(w_, tl_, k_) if ((w_) == 100 && lane == 0) g_wtrace[(tl_) * 8 + (k_)] = clock64();
+#define TRD(w_, tl_, k_, v_) { asm volatile("" ::"d"(v_) : "memory"); TR(w_, tl_, k_) }
+#else
+#define TR(w_, tl_, k_) {}
+#define TRD(w_, tl_, k_, v_) {}
+#endif
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(int *p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_ge(const int *p, int v) {
+    while (ld_acquire(p) < v) {}
+}
+// bulk CTAs: poll with a back-off (147 CTAs hammering one L2 line slow the engine's own traffic)
+__device__ __forceinline__ void wait_ge_sleep(const int *p, int v) {
+    while (ld_acquire(p) < v) __nanosleep(64);
+}
+__device__ __forceinline__ Cell cell_load(const Cell *c) {
+    Cell r;
+    unsigned long long a, b;
+    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_u32(c)) : "memory");
+    r.v = __longlong_as_double((long long)a);
+    r.tag = (long long)b;
+    return r;
+}
+__device__ __forceinline__ void cell_store(Cell *c, double v, long long tag) {
+    asm volatile("st.volatile.shared.v2.b64 [%0], {%1, %2};" ::"r"(smem_u32(c)),
+                 "l"(__double_as_longlong(v)), "l"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ int flag_load(const int *p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_store(int *p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+template <int R> __device__ __forceinline__ void load_rec_cg(const double *p, double (&r)[R]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int u = 0; u < (R + 1) / 2; u++) {
+        const double2 v = __ldcg(q + u);
+        r[2 * u] = v.x;
+        if (2 * u + 1 < R) r[2 * u + 1] = v.y;
+    }
+}
+// stores the R used doubles; records are padded to an even stride, the pad lane is rewritten
+// with whatever was loaded (pad[R] for odd R)
+template <int R> __device__ __forceinline__ void store_rec_cg(double *p, const double (&r)[R], double pad) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int u = 0; u < (R + 1) / 2; u++) {
+        double2 v;
+        v.x = r[2 * u];
+        v.y = (2 * u + 1 < R) ? r[2 * u + 1] : pad;
+        __stcg(q + u, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------- bulk CTAs
+template <int KIND, int DEG, int LOSS>
+__device__ void bulk_role(const WArgs &a, int b, int nbulk) {
+    constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
+    constexpr int R = 2 + NA;
+    constexpr int ND = (KIND == KIND_FM) ? DEG : 1;
+    __shared__ double red[2][WT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = a.stride;
+    const double lam = (KIND == KIND_LINEAR) ? 1.0 : *a.lam_ptr;
+    TP_DECL
+    for (int w = 0; w < a.nwin + a.H; w++) {
+        if (w < a.nwin) {
+            // ---- BASE(w): cold records of window w were last written in window <= w-H-1
+            if (tid == 0) {
+                if (w - 1 - a.H >= 0) wait_ge_sleep(a.wb_cnt + (w - 1 - a.H), nbulk);
+                wait_ge_sleep(a.eng_done, w - a.H);
+            }
+            __syncthreads();
+            TP_MARK(TP_BULK_WAITB)
+            const int t0 = w * a.B, nb = min(a.B, a.d - t0);
+            for (int tl = b; tl < nb; tl += nbulk) {
+                const int t = t0 + tl, j = a.idx_feat[t];
+                const double pold = a.prow[j];
+                double tg = 0.0, th = 0.0;
+                for (int g = a.indptr[j] + tid; g < a.indptr[j + 1]; g += WT) {
+                    const int fi = a.cflag[g];
+                    if (fi >= 0) {
+                        double r[R], dA[ND];
+                        load_rec_cg<R>(a.rec + (size_t)fi * stride, r);
+                        nz_terms<KIND, DEG, LOSS, R, ND>(r, a.data[g], pold, dA, tg, th);
+                    }
+                }
+                tg = sp_warp_allsum(tg);
+                th = sp_warp_allsum(th);
+                if (lane == 0) { red[0][warp] = tg; red[1][warp] = th; }
+                __syncthreads();
+                if (tid == 0) {
+                    double sg = 0.0, sh = 0.0;
+#pragma unroll
+                    for (int q = 0; q < WT / 32; q++) { sg += red[0][q]; sh += red[1][q]; }
+                    __stcg(a.base + t, make_double2(sg, sh));
+                }
+                __syncthreads();
+            }
+            if (tid == 0) { __threadfence(); red_release_add(a.base_cnt + w, 1); }
+            TP_MARK(TP_BULK_BASE)
+        }
+        const int wv = w - a.H;
+        if (wv >= 0) {
+            // ---- WB(wv): apply the published updates to the cold records of window wv
+            if (tid == 0) wait_ge_sleep(a.eng_done, wv + 1);
+            __syncthreads();
+            TP_MARK(TP_BULK_WAITW)
+            const int t0 = wv * a.B, nb = min(a.B, a.d - t0);
+            for (int tl = b; tl < nb; tl += nbulk) {
+                const int t = t0 + tl, j = a.idx_feat[t];
+                const double2 rs = __ldcg(a.res + t);
+                const double upd = rs.x, pnew = rs.y;
+                if (KIND != KIND_ALL && upd == 0.0) continue;
+                const double pold = a.prow[j];
+                for (int g = a.indptr[j] + tid; g < a.indptr[j + 1]; g += WT) {
+                    const int fi = a.cflag[g];
+                    if (fi >= 0) {
+                        double r[R], dA[ND];
+                        double *p = a.rec + (size_t)fi * stride;
+                        load_rec_cg<R>(p, r);
+                        const double pad = (R & 1) ? __ldcg(p + R) : 0.0;
+                        const double x = a.data[g];
+                        nz_dA<KIND, DEG, R, ND>(r, x, pold, dA);
+                        nz_update<KIND, DEG, R, ND>(r, dA, x, lam, upd, pold, pnew);
+                        store_rec_cg<R>(p, r, pad);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { __threadfence(); red_release_add(a.wb_cnt + wv, 1); }
+            TP_MARK(TP_BULK_WB)
+        }
+    }
+    TP_FLUSH(tid == 0 && b == 0)
+}
+
+// ---------------------------------------------------------------------------------- engine CTA
+template <int KIND, int DEG, int LOSS>
+__device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) {
+    constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
+    constexpr int R = 2 + NA;
+    constexpr int NCH = (R + 1) / 2;
+    constexpr int ND = (KIND == KIND_FM) ? DEG : 1;
+    constexpr int NC = (KIND == KIND_FM) ? DEG : 1;
+    constexpr int BM = SP_WINDOW_MAX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = a.stride, d = a.d, B = a.B;
+    const double lam = (KIND == KIND_LINEAR) ? 1.0 : *a.lam_ptr;
+    const double mu = sp_mu<LOSS>();
+    const double ab = a.ab, gamma = a.gamma, eta = a.eta;
+
+    double *recs = reinterpret_cast<double *>(smem_raw);                       // [slot_cap*stride]
+    double *ent_x = recs + (size_t)a.slot_cap * stride;                        // [2*slot_cap] values
+    int *ent_sd = reinterpret_cast<int *>(ent_x + 2 * (size_t)a.slot_cap);     // [2*slot_cap] slot | (dep+1)<<16
+    Cell *cellA = reinterpret_cast<Cell *>(smem_raw + W_REC_BYTES);            // [BM] worker -> chain
+    Cell *cellB = cellA + BM;                                                  // [BM]
+    Cell *rcell = cellB + BM;                                                  // [BM] chain -> worker
+    double2 *base_s = reinterpret_cast<double2 *>(rcell + BM);                 // [BM]
+    double *pold_s = reinterpret_cast<double *>(base_s + BM);                  // [BM]
+    double *cn_s = pold_s + BM;                                                // [BM]
+    unsigned long long *mb_res = reinterpret_cast<unsigned long long *>(cn_s + BM);   // [BM] result published
+    unsigned long long *mb_wb = mb_res + BM;                                   // [BM] write-back done
+    int *hp_s = reinterpret_cast<int *>(mb_wb + BM);                           // [BM+1]
+    int *wbflag = hp_s + BM + 1;                                               // [BM]
+
+    for (int i = tid; i < BM; i += WT) {
+        cellA[i].tag = -1; cellB[i].tag = -1; rcell[i].tag = -1;
+        wbflag[i] = 0;
+        mbar_init(smem_u32(&mb_res[i]), 1);
+        mbar_init(smem_u32(&mb_wb[i]), 1);
+    }
+    // chain-warp state
+    double viol = 0.0, cache[NC];
+    if (warp == 0) {
+        viol = *a.viol;
+#pragma unroll
+        for (int t = 0; t < NC; t++) cache[t] = (KIND == KIND_LINEAR) ? 0.0 : a.regstate[t];
+    }
+    __syncthreads();
+    TP_DECL
+
+    for (int w = 0; w < a.nwin; w++) {
+        const int t0 = w * B, nb = min(B, d - t0);
+        const int wtag = w + 1;
+        if (tid == 0) {
+            wait_ge(a.base_cnt + w, nbulk);
+            if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
+        }
+        __syncthreads();
+        if (tid == 32) TP_MARK(TP_ENG_WAIT)
+        // ---- stage the window: per-position scalars, the hot nonzeros and the hot sample records
+        const int h0 = a.ht_ptr[t0];
+        for (int tl = tid; tl < nb; tl += WT) {
+            const int t = t0 + tl, j = a.idx_feat[t];
+            pold_s[tl] = a.prow[j];
+            cn_s[tl] = (KIND == KIND_LINEAR) ? a.cns[j] : 0.0;
+            base_s[tl] = __ldcg(a.base + t);
+            hp_s[tl] = a.ht_ptr[t] - h0;
+            if (tl == nb - 1) hp_s[nb] = a.ht_ptr[t + 1] - h0;
+        }
+        {
+            const int nh = a.ht_ptr[t0 + nb] - h0;
+            for (int e = tid; e < nh; e += WT) {
+                ent_x[e] = a.h_x[h0 + e];
+                ent_sd[e] = a.h_slot[h0 + e] | ((a.h_dep[h0 + e] + 1) << 16);
+            }
+        }
+        const int ns = a.n_slots[w];
+        const int32_t *srow = a.slot_row + (size_t)w * a.slot_cap;
+        {
+            constexpr int SU = (NCH <= 2) ? 8 : 4;           // independent record gathers in flight per thread
+            for (int s0 = 0; s0 < ns; s0 += WT * SU) {
+                int rows[SU];
+                double2 v[SU][NCH];
+#pragma unroll
+                for (int u = 0; u < SU; u++) {
+                    const int sl = s0 + u * WT + tid;
+                    rows[u] = sl < ns ? srow[sl] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < SU; u++)
+                    if (rows[u] >= 0) {
+                        const double2 *src = reinterpret_cast<const double2 *>(a.rec + (size_t)rows[u] * stride);
+#pragma unroll
+                        for (int h = 0; h < NCH; h++) v[u][h] = __ldcg(src + h);
+                    }
+#pragma unroll
+                for (int u = 0; u < SU; u++)
+                    if (rows[u] >= 0) {
+                        double2 *dst = reinterpret_cast<double2 *>(recs + (size_t)(s0 + u * WT + tid) * stride);
+#pragma unroll
+                        for (int h = 0; h < NCH; h++) dst[h] = v[u][h];
+                    }
+            }
+        }
+        __syncthreads();
+        if (tid == 32) TP_MARK(TP_ENG_STAGE)
+        if (tid != 32) TP_MARK(TP_ENG_WAIT)
+
+        if (warp == 0) {
+            // =========================================================== scalar chain, in order
+            Cell ca = cell_load(&cellA[0]), cb = cell_load(&cellB[0]);
+            double pold = pold_s[0];
+            for (int tl = 0; tl < nb; tl++) {
+                const long long t = t0 + tl;
+                while (ca.tag != t) ca = cell_load(&cellA[tl]);
+                if (KIND != KIND_LINEAR) {
+                    while (cb.tag != t) cb = cell_load(&cellB[tl]);
+                }
+                TP_MARK(TP_CH_WAIT)
+                TR(w, tl, 3)
+                // inputs of the next position: in flight while this one is computed
+                const int tn = tl + 1 < nb ? tl + 1 : tl;
+                const Cell na = cell_load(&cellA[tn]), nbb = cell_load(&cellB[tn]);
+                const double npold = pold_s[tn];
+                double pnew, upd;
+                if (KIND == KIND_LINEAR) {
+                    pnew = pold - ca.v;                              // cd_linear.py:24
+                    upd = ca.v;
+                } else {
+                    pnew = prox_chain<KIND, DEG, NC>(a.reg, ca.v, cb.v, pold, cache);
+                    upd = pold - pnew;                               // pcd.py:121
+                }
+                viol += fabs(upd);
+                if (lane == 0) {
+                    cell_store(&rcell[tl], KIND == KIND_ALL ? pnew : upd, t);
+                    mbar_arrive(smem_u32(&mb_res[tl]));
+                    __stcg(a.res + t, make_double2(upd, pnew));
+                }
+                ca = na; cb = nbb; pold = npold;
+                TP_MARK(TP_CH_COMP)
+                TR(w, tl, 4)
+            }
+        } else {
+            // =========================================================== workers
+            const int W = WT / 32 - 1, wk = warp - 1;
+            for (int tl = wk; tl < nb; tl += W) {
+                const long long t = t0 + tl;
+                const int hs = hp_s[tl], ne = hp_s[tl + 1] - hs;
+                const double pold = pold_s[tl];
+                double tg = 0.0, th = 0.0;
+                TR(w, tl, 0)
+                int k_slot = -1;
+                double k_x = 0.0, k_r[R], k_dA[ND];
+                for (int q = 0; q < ne; q += 32) {
+                    const int e = q + lane;
+                    const bool act = e < ne;
+                    int slot = 0, dep = -1;
+                    double x = 0.0;
+                    if (act) {
+                        const int sd = ent_sd[hs + e];
+                        slot = sd & 0xffff; dep = (sd >> 16) - 1; x = ent_x[hs + e];
+                    }
+                    if (warp == 1) TP_MARK(TP_WK_LOAD)
+                    // wait (warp-uniformly) for the write-backs this round's records depend on
+                    const int mydep = (dep >= 0 && flag_load(&wbflag[dep]) != wtag) ? dep : -1;
+                    unsigned pending = __ballot_sync(0xffffffffu, mydep >= 0);
+                    while (pending) {
+                        const int src = __ffs(pending) - 1;
+                        const int dpos = __shfl_sync(0xffffffffu, mydep, src);
+                        mbar_wait(smem_u32(&mb_wb[dpos]), (uint32_t)(w & 1));
+                        pending &= pending - 1;
+                    }
+                    if (warp == 1) TP_MARK(TP_WK_DEP)
+                    if (act) {
+                        double r[R], dA[ND];
+                        load_rec<R>(recs + (size_t)slot * stride, r);
+                        nz_terms<KIND, DEG, LOSS, R, ND>(r, x, pold, dA, tg, th);
+                        if (q == 0) {
+                            k_slot = slot; k_x = x;
+#pragma unroll
+                            for (int u = 0; u < R; u++) k_r[u] = r[u];
+#pragma unroll
+                            for (int u = 0; u < ND; u++) k_dA[u] = dA[u];
+                        }
+                    }
+                }
+                if (warp == 1) TP_MARK(TP_WK_TERMS)
+                __syncwarp();
+                TRD(w, tl, 1, tg + th)
+                tg = sp_warp_allsum(tg);
+                if (KIND != KIND_LINEAR) th = sp_warp_allsum(th);
+                TRD(w, tl, 7, tg + th)
+                const double2 bs = base_s[tl];
+                tg = tg + bs.x;
+                th = th + bs.y;
+                double v0, v1 = 0.0;
+                if (KIND == KIND_LINEAR) {
+                    double u = tg + ab * pold;                       // cd_linear.py:19-22
+                    const double inv = mu * cn_s[tl] + ab;
+                    v0 = u / inv;
+                } else {
+                    double inv = th * mu;                            // pcd.py:59-68 / pcd_all.py:34-41
+                    inv = inv + ab;
+                    double u = tg * lam;
+                    u = u + ab * pold;
+                    u = u / inv;
+                    v0 = pold - eta * u;
+                    v1 = eta * gamma / inv;
+                }
+                if (lane == 0) {
+                    if (KIND != KIND_LINEAR) cell_store(&cellB[tl], v1, t);
+                    cell_store(&cellA[tl], v0, t);
+                }
+                if (warp == 1) TP_MARK(TP_WK_RED)
+                TRD(w, tl, 2, v0 + v1)
+                Cell rc;
+                mbar_wait(smem_u32(&mb_res[tl]), (uint32_t)(w & 1));
+                rc = cell_load(&rcell[tl]);
+                if (warp == 1) TP_MARK(TP_WK_RESWAIT)
+                TR(w, tl, 5)
+                double upd, pnew;
+                if (KIND == KIND_ALL) { pnew = rc.v; upd = pold - pnew; }
+                else { upd = rc.v; pnew = 0.0; }
+                if (KIND == KIND_ALL || upd != 0.0) {
+                    for (int q = 0; q < ne; q += 32) {
+                        const int e = q + lane;
+                        if (e < ne) {
+                            if (q == 0) {
+                                nz_update<KIND, DEG, R, ND>(k_r, k_dA, k_x, lam, upd, pold, pnew);
+                                double *dst = recs + (size_t)k_slot * stride;
+                                dst[0] = k_r[0];
+#pragma unroll
+                                for (int u = 2; u < R; u++) dst[u] = k_r[u];
+                            } else {
+                                const int slot = ent_sd[hs + e] & 0xffff;
+                                const double x = ent_x[hs + e];
+                                double r[R], dA[ND];
+                                double *dst = recs + (size_t)slot * stride;
+                                load_rec<R>(dst, r);
+                                nz_dA<KIND, DEG, R, ND>(r, x, pold, dA);
+                                nz_update<KIND, DEG, R, ND>(r, dA, x, lam, upd, pold, pnew);
+                                dst[0] = r[0];
+#pragma unroll
+                                for (int u = 2; u < R; u++) dst[u] = r[u];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();                      // the write-back above before the flag
+                    flag_store(&wbflag[tl], wtag);
+                    mbar_arrive(smem_u32(&mb_wb[tl]));          // wakes the lanes sleeping on this position
+                }
+                if (warp == 1) TP_MARK(TP_WK_WB)
+                TR(w, tl, 6)
+            }
+        }
+        __syncthreads();
+        if (tid == 32) TP_MARK(TP_ENG_ROLE)
+        // ---- flush the hot records, publish the window
+        for (int s = tid; s < ns; s += WT) {
+            double2 *dst = reinterpret_cast<double2 *>(a.rec + (size_t)srow[s] * stride);
+            const double2 *src = reinterpret_cast<const double2 *>(recs + (size_t)s * stride);
+#pragma unroll
+            for (int h = 0; h < NCH; h++) __stcg(dst + h, src[h]);
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); st_release(a.eng_done, w + 1); }
+        if (tid == 32) TP_MARK(TP_ENG_FLUSH)
+    }
+    TP_FLUSH(tid == 0 || tid == 32)
+    if (warp == 0 && lane == 0) {
+        *a.viol = viol;
+        if (KIND != KIND_LINEAR) {
+#pragma unroll
+            for (int t = 0; t < NC; t++) a.regstate[t] = cache[t];
+        }
+    }
+}
+
+template <int KIND, int DEG, int LOSS>
+__global__ void __launch_bounds__(WT, 1) wsweep_kernel(const WArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbulk = gridDim.x - 1;
+    if (blockIdx.x == 0) engine_role<KIND, DEG, LOSS>(a, smem_raw, nbulk);
+    else bulk_role<KIND, DEG, LOSS>(a, blockIdx.x - 1, nbulk);
+}
+
+// prow[idx_feat[t]] = new value of position t (the sweep itself never writes P / w: the bulk
+// CTAs read the old values until the last write-back)
+__global__ void apply_res_kernel(int d, const int32_t *__restrict__ idx_feat, const double2 *__restrict__ res,
+                                 double *prow) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d; t += gridDim.x * blockDim.x)
+        prow[idx_feat[t]] = res[t].y;
+}
+
+int g_sm_count = 0;
+
+template <int KIND, int DEG, int LOSS>
+int launch_wsweep(WArgs a, double *prow_out, cudaStream_t st) {
+    auto kern = wsweep_kernel<KIND, DEG, LOSS>;
+    const size_t smem = (size_t)W_REC_BYTES + W_AUX_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return sp_check_cuda(e, "cudaFuncSetAttribute(wsweep_kernel)");
+    if (g_sm_count == 0) {
+        int dev = 0;
+        SP_CUDA(cudaGetDevice(&dev));
+        SP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int nbulk = a.B < a.d ? a.B : a.d;
+    if (nbulk > g_sm_count - 1) nbulk = g_sm_count - 1;
+    if (nbulk < 1) nbulk = 1;
+    SP_CUDA(cudaMemsetAsync(a.base_cnt, 0, sizeof(int) * (2 * (size_t)(a.nwin + 2) + 2), st));
+    void *params[] = {(void *)&a};
+    sp_prof_begin(SP_PROF_SWEEP_PCD, st);
+    cudaError_t le = cudaLaunchCooperativeKernel((void *)kern, dim3(nbulk + 1), dim3(WT), params, smem, st);
+    if (le == cudaSuccess) {
+        apply_res_kernel<<<(a.d + 255) / 256 > 1184 ? 1184 : (a.d + 255) / 256, 256, 0, st>>>(
+            a.d, a.idx_feat, a.res, prow_out);
+        le = cudaGetLastError();
+    }
+    sp_prof_end(st);
+    return sp_check_cuda(le, "wsweep_kernel launch");
+}
+
+template <int KIND, int DEG>
+int wdispatch_loss(int loss, const WArgs &a, double *prow_out, cudaStream_t st) {
+    switch (loss) {
+    case SP_LOSS_SQUARED: return launch_wsweep<KIND, DEG, SP_LOSS_SQUARED>(a, prow_out, st);
+    case SP_LOSS_LOGISTIC: return launch_wsweep<KIND, DEG, SP_LOSS_LOGISTIC>(a, prow_out, st);
+    case SP_LOSS_SQHINGE: return launch_wsweep<KIND, DEG, SP_LOSS_SQHINGE>(a, prow_out, st);
+    default: sp_set_error("unknown loss id %d", loss); return SP_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// cycle counters of the engine roles since the last call (all zero unless built with -DSP_WPROF)
+extern "C" int sp_wprof_read(unsigned long long *out_host /*[16]*/) {
+    unsigned long long z[TP_N] = {};
+    SP_CUDA(cudaDeviceSynchronize());
+    SP_CUDA(cudaMemcpyFromSymbol(out_host, g_wprof, sizeof(z)));
+    SP_CUDA(cudaMemcpyToSymbol(g_wprof, z, sizeof(z)));
+    return SP_OK;
+}
+
+extern "C" int sp_wtrace_read(long long *out_host /*[SP_WINDOW_MAX*8]*/) {
+    SP_CUDA(cudaDeviceSynchronize());
+    SP_CUDA(cudaMemcpyFromSymbol(out_host, g_wtrace, sizeof(long long) * SP_WINDOW_MAX * 8));
+    return SP_OK;
+}
+
+extern "C" int sp_wplan_slot_cap(int rec_stride) {
+    if (rec_stride < 2) rec_stride = 2;
+    return W_REC_BYTES / (rec_stride * 8 + 24);    // + room for 2 hot nonzeros (12 B each) per slot
+}
+
+// degree: 1 = linear (cd_linear), -1 = all-subsets, 2..SP_MAXDEG = ANOVA
+int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat, int degree, double *prow,
+              const double *cns, const double *lam_ptr, double ab, double gamma, double eta, int reg,
+              int loss, double *rec, int rec_stride, double *regstate, double *viol, cudaStream_t st) {
+    if (!wp->cflag || !wp->ht_ptr || !wp->h_slot || !wp->h_dep || !wp->h_x || !wp->n_slots || !wp->slot_row ||
+        !wp->sync || !wp->res || !wp->base) {
+        sp_set_error("window plan: missing buffers");
+        return SP_ERR_INVALID;
+    }
+    if (wp->window < 1 || wp->window > SP_WINDOW_MAX || wp->horizon < 0 || wp->horizon > 1 ||
+        wp->slot_cap > sp_wplan_slot_cap(rec_stride) || wp->slot_cap > 32768) {
+        sp_set_error("window plan: window %d / horizon %d / slot_cap %d invalid for record stride %d",
+                     wp->window, wp->horizon, wp->slot_cap, rec_stride);
+        return SP_ERR_INVALID;
+    }
+    WArgs a = {};
+    a.d = ds->n_features; a.B = wp->window; a.H = wp->horizon; a.nwin = wp->n_windows;
+    a.slot_cap = wp->slot_cap; a.stride = rec_stride; a.reg = reg;
+    a.indptr = ds->csc_indptr; a.cflag = wp->cflag; a.data = ds->csc_data; a.idx_feat = idx_feat;
+    a.ht_ptr = wp->ht_ptr; a.h_slot = wp->h_slot; a.h_dep = wp->h_dep; a.h_x = wp->h_x;
+    a.n_slots = wp->n_slots; a.slot_row = wp->slot_row;
+    a.prow = prow; a.cns = cns; a.lam_ptr = lam_ptr; a.ab = ab; a.gamma = gamma; a.eta = eta;
+    a.rec = rec; a.regstate = regstate; a.viol = viol;
+    a.res = reinterpret_cast<double2 *>(wp->res);
+    a.base = reinterpret_cast<double2 *>(wp->base);
+    a.base_cnt = wp->sync;
+    a.wb_cnt = wp->sync + (a.nwin + 2);
+    a.eng_done = wp->sync + 2 * (a.nwin + 2);
+    switch (degree) {
+    case 1: return wdispatch_loss<KIND_LINEAR, 1>(loss, a, prow, st);
+    case -1: return wdispatch_loss<KIND_ALL, 1>(loss, a, prow, st);
+    case 2: return wdispatch_loss<KIND_FM, 2>(loss, a, prow, st);
+    case 3: return wdispatch_loss<KIND_FM, 3>(loss, a, prow, st);
+    case 4: return wdispatch_loss<KIND_FM, 4>(loss, a, prow, st);
+    case 5: return wdispatch_loss<KIND_FM, 5>(loss, a, prow, st);
+    }
+    sp_set_error("window sweep: degree %d unsupported", degree);
+    return SP_ERR_UNSUPPORTED;
+}

@@ -171,12 +171,118 @@ def choose_geometry(ds, solver, n_cta=None, threads=None):
     return int(n_cta), int(threads)
 
 
+WINDOW_SIZES = (256, 128, 64, 32, 16, 8, 4, 2, 1)
+
+
+class WindowPlan:
+    """struct sp_wplan: the window plan of the pipelined pcd / cd_linear sweep (csrc/wplan.cu,
+    csrc/pcd_window.cu).  build() returns False when no window size fits (then the cluster sweep
+    is used)."""
+
+    def __init__(self, ds, rec_stride, window=None, horizon=None, min_window=8):
+        import os
+        self.ds = ds
+        self.lib = _lib.load()
+        self.slot_cap = min(8192, int(self.lib.sp_wplan_slot_cap(int(rec_stride))))
+        env_b = os.environ.get("SPARSEPOLY_B200_WINDOW")
+        env_h = os.environ.get("SPARSEPOLY_B200_HORIZON")
+        self.window = int(env_b) if (window is None and env_b) else window
+        self.horizon = int(env_h) if (horizon is None and env_h) else (1 if horizon is None else horizon)
+        self.min_window = min_window
+        self.max_hot_frac = 0.5
+        dev, d = ds.device, ds.n_features
+        self.pos = torch.empty(max(d, 1), dtype=torch.int32, device=dev)
+        self.cflag = torch.empty(max(ds.nnz, 1), dtype=torch.int32, device=dev)
+        self.hot_count = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
+        self.ht_ptr = torch.zeros(d + 1, dtype=torch.int32, device=dev)
+        self.res = torch.zeros(2 * max(d, 1), dtype=torch.float64, device=dev)
+        self.base = torch.zeros(2 * max(d, 1), dtype=torch.float64, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.struct = None
+        self.stats = {}
+
+    def _candidates(self):
+        if self.window is not None:
+            return [int(self.window)]
+        ds, H = self.ds, self.horizon
+        col = ds.nnz / max(ds.n_features, 1)
+        row = ds.nnz / max(ds.n_samples, 1)
+        out = []
+        for B in WINDOW_SIZES:
+            if B < self.min_window:
+                break
+            f = min(1.0, (2 * H + 1) * B * row / max(ds.n_features, 1))   # expected hot fraction
+            if f <= self.max_hot_frac and 0.75 * B * col * f <= self.slot_cap:
+                out.append(B)
+        return out
+
+    def _try(self, idx_feat, B):
+        ds, lib, d = self.ds, self.lib, self.ds.n_features
+        _lib.check(lib.sp_wplan_flag(ds.ref(), _ptr(idx_feat), B, self.horizon, _ptr(self.pos),
+                                     _ptr(self.cflag), _ptr(self.hot_count), _stream()))
+        self.ht_ptr[1:] = torch.cumsum(self.hot_count[:d], 0).to(torch.int32)
+        n_hot = int(self.ht_ptr[d].item())
+        if self.window is None and n_hot > self.max_hot_frac * max(ds.nnz, 1):
+            return False
+        n_windows = (d + B - 1) // B
+        dev = ds.device
+        self.h_slot = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
+        self.h_dep = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
+        self.h_x = torch.empty(max(n_hot, 1), dtype=torch.float64, device=dev)
+        self.n_slots = torch.zeros(n_windows, dtype=torch.int32, device=dev)
+        self.slot_row = torch.empty(n_windows * self.slot_cap, dtype=torch.int32, device=dev)
+        self.sync = torch.zeros(2 * (n_windows + 2) + 2, dtype=torch.int32, device=dev)
+        self.overflow.zero_()
+        _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap, _ptr(self.cflag),
+                                     _ptr(self.ht_ptr), _ptr(self.h_slot), _ptr(self.h_dep), _ptr(self.h_x),
+                                     _ptr(self.n_slots), _ptr(self.slot_row), _ptr(self.overflow), _stream()))
+        if int(self.overflow.item()):
+            return False
+        s = _lib.SpWPlan()
+        s.window, s.horizon, s.n_windows, s.slot_cap = B, self.horizon, n_windows, self.slot_cap
+        s.cflag, s.ht_ptr, s.h_slot, s.h_dep = (self.cflag.data_ptr(), self.ht_ptr.data_ptr(),
+                                                self.h_slot.data_ptr(), self.h_dep.data_ptr())
+        s.h_x, s.n_slots, s.slot_row = self.h_x.data_ptr(), self.n_slots.data_ptr(), self.slot_row.data_ptr()
+        s.sync, s.res, s.base = self.sync.data_ptr(), self.res.data_ptr(), self.base.data_ptr()
+        self.struct = s
+        self.stats = dict(window=B, horizon=self.horizon, n_windows=n_windows, n_hot=n_hot,
+                          hot_frac=n_hot / max(ds.nnz, 1), max_slots=int(self.n_slots.max().item()))
+        return True
+
+    def build(self, idx_feat):
+        self.struct = None
+        if self.ds.n_features == 0:
+            return False
+        for B in self._candidates():
+            if self._try(idx_feat, B):
+                return True
+        if self.window is not None:
+            raise ValueError(f"window plan: window={self.window} horizon={self.horizon} does not fit "
+                             f"{self.slot_cap} shared-memory slots")
+        return False
+
+
 class SweepPlan:
     """Coordinate-order plan (struct sp_plan): per-position column slices of every CTA and the
-    read-after-write hazard flags.  Rebuilt (cheaply, on device) whenever the order changes."""
+    read-after-write hazard flags.  Rebuilt (cheaply, on device) whenever the order changes.
 
-    def __init__(self, ds, solver="pcd", n_cta=None, threads=None):
+    sweep="window" (pcd / cd_linear only) additionally builds the WindowPlan of the pipelined
+    sweep; "auto" uses it when the columns are sparse enough for it to fit, "cluster" never.
+    Environment override: SPARSEPOLY_B200_SWEEP."""
+
+    def __init__(self, ds, solver="pcd", n_cta=None, threads=None, rec_stride=None, sweep=None):
+        import os
         self.ds = ds
+        if sweep is None:
+            sweep = os.environ.get("SPARSEPOLY_B200_SWEEP", "auto")
+        if solver != "pcd" or rec_stride is None:
+            sweep = "cluster"
+        self.sweep = sweep
+        self.wplan = None
+        if sweep in ("auto", "window"):
+            self.wplan = WindowPlan(ds, rec_stride, min_window=8 if sweep == "auto" else 1)
+            if sweep == "window" and self.wplan.window is None:
+                self.wplan.max_hot_frac = 2.0
         self.n_cta, self.threads = choose_geometry(ds, solver, n_cta, threads)
         dev = ds.device
         d, C_ = ds.n_features, self.n_cta
@@ -200,6 +306,12 @@ class SweepPlan:
             return
         self._order_host = idx.copy()
         self.idx_feat[: idx.size].copy_(torch.from_numpy(idx))
+        self.struct.win = None
+        self.mode = "cluster"
+        if self.wplan is not None and self.wplan.build(self.idx_feat):
+            self.struct.win = C.pointer(self.wplan.struct)
+            self.mode = "window"
+            return
         _lib.check(_lib.load().sp_plan_order(self.ds.ref(), self.n_cta, _ptr(self.col_part),
                                              _ptr(self.idx_feat), _ptr(self.pos_ptr),
                                              _ptr(self.flag_idx), _ptr(self.pos_conf), _stream()))

@@ -229,7 +229,7 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         k, m = self.n_components, self.degree
         alpha, beta, gamma = self._scaled(n)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
-        plan = SweepPlan(ds, "pcd")
+        plan = SweepPlan(ds, "pcd", rec_stride=solvers.rec_stride(m))
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         indices_feature = np.arange(d, dtype=np.int32)
         indices_component = np.arange(k, dtype=np.int32)
@@ -292,7 +292,7 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         alpha, beta, gamma = self._scaled(n)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
         plan = SweepPlan(ds, "pbcd")
-        plan_lin = SweepPlan(ds, "pcd") if self.fit_linear else None
+        plan_lin = SweepPlan(ds, "pcd", rec_stride=2) if self.fit_linear else None
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         indices_feature = np.arange(d, dtype=np.int32)
         plan.set_order(indices_feature)
@@ -574,7 +574,8 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
 
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
         self._h2d_bytes = ds.h2d_bytes
-        plan = SweepPlan(ds, self.solver)
+        plan = SweepPlan(ds, self.solver,
+                         rec_stride=solvers.rec_stride(-1) if self.solver == "pcd" else None)
         indices_feature = np.arange(d, dtype=np.int32)
         indices_component = np.arange(k, dtype=np.int32)
         plan.set_order(indices_feature)
@@ -588,6 +589,7 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
         rec[1::stride] = torch.from_numpy(y).to(dev)
         P_dk = solvers.transpose(P_kd)
         solvers.poly_predict(ds, P_dk, lams, -1, out=rec, out_stride=stride)     # _get_output
+        self._dev_state = dict(ds=ds, plan=plan, rec=rec, stride=stride, P=P_kd if pcd else P_dk)
         if not pcd:
             A = torch.empty(max(n * k, 1), dtype=_f64, device=dev)
             reg_norms = torch.zeros(max(d, 1), dtype=_f64, device=dev)

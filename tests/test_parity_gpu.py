@@ -67,6 +67,74 @@ def test_cluster_geometries_match_golden(name, n_cta, threads, monkeypatch):
         assert rel_err(est.w_, arr["w_"]) <= TOL
 
 
+# ------------------------------------------------------------- pipelined window sweep (pcd_window.cu)
+WINDOW_GEOMS = [(None, 0), (None, 1), (2, 1), (1, 0), (3, 0)]
+
+
+@pytest.mark.parametrize("window,horizon", WINDOW_GEOMS)
+@pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("pcd")])
+def test_window_sweep_matches_golden(name, window, horizon, monkeypatch):
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window")
+    monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    if window is not None:
+        monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
+    rec, X, arr = load_case(name)
+    est = _fit(_estimator(rec), X, arr["y"], arr.get("P_init"))
+    assert est._dev_state["plan"].mode == "window"
+    assert rel_err(est.P_, arr["P_"]) <= TOL
+    assert same_support(est.P_, arr["P_"])
+    if "w_" in arr:
+        assert rel_err(est.w_, arr["w_"]) <= TOL
+    assert est.n_iter_ == int(arr["n_iter_"])
+
+
+WINDOW_ORACLE = [
+    ("fm3_omegati_logistic", "anova", 3, True,
+     dict(degree=3, loss="logistic", n_components=4, solver="pcd", regularizer="omegati", beta=1e-6,
+          gamma=2e-9, alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True, fit_lower="explicit")),
+    ("fm2_sql12_squared", "anova", 2, False,
+     dict(degree=2, n_components=4, solver="pcd", regularizer="squaredl12", beta=1e-5, gamma=1e-6,
+          alpha=1e-3, max_iter=2, tol=-1.0, random_state=0, mean=True)),
+    ("fm4_l1_sqhinge_shuffle", "anova", 2, True,
+     dict(degree=4, loss="squared_hinge", n_components=3, solver="pcd", regularizer="l1", beta=1e-4,
+          gamma=1e-5, alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True, shuffle=True)),
+]
+
+
+@pytest.mark.parametrize("window,horizon", [(None, 1), (None, 0), (64, 0), (8, 1)])
+@pytest.mark.parametrize("tag,kernel,degree,clf,kw", WINDOW_ORACLE, ids=[c[0] for c in WINDOW_ORACLE])
+def test_window_sweep_sparse_matches_oracle(tag, kernel, degree, clf, kw, window, horizon, monkeypatch):
+    """columns share ~0.4 samples pairwise: most nonzeros are cold (bulk CTAs), the rest go through
+    the engine's shared-memory slots"""
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window" if window else "auto")
+    monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    if window is not None:
+        monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
+    X, y = _problem(n=100000, d=5000, r=10, seed=5, kernel=kernel, degree=degree, clf=clf)
+    est, out, frac = _compare_fm(kw, X, y)
+    plan = est._dev_state["plan"]
+    assert plan.mode == "window", plan.wplan.stats
+    assert 0.0 < plan.wplan.stats["hot_frac"] < 0.6
+    assert 0.01 < frac < 0.99
+    print(tag, plan.wplan.stats, "nonzero fraction of P_", frac)
+
+
+@pytest.mark.parametrize("horizon", [0, 1])
+def test_window_sweep_all_subsets_matches_oracle(horizon, monkeypatch):
+    import sparsepoly_b200 as S
+    from oracle import oracle as O
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "auto")
+    monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    X, y = _problem(n=100000, d=4000, r=8, seed=3, kernel="all", degree=2, clf=True)
+    kw = dict(loss="squared_hinge", n_components=4, solver="pcd", regularizer="omegati", beta=1e-4,
+              gamma=1e-5, mean=True, max_iter=2, tol=-1.0, random_state=0)
+    est = _fit(S.SparseAllSubsetsClassifier(**kw), X, y)
+    assert est._dev_state["plan"].mode == "window"
+    out = O.fit_all_subsets(X, y, **kw)
+    assert rel_err(est.P_, out["P_"]) <= TOL
+    assert same_support(est.P_, out["P_"])
+
+
 # ----------------------------------------------------------------------------- vs the C oracle
 def _problem(n, d, r, seed, kernel, degree, clf):
     from sparsepoly_b200 import synth
@@ -157,9 +225,11 @@ def test_predict_matches_oracle_and_kernels_module():
     assert np.array_equal(kernels.all_subsets_kernel(Xe, P), np.ones((5, 7)))
 
 
-def test_ragged_and_dense_columns():
+@pytest.mark.parametrize("sweep", ["cluster", "window"])
+def test_ragged_and_dense_columns(sweep, monkeypatch):
     """empty columns, one dense column (slice longer than a CTA: slow path), 1-sample data."""
     import sparsepoly_b200 as S
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", sweep)
     from oracle import oracle as O
     rng = np.random.RandomState(3)
     n, d = 700, 9
