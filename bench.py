@@ -36,11 +36,11 @@ if ROOT not in sys.path:
 WORKLOADS = {
     "pcd": dict(tag="C2", n=1_000_000, d=100_000, r=50, seed=1, k=16, degree=3, clf=True,
                 kw=dict(degree=3, loss="logistic", n_components=16, solver="pcd", regularizer="omegati",
-                        alpha=1e-6, beta=1e-6, gamma=1e-7, mean=True, fit_linear=True,
+                        alpha=1e-6, beta=1e-6, gamma=5e-10, mean=True, fit_linear=True,
                         fit_lower="explicit", shuffle=False, random_state=0, tol=-1.0)),
     "pbcd": dict(tag="C3", n=1_000_000, d=100_000, r=50, seed=2, k=32, degree=2, clf=False,
                  kw=dict(degree=2, n_components=32, solver="pbcd", regularizer="omegacs", alpha=1e-6,
-                         beta=1e-6, gamma=1e-7, mean=True, fit_linear=True, fit_lower="explicit",
+                         beta=1e-6, gamma=1e-8, mean=True, fit_linear=True, fit_lower="explicit",
                          shuffle=False, random_state=0, tol=-1.0)),
     "allsub": dict(tag="C4", n=500_000, d=20_000, r=20, seed=3, k=16, degree=-1, clf=True,
                    kw=dict(loss="squared_hinge", n_components=16, solver="pcd", regularizer="omegati",

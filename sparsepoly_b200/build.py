@@ -45,8 +45,8 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-DSP_WPROF=" + os.environ["SP_WPROF"]] if os.environ.get("SP_WPROF") else []     # debug: engine cycle accounting
-    if os.environ.get("SP_BACKOFF_NS"):
-        extra.append("-DSP_BACKOFF_NS=" + os.environ["SP_BACKOFF_NS"])
+    if os.environ.get("SP_DEFS"):                                     # debug: extra -D switches
+        extra += ["-D" + x for x in os.environ["SP_DEFS"].split(",")]
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))

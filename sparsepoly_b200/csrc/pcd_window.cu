@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int WT = 512;                        // threads per CTA: chain warp + 15 worker warps
+constexpr int WT = 384;                        // threads per CTA: chain warp + 11 worker warps (<= 168 regs)
 constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 3 * 4 + 2 * 8) + 64;
 constexpr int W_REC_BYTES = 196608;            // shared memory reserved for the hot record slots
 
@@ -106,6 +106,23 @@ __device__ __forceinline__ void cell_store(Cell *c, double v, long long tag) {
     asm volatile("st.volatile.shared.v2.b64 [%0], {%1, %2};" ::"r"(smem_u32(c)),
                  "l"(__double_as_longlong(v)), "l"(tag)
                  : "memory");
+}
+// same, on precomputed shared-window addresses (saves the cvta sequence in the hot loops)
+__device__ __forceinline__ void cell_load_a(uint32_t addr, double &v, int &tag) {
+    unsigned long long a, b;
+    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+    v = __longlong_as_double((long long)a);
+    tag = (int)b;
+}
+__device__ __forceinline__ void cell_store_a(uint32_t addr, double v, int tag) {
+    asm volatile("st.volatile.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(__double_as_longlong(v)),
+                 "l"((long long)tag)
+                 : "memory");
+}
+__device__ __forceinline__ double lds_f64_a(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ int flag_load(const int *p) {
     int v;
@@ -256,12 +273,13 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         mbar_init(smem_u32(&mb_res[i]), 1);
         mbar_init(smem_u32(&mb_wb[i]), 1);
     }
-    // chain-warp state
-    double viol = 0.0, cache[NC];
-    if (warp == 0) {
-        viol = *a.viol;
+    // chain-warp state (viol, regularizer cache): lives in shared memory between windows so that it
+    // only occupies registers inside the chain loop
+    __shared__ double chain_state[1 + SP_MAXDEG];
+    if (tid == 0) {
+        chain_state[0] = *a.viol;
 #pragma unroll
-        for (int t = 0; t < NC; t++) cache[t] = (KIND == KIND_LINEAR) ? 0.0 : a.regstate[t];
+        for (int t = 0; t < NC; t++) chain_state[1 + t] = (KIND == KIND_LINEAR) ? 0.0 : a.regstate[t];
     }
     __syncthreads();
     TP_DECL
@@ -326,95 +344,130 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
 
         if (warp == 0) {
             // =========================================================== scalar chain, in order
-            Cell ca = cell_load(&cellA[0]), cb = cell_load(&cellB[0]);
-            double pold = pold_s[0];
+            double viol = chain_state[0], cache[NC];
+#pragma unroll
+            for (int q = 0; q < NC; q++) cache[q] = chain_state[1 + q];
+            const int reg = a.reg;
+            uint32_t pa = smem_u32(cellA), pb = smem_u32(cellB), pr = smem_u32(rcell), pp = smem_u32(pold_s),
+                     pm = smem_u32(mb_res);
+            double2 *resg = a.res + t0;
+            const bool lane0 = lane == 0;
+            double va, vb = 0.0, pold;
+            int ta, tb;
+            cell_load_a(pa, va, ta);
+            cell_load_a(pb, vb, tb);
+            pold = lds_f64_a(pp);
             for (int tl = 0; tl < nb; tl++) {
-                const long long t = t0 + tl;
-                while (ca.tag != t) ca = cell_load(&cellA[tl]);
+                const int t = t0 + tl;
+                while (ta != t) cell_load_a(pa, va, ta);
                 if (KIND != KIND_LINEAR) {
-                    while (cb.tag != t) cb = cell_load(&cellB[tl]);
+                    while (tb != t) cell_load_a(pb, vb, tb);
                 }
-                TP_MARK(TP_CH_WAIT)
                 TR(w, tl, 3)
-                // inputs of the next position: in flight while this one is computed
-                const int tn = tl + 1 < nb ? tl + 1 : tl;
-                const Cell na = cell_load(&cellA[tn]), nbb = cell_load(&cellB[tn]);
-                const double npold = pold_s[tn];
+                // inputs of the next position: in flight while this one is computed (stale tags of an
+                // earlier window never match)
+                double nva, nvb, npold;
+                int nta, ntb;
+                cell_load_a(pa + 16, nva, nta);
+                cell_load_a(pb + 16, nvb, ntb);
+                npold = lds_f64_a(pp + 8);
                 double pnew, upd;
                 if (KIND == KIND_LINEAR) {
-                    pnew = pold - ca.v;                              // cd_linear.py:24
-                    upd = ca.v;
+                    pnew = pold - va;                                // cd_linear.py:24
+                    upd = va;
                 } else {
-                    pnew = prox_chain<KIND, DEG, NC>(a.reg, ca.v, cb.v, pold, cache);
+                    pnew = prox_chain<KIND, DEG, NC>(reg, va, vb, pold, cache);
                     upd = pold - pnew;                               // pcd.py:121
                 }
-                viol += fabs(upd);
-                if (lane == 0) {
-                    cell_store(&rcell[tl], KIND == KIND_ALL ? pnew : upd, t);
-                    mbar_arrive(smem_u32(&mb_res[tl]));
-                    __stcg(a.res + t, make_double2(upd, pnew));
+                if (lane0) {
+                    cell_store_a(pr, KIND == KIND_ALL ? pnew : upd, t);
+                    mbar_arrive(pm);
+                    __stcg(resg + tl, make_double2(upd, pnew));
                 }
-                ca = na; cb = nbb; pold = npold;
-                TP_MARK(TP_CH_COMP)
+                viol += fabs(upd);
+                va = nva; vb = nvb; ta = nta; tb = ntb; pold = npold;
+                pa += 16; pb += 16; pr += 16; pp += 8; pm += 8;
                 TR(w, tl, 4)
+            }
+            if (lane0) {
+                chain_state[0] = viol;
+#pragma unroll
+                for (int q = 0; q < NC; q++) chain_state[1 + q] = cache[q];
             }
         } else {
             // =========================================================== workers
+            constexpr int KR = 2;                               // rounds of 32 hot nonzeros kept in registers
             const int W = WT / 32 - 1, wk = warp - 1;
+            const uint32_t wpar = (uint32_t)(w & 1);
             for (int tl = wk; tl < nb; tl += W) {
-                const long long t = t0 + tl;
+                const int t = t0 + tl;
                 const int hs = hp_s[tl], ne = hp_s[tl + 1] - hs;
                 const double pold = pold_s[tl];
+                const double2 bs = base_s[tl];
+                const double cn = cn_s[tl];
                 double tg = 0.0, th = 0.0;
                 TR(w, tl, 0)
-                int k_slot = -1;
-                double k_x = 0.0, k_r[R], k_dA[ND];
-                for (int q = 0; q < ne; q += 32) {
-                    const int e = q + lane;
-                    const bool act = e < ne;
-                    int slot = 0, dep = -1;
-                    double x = 0.0;
-                    if (act) {
-                        const int sd = ent_sd[hs + e];
-                        slot = sd & 0xffff; dep = (sd >> 16) - 1; x = ent_x[hs + e];
-                    }
-                    if (warp == 1) TP_MARK(TP_WK_LOAD)
-                    // wait (warp-uniformly) for the write-backs this round's records depend on
-                    const int mydep = (dep >= 0 && flag_load(&wbflag[dep]) != wtag) ? dep : -1;
-                    unsigned pending = __ballot_sync(0xffffffffu, mydep >= 0);
-                    while (pending) {
-                        const int src = __ffs(pending) - 1;
-                        const int dpos = __shfl_sync(0xffffffffu, mydep, src);
-                        mbar_wait(smem_u32(&mb_wb[dpos]), (uint32_t)(w & 1));
-                        pending &= pending - 1;
-                    }
-                    if (warp == 1) TP_MARK(TP_WK_DEP)
-                    if (act) {
-                        double r[R], dA[ND];
-                        load_rec<R>(recs + (size_t)slot * stride, r);
-                        nz_terms<KIND, DEG, LOSS, R, ND>(r, x, pold, dA, tg, th);
-                        if (q == 0) {
-                            k_slot = slot; k_x = x;
+                int k_slot[KR];
+                double k_x[KR], k_r[KR][R], k_dA[KR][ND];
 #pragma unroll
-                            for (int u = 0; u < R; u++) k_r[u] = r[u];
+                for (int u = 0; u < KR; u++) k_slot[u] = -1;
+                for (int q0 = 0; q0 < ne; q0 += 32 * KR) {
+                    int slot[KR], mydep[KR];
+                    double x[KR];
 #pragma unroll
-                            for (int u = 0; u < ND; u++) k_dA[u] = dA[u];
+                    for (int u = 0; u < KR; u++) {
+                        const int e = q0 + u * 32 + lane;
+                        slot[u] = -1; mydep[u] = -1; x[u] = 0.0;
+                        if (e < ne) {
+                            const int sd = ent_sd[hs + e];
+                            const int dep = (sd >> 16) - 1;
+                            slot[u] = sd & 0xffff;
+                            x[u] = ent_x[hs + e];
+                            if (dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
+                        }
+                    }
+                    // wait (warp-uniformly: divergent waits would leave the warp fragmented for the
+                    // shuffles below) for the write-backs these records depend on
+#pragma unroll
+                    for (int u = 0; u < KR; u++) {
+                        unsigned pending = __ballot_sync(0xffffffffu, mydep[u] >= 0);
+                        while (pending) {
+                            const int src = __ffs(pending) - 1;
+                            const int dpos = __shfl_sync(0xffffffffu, mydep[u], src);
+#ifdef SP_SPIN_WAIT
+                            while (flag_load(&wbflag[dpos]) != wtag) {}
+#else
+                            mbar_wait(smem_u32(&mb_wb[dpos]), wpar);
+#endif
+                            pending &= pending - 1;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KR; u++) {
+                        if (slot[u] >= 0) {
+                            double r[R], dA[ND];
+                            load_rec<R>(recs + (size_t)slot[u] * stride, r);
+                            nz_terms<KIND, DEG, LOSS, R, ND>(r, x[u], pold, dA, tg, th);
+                            if (q0 == 0) {
+                                k_slot[u] = slot[u]; k_x[u] = x[u];
+#pragma unroll
+                                for (int v = 0; v < R; v++) k_r[u][v] = r[v];
+#pragma unroll
+                                for (int v = 0; v < ND; v++) k_dA[u][v] = dA[v];
+                            }
                         }
                     }
                 }
-                if (warp == 1) TP_MARK(TP_WK_TERMS)
-                __syncwarp();
                 TRD(w, tl, 1, tg + th)
                 tg = sp_warp_allsum(tg);
                 if (KIND != KIND_LINEAR) th = sp_warp_allsum(th);
                 TRD(w, tl, 7, tg + th)
-                const double2 bs = base_s[tl];
                 tg = tg + bs.x;
                 th = th + bs.y;
                 double v0, v1 = 0.0;
                 if (KIND == KIND_LINEAR) {
                     double u = tg + ab * pold;                       // cd_linear.py:19-22
-                    const double inv = mu * cn_s[tl] + ab;
+                    const double inv = mu * cn + ab;
                     v0 = u / inv;
                 } else {
                     double inv = th * mu;                            // pcd.py:59-68 / pcd_all.py:34-41
@@ -429,48 +482,48 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     if (KIND != KIND_LINEAR) cell_store(&cellB[tl], v1, t);
                     cell_store(&cellA[tl], v0, t);
                 }
-                if (warp == 1) TP_MARK(TP_WK_RED)
                 TRD(w, tl, 2, v0 + v1)
+#ifdef SP_SPIN_WAIT
                 Cell rc;
-                mbar_wait(smem_u32(&mb_res[tl]), (uint32_t)(w & 1));
-                rc = cell_load(&rcell[tl]);
-                if (warp == 1) TP_MARK(TP_WK_RESWAIT)
+                do { rc = cell_load(&rcell[tl]); } while ((int)rc.tag != t);
+#else
+                mbar_wait(smem_u32(&mb_res[tl]), wpar);
+                const Cell rc = cell_load(&rcell[tl]);
+#endif
                 TR(w, tl, 5)
                 double upd, pnew;
                 if (KIND == KIND_ALL) { pnew = rc.v; upd = pold - pnew; }
                 else { upd = rc.v; pnew = 0.0; }
                 if (KIND == KIND_ALL || upd != 0.0) {
-                    for (int q = 0; q < ne; q += 32) {
-                        const int e = q + lane;
-                        if (e < ne) {
-                            if (q == 0) {
-                                nz_update<KIND, DEG, R, ND>(k_r, k_dA, k_x, lam, upd, pold, pnew);
-                                double *dst = recs + (size_t)k_slot * stride;
-                                dst[0] = k_r[0];
 #pragma unroll
-                                for (int u = 2; u < R; u++) dst[u] = k_r[u];
-                            } else {
-                                const int slot = ent_sd[hs + e] & 0xffff;
-                                const double x = ent_x[hs + e];
-                                double r[R], dA[ND];
-                                double *dst = recs + (size_t)slot * stride;
-                                load_rec<R>(dst, r);
-                                nz_dA<KIND, DEG, R, ND>(r, x, pold, dA);
-                                nz_update<KIND, DEG, R, ND>(r, dA, x, lam, upd, pold, pnew);
-                                dst[0] = r[0];
+                    for (int u = 0; u < KR; u++) {
+                        if (k_slot[u] >= 0) {
+                            nz_update<KIND, DEG, R, ND>(k_r[u], k_dA[u], k_x[u], lam, upd, pold, pnew);
+                            double *dst = recs + (size_t)k_slot[u] * stride;
+                            dst[0] = k_r[u][0];
 #pragma unroll
-                                for (int u = 2; u < R; u++) dst[u] = r[u];
-                            }
+                            for (int v = 2; v < R; v++) dst[v] = k_r[u][v];
                         }
+                    }
+                    for (int e = 32 * KR + lane; e < ne; e += 32) {   // rare: more than 64 hot nonzeros
+                        const int slot = ent_sd[hs + e] & 0xffff;
+                        const double x = ent_x[hs + e];
+                        double r[R], dA[ND];
+                        double *dst = recs + (size_t)slot * stride;
+                        load_rec<R>(dst, r);
+                        nz_dA<KIND, DEG, R, ND>(r, x, pold, dA);
+                        nz_update<KIND, DEG, R, ND>(r, dA, x, lam, upd, pold, pnew);
+                        dst[0] = r[0];
+#pragma unroll
+                        for (int v = 2; v < R; v++) dst[v] = r[v];
                     }
                 }
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();                      // the write-back above before the flag
                     flag_store(&wbflag[tl], wtag);
-                    mbar_arrive(smem_u32(&mb_wb[tl]));          // wakes the lanes sleeping on this position
+                    mbar_arrive(smem_u32(&mb_wb[tl]));          // wakes the warps sleeping on this position
                 }
-                if (warp == 1) TP_MARK(TP_WK_WB)
                 TR(w, tl, 6)
             }
         }
@@ -488,11 +541,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         if (tid == 32) TP_MARK(TP_ENG_FLUSH)
     }
     TP_FLUSH(tid == 0 || tid == 32)
-    if (warp == 0 && lane == 0) {
-        *a.viol = viol;
+    if (tid == 0) {
+        *a.viol = chain_state[0];
         if (KIND != KIND_LINEAR) {
 #pragma unroll
-            for (int t = 0; t < NC; t++) a.regstate[t] = cache[t];
+            for (int t = 0; t < NC; t++) a.regstate[t] = chain_state[1 + t];
         }
     }
 }

@@ -187,7 +187,7 @@ class WindowPlan:
         env_b = os.environ.get("SPARSEPOLY_B200_WINDOW")
         env_h = os.environ.get("SPARSEPOLY_B200_HORIZON")
         self.window = int(env_b) if (window is None and env_b) else window
-        self.horizon = int(env_h) if (horizon is None and env_h) else (1 if horizon is None else horizon)
+        self.horizon = int(env_h) if (horizon is None and env_h) else (0 if horizon is None else horizon)
         self.min_window = min_window
         self.max_hot_frac = 0.5
         dev, d = ds.device, ds.n_features
