@@ -74,10 +74,14 @@ typedef struct sp_plan {
  * all other CTAs in bulk. */
 typedef struct sp_wplan {
     int32_t window, horizon, n_windows, slot_cap;
+    int32_t near, reserved;   /* hot nonzeros whose slot was last touched <= near positions back are
+                                 "late": evaluated by the engine's chain warp itself */
     const int32_t *cflag;     /* [nnz] CSC row index | 0x80000000 when the nonzero is hot */
     const int32_t *ht_ptr;    /* [d+1] offsets of the hot nonzeros of position t */
-    const int32_t *h_slot;    /* [n_hot] slot of the sample within its window */
-    const int32_t *h_dep;     /* [n_hot] window-local position that last touched the slot, or -1 */
+    const int32_t *ht_cls;    /* [d] per position: #late-only | #late+fwd << 8 | #fwd-only << 16 (the
+                                 position's hot nonzeros are stored in that class order) */
+    const int32_t *h_sd;      /* [n_hot] slot | (dep+1) << 16 | fwd << 29 | late << 30; dep = window-local
+                                 position that last touched the slot, -1 = none */
     const double *h_x;        /* [n_hot] value */
     const int32_t *n_slots;   /* [n_windows] distinct hot samples */
     const int32_t *slot_row;  /* [n_windows*slot_cap] sample index of every slot */
@@ -110,13 +114,14 @@ int sp_plan_order(const sp_dataset *ds, int n_cta, const int32_t *col_part, cons
  * are written.  The caller turns hot_count into ht_ptr (exclusive prefix sum, d+1 entries). */
 int sp_wplan_flag(const sp_dataset *ds, const int32_t *idx_feat, int window, int horizon,
                   int32_t *pos_scratch, int32_t *cflag, int32_t *hot_count, sp_stream stream);
-/* Window plan, step 2: fills h_slot / h_dep / h_x [ht_ptr[d]], n_slots [n_windows], slot_row
- * [n_windows*slot_cap]; *overflow is set to 1 when a window has more than slot_cap distinct hot
- * samples (retry with a smaller window). */
-int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap,
-                  const int32_t *cflag, const int32_t *ht_ptr, int32_t *h_slot, int32_t *h_dep,
-                  double *h_x, int32_t *n_slots, int32_t *slot_row, int32_t *overflow,
-                  sp_stream stream);
+/* Window plan, step 2: fills h_sd / h_x [ht_ptr[d]] (tmp_sd / tmp_x: scratch of the same size),
+ * ht_cls [d], n_slots [n_windows], slot_row [n_windows*slot_cap]; *overflow is set to 1 when a window
+ * needs more than slot_cap slots, more than 2*slot_cap hot nonzeros, or a position has more than 32
+ * chain-warp nonzeros (retry with a smaller window). */
+int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap, int near,
+                  const int32_t *cflag, const int32_t *ht_ptr, int32_t *tmp_sd, double *tmp_x,
+                  int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots, int32_t *slot_row,
+                  int32_t *overflow, sp_stream stream);
 /* debug: cycle counters of the window sweep's roles (zeros unless the library was built with
  * -DSP_WPROF); out_host [16] */
 int sp_wprof_read(unsigned long long *out_host);

@@ -30,9 +30,9 @@ class SpDataset(C.Structure):
 class SpWPlan(C.Structure):
     """struct sp_wplan (include/sparsepoly_b200.h)."""
     _fields_ = [("window", C.c_int32), ("horizon", C.c_int32), ("n_windows", C.c_int32),
-                ("slot_cap", C.c_int32), ("cflag", _vp), ("ht_ptr", _vp), ("h_slot", _vp), ("h_dep", _vp),
-                ("h_x", _vp), ("n_slots", _vp), ("slot_row", _vp), ("sync", _vp), ("res", _vp),
-                ("base", _vp)]
+                ("slot_cap", C.c_int32), ("near", C.c_int32), ("reserved", C.c_int32), ("cflag", _vp),
+                ("ht_ptr", _vp), ("ht_cls", _vp), ("h_sd", _vp), ("h_x", _vp), ("n_slots", _vp),
+                ("slot_row", _vp), ("sync", _vp), ("res", _vp), ("base", _vp)]
 
 
 class SpPlan(C.Structure):
@@ -56,7 +56,7 @@ SIGNATURES = {
     "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
     "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sp_wplan_flag": (_i, [_DSP, _vp, _i, _i, _vp, _vp, _vp, _vp]),
-    "sp_wplan_fill": (_i, [_DSP, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sp_wplan_fill": (_i, [_DSP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sp_wplan_slot_cap": (_i, [_i]),
     "sp_wprof_read": (_i, [C.POINTER(C.c_ulonglong)]),
     "sp_wtrace_read": (_i, [C.POINTER(C.c_longlong)]),

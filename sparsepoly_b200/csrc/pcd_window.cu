@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int WT = 384;                        // threads per CTA: chain warp + 11 worker warps (<= 168 regs)
-constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 3 * 4 + 2 * 8) + 64;
+constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 4 * 4 + 2 * 8) + 64;
 constexpr int W_REC_BYTES = 196608;            // shared memory reserved for the hot record slots
 
 struct WArgs {
@@ -34,7 +34,7 @@ struct WArgs {
     const int32_t *cflag;
     const double *data;
     const int32_t *idx_feat;
-    const int32_t *ht_ptr, *h_slot, *h_dep;
+    const int32_t *ht_ptr, *ht_cls, *h_sd;
     const double *h_x;
     const int32_t *n_slots, *slot_row;
     const double *prow;          // P[s, :] (or w): read-only during the sweep
@@ -48,6 +48,8 @@ struct WArgs {
 };
 
 struct __align__(16) Cell { double v; long long tag; };
+#define SP_ENT_FWD 0x20000000       // packed hot nonzero (wplan.cu): slot | (dep+1) << 16 | fwd | late
+#define SP_ENT_LATE 0x40000000
 #ifndef SP_BACKOFF_NS
 #define SP_BACKOFF_NS 0
 #endif
@@ -266,6 +268,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     unsigned long long *mb_wb = mb_res + BM;                                   // [BM] write-back done
     int *hp_s = reinterpret_cast<int *>(mb_wb + BM);                           // [BM+1]
     int *wbflag = hp_s + BM + 1;                                               // [BM]
+    int *cls_s = wbflag + BM;                                                  // [BM] chain-warp nonzero counts
 
     for (int i = tid; i < BM; i += WT) {
         cellA[i].tag = -1; cellB[i].tag = -1; rcell[i].tag = -1;
@@ -301,13 +304,14 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             cn_s[tl] = (KIND == KIND_LINEAR) ? a.cns[j] : 0.0;
             base_s[tl] = __ldcg(a.base + t);
             hp_s[tl] = a.ht_ptr[t] - h0;
+            cls_s[tl] = a.ht_cls[t];
             if (tl == nb - 1) hp_s[nb] = a.ht_ptr[t + 1] - h0;
         }
         {
             const int nh = a.ht_ptr[t0 + nb] - h0;
             for (int e = tid; e < nh; e += WT) {
                 ent_x[e] = a.h_x[h0 + e];
-                ent_sd[e] = a.h_slot[h0 + e] | ((a.h_dep[h0 + e] + 1) << 16);
+                ent_sd[e] = a.h_sd[h0 + e];
             }
         }
         const int ns = a.n_slots[w];
@@ -359,6 +363,36 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             pold = lds_f64_a(pp);
             for (int tl = 0; tl < nb; tl++) {
                 const int t = t0 + tl;
+                // ---- this position's chain nonzeros, one per lane: [late only][late+fwd][fwd only].
+                //      Late terms read records the PREVIOUS steps of this warp just wrote back.
+                const int cls = cls_s[tl];
+                const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff), nC = nL + ((cls >> 16) & 0xff);
+                double tgl = 0.0, thl = 0.0, cx = 0.0, cr[R], cdA[ND];
+                int cslot = -1;
+                if (nL > 0) {
+                    // (a late record was last written by this warp, so it can be read before the
+                    // worker's cell arrives)
+                    if (lane < nL) {
+                        const int e = hp_s[tl] + lane;
+                        cslot = ent_sd[e] & 0xffff;
+                        cx = ent_x[e];
+                        load_rec<R>(recs + (size_t)cslot * stride, cr);
+                        nz_terms<KIND, DEG, LOSS, R, ND>(cr, cx, pold, cdA, tgl, thl);
+                    }
+                    if (nL > 1) {
+                        int P2 = 2;
+                        while (P2 < nL) P2 <<= 1;
+                        for (int m = P2 >> 1; m > 0; m >>= 1) {
+                            tgl += sp_shfl_xor(tgl, m);
+                            if (KIND != KIND_LINEAR) thl += sp_shfl_xor(thl, m);
+                        }
+                    }
+                    if (nL > 0) {
+                        tgl = sp_shfl(tgl, 0);
+                        if (KIND != KIND_LINEAR) thl = sp_shfl(thl, 0);
+                    }
+                }
+                const double cn = (KIND == KIND_LINEAR && nL > 0) ? cn_s[tl] : 0.0;
                 while (ta != t) cell_load_a(pa, va, ta);
                 if (KIND != KIND_LINEAR) {
                     while (tb != t) cell_load_a(pb, vb, tb);
@@ -371,6 +405,33 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 cell_load_a(pa + 16, nva, nta);
                 cell_load_a(pb + 16, nvb, ntb);
                 npold = lds_f64_a(pp + 8);
+                if (lane >= nL && lane < nC) {
+                    // fwd-only records: their last writer may have been a worker, whose write-back is
+                    // ordered before the cell that has just arrived
+                    const int e = hp_s[tl] + lane;
+                    cslot = ent_sd[e] & 0xffff;
+                    cx = ent_x[e];
+                    load_rec<R>(recs + (size_t)cslot * stride, cr);
+                    nz_dA<KIND, DEG, R, ND>(cr, cx, pold, cdA);
+                }
+                if (nL > 0) {
+                    // the worker sent the sums over the other nonzeros: finish the Newton step here
+                    const double tg = va + tgl;
+                    if (KIND == KIND_LINEAR) {
+                        double u = tg + ab * pold;                   // cd_linear.py:19-22
+                        const double inv = mu * cn + ab;
+                        va = u / inv;
+                    } else {
+                        const double th = vb + thl;
+                        double inv = th * mu;                        // pcd.py:59-68 / pcd_all.py:34-41
+                        inv = inv + ab;
+                        double u = tg * lam;
+                        u = u + ab * pold;
+                        u = u / inv;
+                        va = pold - eta * u;
+                        vb = eta * gamma / inv;
+                    }
+                }
                 double pnew, upd;
                 if (KIND == KIND_LINEAR) {
                     pnew = pold - va;                                // cd_linear.py:24
@@ -378,6 +439,17 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 } else {
                     pnew = prox_chain<KIND, DEG, NC>(reg, va, vb, pold, cache);
                     upd = pold - pnew;                               // pcd.py:121
+                }
+                if (nC > nLo) {
+                    // records the next positions' late terms need: written back right here
+                    if (lane >= nLo && lane < nC && (KIND == KIND_ALL || upd != 0.0)) {
+                        nz_update<KIND, DEG, R, ND>(cr, cdA, cx, lam, upd, pold, pnew);
+                        double *dst = recs + (size_t)cslot * stride;
+                        dst[0] = cr[0];
+#pragma unroll
+                        for (int v = 2; v < R; v++) dst[v] = cr[v];
+                    }
+                    __syncwarp();
                 }
                 if (lane0) {
                     cell_store_a(pr, KIND == KIND_ALL ? pnew : upd, t);
@@ -405,9 +477,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 const double pold = pold_s[tl];
                 const double2 bs = base_s[tl];
                 const double cn = cn_s[tl];
+                const int cls = cls_s[tl];
+                const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff);
                 double tg = 0.0, th = 0.0;
                 TR(w, tl, 0)
-                int k_slot[KR];
+                int k_slot[KR];                                 // kept for the write-back (-1: none / not ours)
                 double k_x[KR], k_r[KR][R], k_dA[KR][ND];
 #pragma unroll
                 for (int u = 0; u < KR; u++) k_slot[u] = -1;
@@ -418,10 +492,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     for (int u = 0; u < KR; u++) {
                         const int e = q0 + u * 32 + lane;
                         slot[u] = -1; mydep[u] = -1; x[u] = 0.0;
-                        if (e < ne) {
+                        if (e >= nL && e < ne) {                    // (late nonzeros: the chain warp's)
                             const int sd = ent_sd[hs + e];
-                            const int dep = (sd >> 16) - 1;
+                            const int dep = ((sd >> 16) & 0x1ff) - 1;
                             slot[u] = sd & 0xffff;
+                            if (sd & SP_ENT_FWD) slot[u] |= 0x10000;   // term ours, write-back the chain warp's
                             x[u] = ent_x[hs + e];
                             if (dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
                         }
@@ -446,9 +521,9 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     for (int u = 0; u < KR; u++) {
                         if (slot[u] >= 0) {
                             double r[R], dA[ND];
-                            load_rec<R>(recs + (size_t)slot[u] * stride, r);
+                            load_rec<R>(recs + (size_t)(slot[u] & 0xffff) * stride, r);
                             nz_terms<KIND, DEG, LOSS, R, ND>(r, x[u], pold, dA, tg, th);
-                            if (q0 == 0) {
+                            if (q0 == 0 && slot[u] < 0x10000) {
                                 k_slot[u] = slot[u]; k_x[u] = x[u];
 #pragma unroll
                                 for (int v = 0; v < R; v++) k_r[u][v] = r[v];
@@ -465,7 +540,9 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 tg = tg + bs.x;
                 th = th + bs.y;
                 double v0, v1 = 0.0;
-                if (KIND == KIND_LINEAR) {
+                if (nL > 0) {
+                    v0 = tg; v1 = th;                                // the chain warp adds its late terms
+                } else if (KIND == KIND_LINEAR) {
                     double u = tg + ab * pold;                       // cd_linear.py:19-22
                     const double inv = mu * cn + ab;
                     v0 = u / inv;
@@ -505,8 +582,13 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                             for (int v = 2; v < R; v++) dst[v] = k_r[u][v];
                         }
                     }
-                    for (int e = 32 * KR + lane; e < ne; e += 32) {   // rare: more than 64 hot nonzeros
-                        const int slot = ent_sd[hs + e] & 0xffff;
+                    // late-only nonzeros (term by the chain warp, write-back ours) and, rarely, nonzeros
+                    // beyond the 64 kept in registers: recompute dA from the record
+                    for (int e = lane; e < ne; e += 32) {
+                        if (e >= nLo && e < 32 * KR) continue;
+                        const int sd = ent_sd[hs + e];
+                        if (sd & SP_ENT_FWD) continue;
+                        const int slot = sd & 0xffff;
                         const double x = ent_x[hs + e];
                         double r[R], dA[ND];
                         double *dst = recs + (size_t)slot * stride;
@@ -631,7 +713,7 @@ extern "C" int sp_wplan_slot_cap(int rec_stride) {
 int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat, int degree, double *prow,
               const double *cns, const double *lam_ptr, double ab, double gamma, double eta, int reg,
               int loss, double *rec, int rec_stride, double *regstate, double *viol, cudaStream_t st) {
-    if (!wp->cflag || !wp->ht_ptr || !wp->h_slot || !wp->h_dep || !wp->h_x || !wp->n_slots || !wp->slot_row ||
+    if (!wp->cflag || !wp->ht_ptr || !wp->ht_cls || !wp->h_sd || !wp->h_x || !wp->n_slots || !wp->slot_row ||
         !wp->sync || !wp->res || !wp->base) {
         sp_set_error("window plan: missing buffers");
         return SP_ERR_INVALID;
@@ -646,7 +728,7 @@ int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat,
     a.d = ds->n_features; a.B = wp->window; a.H = wp->horizon; a.nwin = wp->n_windows;
     a.slot_cap = wp->slot_cap; a.stride = rec_stride; a.reg = reg;
     a.indptr = ds->csc_indptr; a.cflag = wp->cflag; a.data = ds->csc_data; a.idx_feat = idx_feat;
-    a.ht_ptr = wp->ht_ptr; a.h_slot = wp->h_slot; a.h_dep = wp->h_dep; a.h_x = wp->h_x;
+    a.ht_ptr = wp->ht_ptr; a.ht_cls = wp->ht_cls; a.h_sd = wp->h_sd; a.h_x = wp->h_x;
     a.n_slots = wp->n_slots; a.slot_row = wp->slot_row;
     a.prow = prow; a.cns = cns; a.lam_ptr = lam_ptr; a.ab = ab; a.gamma = gamma; a.eta = eta;
     a.rec = rec; a.regstate = regstate; a.viol = viol;

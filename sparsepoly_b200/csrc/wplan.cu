@@ -60,23 +60,33 @@ __device__ __forceinline__ uint32_t hash_row(uint32_t row, int log2hs) {
     return (row * 2654435761u) >> (32 - log2hs);
 }
 
-// one CTA per window.  smem: keys[HS] (row or -1), meta[HS] = slot | last << 16 (last+1 in the
-// upper half, 0 = none)
+// packed hot nonzero: slot | (dep+1) << 16 | fwd << 29 | late << 30
+//   dep  = window-local position that last touched the slot (-1: none)
+//   late = dep is at most `near` positions back: the engine's chain warp evaluates this term
+//          itself, right after it has produced the update it depends on
+//   fwd  = the slot's next toucher is late: the chain warp also writes this record back itself
+#define SP_ENT_FWD 0x20000000
+#define SP_ENT_LATE 0x40000000
+
+// one CTA per window.  smem: keys[HS] (row or -1), meta[HS] = slot | (last position + 1) << 16,
+// lastent[HS] = global index of the slot's previous hot nonzero
 __global__ void __launch_bounds__(FILL_THREADS)
-wfill_kernel(int d, int B, int slot_cap, int log2hs, const int32_t *__restrict__ idx_feat,
+wfill_kernel(int d, int B, int slot_cap, int near, int log2hs, const int32_t *__restrict__ idx_feat,
              const int32_t *__restrict__ csc_indptr, const double *__restrict__ csc_data,
-             const int32_t *__restrict__ cflag, const int32_t *__restrict__ ht_ptr, int32_t *h_slot,
-             int32_t *h_dep, double *h_x, int32_t *n_slots, int32_t *slot_row, int32_t *overflow) {
+             const int32_t *__restrict__ cflag, const int32_t *__restrict__ ht_ptr, int32_t *tmp_sd,
+             double *tmp_x, int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots,
+             int32_t *slot_row, int32_t *overflow) {
     extern __shared__ int32_t sm[];
     const int HS = 1 << log2hs;
     int32_t *keys = sm;
     uint32_t *meta = reinterpret_cast<uint32_t *>(sm + HS);
+    int32_t *lastent = sm + 2 * HS;
     __shared__ int32_t scan[FILL_THREADS];
     __shared__ int32_t bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = FILL_THREADS / 32;
     const int w = blockIdx.x;
     const int t0 = w * B, nb = min(B, d - t0);
-    for (int c = tid; c < HS; c += FILL_THREADS) { keys[c] = -1; meta[c] = 0u; }
+    for (int c = tid; c < HS; c += FILL_THREADS) { keys[c] = -1; meta[c] = 0u; lastent[c] = -1; }
     if (tid == 0) bad = 0;
     __syncthreads();
     // ---- phase 1: compact the hot nonzeros of every position (row order) and collect the rows
@@ -92,8 +102,8 @@ wfill_kernel(int d, int B, int slot_cap, int log2hs, const int32_t *__restrict__
             if (hot) {
                 const int o = out + __popc(bal & ((1u << lane) - 1u));
                 const int row = fi & SP_ROW_MASK;
-                h_slot[o] = row;                      // temporary: replaced by the slot in phase 2
-                h_x[o] = csc_data[g];
+                tmp_sd[o] = row;                      // temporary: replaced by the packed entry in phase 2
+                tmp_x[o] = csc_data[g];
                 uint32_t c = hash_row((uint32_t)row, log2hs);
                 bool done = false;
                 for (int probe = 0; probe < HS; probe++) {
@@ -132,20 +142,68 @@ wfill_kernel(int d, int B, int slot_cap, int log2hs, const int32_t *__restrict__
             }
     }
     __syncthreads();
-    // ---- phase 2: positions in order: slot of every hot nonzero and the position that last
-    //      touched that slot inside this window
+    // ---- phase 2: positions in order: slot of every hot nonzero, the position that last touched
+    //      that slot inside this window, late / fwd marks
     for (int tl = 0; tl < nb; tl++) {
         const int t = t0 + tl;
         for (int o = ht_ptr[t] + tid; o < ht_ptr[t + 1]; o += FILL_THREADS) {
-            const int row = h_slot[o];
+            const int row = tmp_sd[o];
             uint32_t c = hash_row((uint32_t)row, log2hs);
             while (keys[c] != row) c = (c + 1) & (HS - 1);
             const uint32_t mt = meta[c];
-            h_slot[o] = (int32_t)(mt & 0xffffu);
-            h_dep[o] = (int32_t)(mt >> 16) - 1;
+            const int dep = (int)(mt >> 16) - 1;
+            int sd = (int)(mt & 0xffffu) | ((dep + 1) << 16);
+            if (dep >= 0 && tl - dep <= near) {
+                sd |= SP_ENT_LATE;
+                tmp_sd[lastent[c]] |= SP_ENT_FWD;     // (that nonzero belongs to an earlier position)
+            }
+            tmp_sd[o] = sd;
+            lastent[c] = o;
             meta[c] = (mt & 0xffffu) | ((uint32_t)(tl + 1) << 16);
         }
         __syncthreads();
+    }
+    // ---- phase 3: order the nonzeros of every position by class (stable): late only, late+fwd,
+    //      fwd only, rest -- the chain warp handles the first three, one nonzero per lane
+    for (int tl = warp; tl < nb; tl += n_warps) {
+        const int t = t0 + tl;
+        const int hs = ht_ptr[t], ne = ht_ptr[t + 1] - hs;
+        int cnt[4] = {0, 0, 0, 0};
+        for (int q = 0; q < ne; q += 32) {
+            const int e = q + lane;
+            int cls = -1;
+            if (e < ne) {
+                const int sd = tmp_sd[hs + e];
+                const bool late = sd & SP_ENT_LATE, fwd = sd & SP_ENT_FWD;
+                cls = late ? (fwd ? 1 : 0) : (fwd ? 2 : 3);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) cnt[c] += __popc(__ballot_sync(0xffffffffu, cls == c));
+        }
+        int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
+        for (int q = 0; q < ne; q += 32) {
+            const int e = q + lane;
+            int cls = -1, sd = 0;
+            double x = 0.0;
+            if (e < ne) {
+                sd = tmp_sd[hs + e]; x = tmp_x[hs + e];
+                const bool late = sd & SP_ENT_LATE, fwd = sd & SP_ENT_FWD;
+                cls = late ? (fwd ? 1 : 0) : (fwd ? 2 : 3);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, cls == c);
+                if (cls == c) {
+                    const int o = hs + off[c] + __popc(bal & ((1u << lane) - 1u));
+                    h_sd[o] = sd; h_x[o] = x;
+                }
+                off[c] += __popc(bal);
+            }
+        }
+        if (lane == 0) {
+            ht_cls[t] = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16);
+            if (cnt[0] + cnt[1] + cnt[2] > 32) { *overflow = 1; }
+        }
     }
 }
 
@@ -183,12 +241,13 @@ extern "C" int sp_wplan_flag(const sp_dataset *ds, const int32_t *idx_feat, int 
     return SP_OK;
 }
 
-extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap,
-                             const int32_t *cflag, const int32_t *ht_ptr, int32_t *h_slot,
-                             int32_t *h_dep, double *h_x, int32_t *n_slots, int32_t *slot_row,
-                             int32_t *overflow, sp_stream stream) {
-    if (!ds || !idx_feat || !cflag || !ht_ptr || !h_slot || !h_dep || !h_x || !n_slots || !slot_row ||
-        !overflow || window < 1 || window > SP_WINDOW_MAX || slot_cap < 1 || slot_cap > 16384) {
+extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap, int near,
+                             const int32_t *cflag, const int32_t *ht_ptr, int32_t *tmp_sd, double *tmp_x,
+                             int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots,
+                             int32_t *slot_row, int32_t *overflow, sp_stream stream) {
+    if (!ds || !idx_feat || !cflag || !ht_ptr || !tmp_sd || !tmp_x || !h_sd || !h_x || !ht_cls || !n_slots ||
+        !slot_row || !overflow || window < 1 || window > SP_WINDOW_MAX || slot_cap < 1 || slot_cap > 8192 ||
+        near < 0 || near > 16) {
         sp_set_error("sp_wplan_fill: invalid argument");
         return SP_ERR_INVALID;
     }
@@ -196,15 +255,15 @@ extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int 
     if (d == 0) return SP_OK;
     int log2hs = 9;
     while ((1 << log2hs) < 2 * slot_cap) log2hs++;
-    const size_t smem = (size_t)(1 << log2hs) * 8;
+    const size_t smem = (size_t)(1 << log2hs) * 12;
     cudaError_t e = cudaFuncSetAttribute(wfill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return sp_check_cuda(e, "cudaFuncSetAttribute(wfill_kernel)");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_windows = (d + window - 1) / window;
     sp_prof_begin(SP_PROF_PLAN, st);
-    wfill_kernel<<<n_windows, FILL_THREADS, smem, st>>>(d, window, slot_cap, log2hs, idx_feat, ds->csc_indptr,
-                                                        ds->csc_data, cflag, ht_ptr, h_slot, h_dep, h_x,
-                                                        n_slots, slot_row, overflow);
+    wfill_kernel<<<n_windows, FILL_THREADS, smem, st>>>(d, window, slot_cap, near, log2hs, idx_feat,
+                                                        ds->csc_indptr, ds->csc_data, cflag, ht_ptr, tmp_sd,
+                                                        tmp_x, h_sd, h_x, ht_cls, n_slots, slot_row, overflow);
     sp_prof_end(st);
     SP_LAUNCH_CHECK("wfill_kernel");
     return SP_OK;

@@ -188,6 +188,8 @@ class WindowPlan:
         env_h = os.environ.get("SPARSEPOLY_B200_HORIZON")
         self.window = int(env_b) if (window is None and env_b) else window
         self.horizon = int(env_h) if (horizon is None and env_h) else (0 if horizon is None else horizon)
+        env_n = os.environ.get("SPARSEPOLY_B200_NEAR")
+        self.near = int(env_n) if env_n else 1
         self.min_window = min_window
         self.max_hot_frac = 0.5
         dev, d = ds.device, ds.n_features
@@ -226,26 +228,30 @@ class WindowPlan:
             return False
         n_windows = (d + B - 1) // B
         dev = ds.device
-        self.h_slot = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
-        self.h_dep = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
+        self.h_sd = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
         self.h_x = torch.empty(max(n_hot, 1), dtype=torch.float64, device=dev)
+        tmp_sd = torch.empty(max(n_hot, 1), dtype=torch.int32, device=dev)
+        tmp_x = torch.empty(max(n_hot, 1), dtype=torch.float64, device=dev)
+        self.ht_cls = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
         self.n_slots = torch.zeros(n_windows, dtype=torch.int32, device=dev)
         self.slot_row = torch.empty(n_windows * self.slot_cap, dtype=torch.int32, device=dev)
         self.sync = torch.zeros(2 * (n_windows + 2) + 2, dtype=torch.int32, device=dev)
         self.overflow.zero_()
-        _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap, _ptr(self.cflag),
-                                     _ptr(self.ht_ptr), _ptr(self.h_slot), _ptr(self.h_dep), _ptr(self.h_x),
-                                     _ptr(self.n_slots), _ptr(self.slot_row), _ptr(self.overflow), _stream()))
+        _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap, self.near, _ptr(self.cflag),
+                                     _ptr(self.ht_ptr), _ptr(tmp_sd), _ptr(tmp_x), _ptr(self.h_sd),
+                                     _ptr(self.h_x), _ptr(self.ht_cls), _ptr(self.n_slots),
+                                     _ptr(self.slot_row), _ptr(self.overflow), _stream()))
         if int(self.overflow.item()):
             return False
         s = _lib.SpWPlan()
         s.window, s.horizon, s.n_windows, s.slot_cap = B, self.horizon, n_windows, self.slot_cap
-        s.cflag, s.ht_ptr, s.h_slot, s.h_dep = (self.cflag.data_ptr(), self.ht_ptr.data_ptr(),
-                                                self.h_slot.data_ptr(), self.h_dep.data_ptr())
-        s.h_x, s.n_slots, s.slot_row = self.h_x.data_ptr(), self.n_slots.data_ptr(), self.slot_row.data_ptr()
+        s.near = self.near
+        s.cflag, s.ht_ptr, s.ht_cls = self.cflag.data_ptr(), self.ht_ptr.data_ptr(), self.ht_cls.data_ptr()
+        s.h_sd, s.h_x = self.h_sd.data_ptr(), self.h_x.data_ptr()
+        s.n_slots, s.slot_row = self.n_slots.data_ptr(), self.slot_row.data_ptr()
         s.sync, s.res, s.base = self.sync.data_ptr(), self.res.data_ptr(), self.base.data_ptr()
         self.struct = s
-        self.stats = dict(window=B, horizon=self.horizon, n_windows=n_windows, n_hot=n_hot,
+        self.stats = dict(window=B, horizon=self.horizon, near=self.near, n_windows=n_windows, n_hot=n_hot,
                           hot_frac=n_hot / max(ds.nnz, 1), max_slots=int(self.n_slots.max().item()))
         return True
 
@@ -253,9 +259,16 @@ class WindowPlan:
         self.struct = None
         if self.ds.n_features == 0:
             return False
+        near0 = self.near
         for B in self._candidates():
-            if self._try(idx_feat, B):
-                return True
+            # a position may hand at most 32 nonzeros to the chain warp: fall back to near=0 (every
+            # hot nonzero goes through the worker warps) before shrinking the window
+            for near in ((near0, 0) if near0 > 0 else (0,)):
+                self.near = near
+                if self._try(idx_feat, B):
+                    self.near = near0
+                    return True
+        self.near = near0
         if self.window is not None:
             raise ValueError(f"window plan: window={self.window} horizon={self.horizon} does not fit "
                              f"{self.slot_cap} shared-memory slots")

@@ -76,6 +76,7 @@ WINDOW_GEOMS = [(None, 0), (None, 1), (2, 1), (1, 0), (3, 0)]
 def test_window_sweep_matches_golden(name, window, horizon, monkeypatch):
     monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window")
     monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    monkeypatch.setenv("SPARSEPOLY_B200_NEAR", "2" if horizon else "1")
     if window is not None:
         monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
     rec, X, arr = load_case(name)
@@ -101,13 +102,15 @@ WINDOW_ORACLE = [
 ]
 
 
-@pytest.mark.parametrize("window,horizon", [(None, 1), (None, 0), (64, 0), (8, 1)])
+@pytest.mark.parametrize("window,horizon,near", [(None, 1, 1), (None, 0, 2), (64, 0, 0), (8, 1, 2), (32, 0, 4)])
 @pytest.mark.parametrize("tag,kernel,degree,clf,kw", WINDOW_ORACLE, ids=[c[0] for c in WINDOW_ORACLE])
-def test_window_sweep_sparse_matches_oracle(tag, kernel, degree, clf, kw, window, horizon, monkeypatch):
+def test_window_sweep_sparse_matches_oracle(tag, kernel, degree, clf, kw, window, horizon, near, monkeypatch):
     """columns share ~0.4 samples pairwise: most nonzeros are cold (bulk CTAs), the rest go through
-    the engine's shared-memory slots"""
+    the engine's shared-memory slots; `near` = how far back a dependency is resolved by the chain
+    warp itself"""
     monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window" if window else "auto")
     monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    monkeypatch.setenv("SPARSEPOLY_B200_NEAR", str(near))
     if window is not None:
         monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
     X, y = _problem(n=100000, d=5000, r=10, seed=5, kernel=kernel, degree=degree, clf=clf)
