@@ -74,6 +74,26 @@ def host_csc(X):
     return indptr, indices, np.ascontiguousarray(X.T).reshape(-1)
 
 
+def csr_to_csc_device(n, d, indptr, indices, data):
+    """CSC (indptr, indices, data) of a canonical device CSR matrix: stable sort of the nonzeros by
+    column keeps the rows ascending inside every column, i.e. scipy's canonical CSC, bit for bit."""
+    nnz = int(data.numel())
+    dev = data.device
+    if nnz == 0:
+        return (torch.zeros(d + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev),
+                torch.zeros(0, dtype=torch.float64, device=dev))
+    counts = (indptr[1:] - indptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n, dtype=torch.int32, device=dev), counts, output_size=nnz)
+    _, perm = torch.sort(indices, stable=True)
+    csc_indices = rows[perm]
+    csc_data = data[perm]
+    del rows
+    colcount = torch.bincount(indices, minlength=d)
+    csc_indptr = torch.zeros(d + 1, dtype=torch.int32, device=dev)
+    csc_indptr[1:] = torch.cumsum(colcount, 0).to(torch.int32)
+    return csc_indptr, csc_indices.contiguous(), csc_data.contiguous()
+
+
 class DeviceDataset:
     """CSR and/or CSC copy of X in device memory + the sp_dataset struct handed to the C ABI."""
 
@@ -86,8 +106,13 @@ class DeviceDataset:
             self.csr = tuple(_h2d(a, self.device, pin) for a in host_csr(X))
             self.h2d_bytes += sum(t.numel() * t.element_size() for t in self.csr)
         if need_csc:
-            self.csc = tuple(_h2d(a, self.device, pin) for a in host_csc(X))
-            self.h2d_bytes += sum(t.numel() * t.element_size() for t in self.csc)
+            if need_csr and sp.issparse(X):
+                # transpose on the device (the reference's get_dataset does a host tocsc(),
+                # dataset.py:119-134; at C2 that is ~1 s of scipy against a few ms here)
+                self.csc = csr_to_csc_device(self.n_samples, self.n_features, *self.csr)
+            else:
+                self.csc = tuple(_h2d(a, self.device, pin) for a in host_csc(X))
+                self.h2d_bytes += sum(t.numel() * t.element_size() for t in self.csc)
         ref = self.csr if self.csr is not None else self.csc
         self.nnz = int(ref[2].numel())
         s = _lib.SpDataset()
@@ -297,21 +322,32 @@ class SweepPlan:
             if sweep == "window" and self.wplan.window is None:
                 self.wplan.max_hot_frac = 2.0
         self.n_cta, self.threads = choose_geometry(ds, solver, n_cta, threads)
-        dev = ds.device
+        self.idx_feat = torch.empty(max(ds.n_features, 1), dtype=torch.int32, device=ds.device)
+        self._order_host = None
+        self._cluster_ready = False
+        s = _lib.SpPlan()
+        s.n_cta, s.threads = self.n_cta, self.threads
+        s.idx_feat = self.idx_feat.data_ptr()
+        self.struct = s
+        self.mode = "cluster"
+        if self.wplan is None:
+            self._ensure_cluster()
+
+    def _ensure_cluster(self):
+        """Buffers of the cluster sweep (allocated only when the window sweep is not used)."""
+        if self._cluster_ready:
+            return
+        ds, dev = self.ds, self.ds.device
         d, C_ = ds.n_features, self.n_cta
         self.col_part = torch.empty(max(d * (C_ + 1), 1), dtype=torch.int32, device=dev)
         self.pos_ptr = torch.empty(max(d * (C_ + 1), 1), dtype=torch.int32, device=dev)
         self.flag_idx = torch.empty(max(ds.nnz, 1), dtype=torch.int32, device=dev)
-        self.idx_feat = torch.empty(max(d, 1), dtype=torch.int32, device=dev)
         self.pos_conf = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
         _lib.check(_lib.load().sp_plan_partition(ds.ref(), C_, _ptr(self.col_part), _stream()))
-        self._order_host = None
-        s = _lib.SpPlan()
-        s.n_cta, s.threads = C_, self.threads
-        s.pos_ptr, s.flag_idx, s.idx_feat = (self.pos_ptr.data_ptr(), self.flag_idx.data_ptr(),
-                                             self.idx_feat.data_ptr())
-        s.pos_conf = self.pos_conf.data_ptr()
-        self.struct = s
+        s = self.struct
+        s.pos_ptr, s.flag_idx, s.pos_conf = (self.pos_ptr.data_ptr(), self.flag_idx.data_ptr(),
+                                             self.pos_conf.data_ptr())
+        self._cluster_ready = True
 
     def set_order(self, idx_feat_host):
         idx = np.ascontiguousarray(idx_feat_host, dtype=np.int32)
@@ -325,6 +361,7 @@ class SweepPlan:
             self.struct.win = C.pointer(self.wplan.struct)
             self.mode = "window"
             return
+        self._ensure_cluster()
         _lib.check(_lib.load().sp_plan_order(self.ds.ref(), self.n_cta, _ptr(self.col_part),
                                              _ptr(self.idx_feat), _ptr(self.pos_ptr),
                                              _ptr(self.flag_idx), _ptr(self.pos_conf), _stream()))
