@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 #define SP_ABI_VERSION 2
+#define SP_MAX_HOT_FEATURES 16
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
 
 typedef void *sp_stream;
@@ -50,6 +51,12 @@ typedef struct sp_dataset {
     const double *csr_data;
     const int32_t *csc_indptr, *csc_indices;
     const double *csc_data;
+    /* optional (may be NULL / 0): dense features, used by sp_psgd_grad to pre-reduce their
+     * gradient rows per warp instead of issuing one atomic per sample.  feat_hot[j] = slot
+     * 0..n_hot_feat-1 or -1; hot_feat[slot] = j. */
+    const int8_t *feat_hot;
+    const int32_t *hot_feat;
+    int32_t n_hot_feat;
 } sp_dataset;
 
 /* Coordinate-order plan for the sequential sweeps (built by sp_plan_partition + sp_plan_order).

@@ -24,7 +24,8 @@ class SpDataset(C.Structure):
     """struct sp_dataset (include/sparsepoly_b200.h)."""
     _fields_ = [("n_samples", C.c_int32), ("n_features", C.c_int32), ("nnz", C.c_int64),
                 ("csr_indptr", _vp), ("csr_indices", _vp), ("csr_data", _vp),
-                ("csc_indptr", _vp), ("csc_indices", _vp), ("csc_data", _vp)]
+                ("csc_indptr", _vp), ("csc_indices", _vp), ("csc_data", _vp),
+                ("feat_hot", _vp), ("hot_feat", _vp), ("n_hot_feat", C.c_int32)]
 
 
 class SpWPlan(C.Structure):

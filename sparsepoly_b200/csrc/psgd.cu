@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int PG_THREADS = 256;
+constexpr int PG_HOT = SP_MAX_HOT_FEATURES;   // dense features whose gradient is pre-reduced per warp
 
 // ------------------------------------------------------------------------------ gradient
 // One group of G lanes per sample; lane l owns components l, l+G, ... (KCH of them).
@@ -32,7 +33,8 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                  const double *__restrict__ P, const double *__restrict__ w,
                  const double *__restrict__ lams, int loss, int fit_linear,
                  const int32_t *__restrict__ idx_samples, int b0, int b1, double *grad_P,
-                 double *grad_w, double *loss_sum, const double *__restrict__ col_thresh, int dbg) {
+                 double *grad_w, double *loss_sum, const double *__restrict__ col_thresh, int dbg,
+                 const int8_t *__restrict__ feat_hot, int n_hot, const int32_t *__restrict__ hot_feat) {
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu
                                      : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -40,6 +42,19 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
     const int group = blockIdx.x * groups_per_block + threadIdx.x / G;
     const int n_groups = gridDim.x * groups_per_block;
     const size_t dk = (size_t)d * k;
+    // Dense ("hot") features are hit by (almost) every sample: their same-address fp64 REDs
+    // serialise in L2.  Each group of lanes therefore sums its samples' contributions to those
+    // rows in a private shared-memory tile (lane = component, no atomics) and issues one RED per
+    // (row, component) when it is done.
+    constexpr bool HOT = (KCH * NORD == 1);
+    extern __shared__ double pg_smem[];
+    double *hacc = pg_smem + (size_t)(threadIdx.x / G) * (PG_HOT * G + PG_HOT);   // [PG_HOT][G] + w[PG_HOT]
+    double *hw = hacc + PG_HOT * G;
+    const bool use_hot = HOT && feat_hot != nullptr && n_hot > 0;
+    if (use_hot) {
+        for (int q = lane; q < PG_HOT * G + PG_HOT; q += G) hacc[q] = 0.0;
+        __syncwarp(gmask);
+    }
     double lam[KCH];
 #pragma unroll
     for (int c = 0; c < KCH; c++) lam[c] = (lane + G * c < k) ? lams[lane + G * c] : 0.0;
@@ -97,6 +112,7 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
 #pragma unroll
                             for (int o = 0; o < NORD; o++) pv[u][c][o] = sp_soft_threshold(pv[u][c][o], thr[c][o]);
                 }
+
 #pragma unroll
                 for (int u = 0; u < UB; u++) {
                     if (q0 + u < cnt) {
@@ -125,16 +141,23 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
         const double dL = sp_dloss_rt(loss, ypred, yi);
         // ---- _update_grads, psgd.py:60-91
         if (fit_linear)
-            for (int e = st + lane; e < en; e += G) atomicAdd(grad_w + indices[e], dL * data[e]);
+            for (int e = st + lane; e < en; e += G) {
+                const int j = indices[e];
+                const int h = use_hot ? (int)feat_hot[j] : -1;
+                if (h >= 0) hw[h] += dL * data[e];               // (a row's features are distinct)
+                else atomicAdd(grad_w + j, dL * data[e]);
+            }
         for (int base = st; base < en; base += G) {
             const int e = base + lane;
-            int jl = 0;
+            int jl = 0, hl = -1;
             double xl = 0.0;
-            if (e < en) { jl = indices[e]; xl = data[e]; }
+            if (e < en) { jl = indices[e]; xl = data[e]; if (use_hot) hl = (int)feat_hot[jl]; }
             const int cnt = min(G, en - base);
+#pragma unroll 4
             for (int q = 0; q < cnt; q++) {
                 const int j = __shfl_sync(gmask, jl, q, G);
                 const double x = __shfl_sync(gmask, xl, q, G);
+                const int hq = HOT ? __shfl_sync(gmask, hl, q, G) : -1;
 #pragma unroll
                 for (int c = 0; c < KCH; c++) {
                     const int s = lane + G * c;
@@ -148,12 +171,23 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
 #pragma unroll
                                 for (int t = 1; t < DEG - o; t++) dprev = x * (A[c][o][t] - p * dprev);
                             }
-                            if (!(dbg & 1)) atomicAdd(grad_P + o * dk + (size_t)j * k + s, (dL * lam[c]) * dprev);   // psgd.py:91
+                            const double gv = (dL * lam[c]) * dprev;                    // psgd.py:91
+                            if (HOT && hq >= 0) hacc[hq * G + lane] += gv;
+                            else if (!(dbg & 1)) atomicAdd(grad_P + o * dk + (size_t)j * k + s, gv);
                             else if (dprev == 1.2345e-300) loss_acc += 1.0;
                         }
                     }
                 }
             }
+        }
+    }
+    if (use_hot) {
+        __syncwarp(gmask);
+        for (int h = 0; h < n_hot; h++) {
+            const int j = hot_feat[h];
+            const double gv = hacc[h * G + lane];
+            if (lane < k && gv != 0.0) atomicAdd(grad_P + (size_t)j * k + lane, gv);
+            if (lane == 0 && hw[h] != 0.0) atomicAdd(grad_w + j, hw[h]);
         }
     }
     if (lane == 0 && loss_acc != 0.0) atomicAdd(loss_sum, loss_acc);
@@ -584,14 +618,26 @@ static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, cons
     const int per_block = PG_THREADS / G;
     long long blocks = ((long long)(b1 - b0) + per_block - 1) / per_block;
     if (blocks > 148LL * 8 * 8) blocks = 148LL * 8 * 8;
+    const size_t smem = (size_t)(PG_THREADS / G) * (PG_HOT * G + PG_HOT) * sizeof(double);
+    // persistent grid: the fewer groups, the fewer flushes of the hot-feature tiles
+    if (ds->feat_hot && ds->n_hot_feat > 0 && blocks > 148LL * 4) blocks = 148LL * 4;
 #define SP_GRAD(GG, KC)                                                                           \
-    psgd_grad_kernel<DEG, NORD, GG, KC><<<(int)blocks, PG_THREADS, 0, st>>>(k, d, ds->csr_indptr, \
-        ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls, thr, dbg_flags())
+    {                                                                                             \
+        const size_t sm = (KC * NORD == 1) ? smem : 0;                                            \
+        if (sm) {                                                                                 \
+            cudaError_t e_ = cudaFuncSetAttribute(psgd_grad_kernel<DEG, NORD, GG, KC>,            \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            if (e_ != cudaSuccess) return sp_check_cuda(e_, "cudaFuncSetAttribute(psgd_grad_kernel)"); \
+        }                                                                                         \
+        psgd_grad_kernel<DEG, NORD, GG, KC><<<(int)blocks, PG_THREADS, sm, st>>>(k, d, ds->csr_indptr, \
+            ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls, thr, dbg_flags(), \
+            ds->feat_hot, ds->n_hot_feat, ds->hot_feat); \
+    }
     sp_prof_begin(SP_PROF_PSGD_GRAD, st);
-    if (k <= 16) SP_GRAD(16, 1);
-    else if (k <= 32) SP_GRAD(32, 1);
-    else if (k <= 64) SP_GRAD(32, 2);
-    else if (k <= 128) SP_GRAD(32, 4);
+    if (k <= 16) SP_GRAD(16, 1)
+    else if (k <= 32) SP_GRAD(32, 1)
+    else if (k <= 64) SP_GRAD(32, 2)
+    else if (k <= 128) SP_GRAD(32, 4)
     else { sp_set_error("psgd: n_components=%d > 128 is not supported by the CUDA backend", k); return SP_ERR_UNSUPPORTED; }
 #undef SP_GRAD
     sp_prof_end(st);

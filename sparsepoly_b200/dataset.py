@@ -122,6 +122,26 @@ class DeviceDataset:
         if self.csc is not None:
             s.csc_indptr, s.csc_indices, s.csc_data = (t.data_ptr() for t in self.csc)
         self.struct = s
+        if self.csr is not None and not need_csc:
+            self.mark_hot_features()
+
+    def mark_hot_features(self, min_density=1.0 / 16, max_hot=16):
+        """Dense features (present in >= 1/16 of the rows): sp_psgd_grad pre-reduces their gradient
+        rows per warp (they would otherwise take one same-address atomic per sample)."""
+        if self.csr is None or self.nnz == 0:
+            return
+        cnt = torch.bincount(self.csr[1], minlength=self.n_features)
+        top = torch.topk(cnt, min(max_hot, self.n_features))
+        keep = top.values.to(torch.float64) >= min_density * self.n_samples
+        feats = top.indices[keep].to(torch.int32)
+        if feats.numel() == 0:
+            return
+        self.hot_feat = feats.contiguous()
+        self.feat_hot = torch.full((self.n_features,), -1, dtype=torch.int8, device=self.device)
+        self.feat_hot[feats.long()] = torch.arange(feats.numel(), dtype=torch.int8, device=self.device)
+        self.struct.feat_hot = self.feat_hot.data_ptr()
+        self.struct.hot_feat = self.hot_feat.data_ptr()
+        self.struct.n_hot_feat = int(feats.numel())
 
     @classmethod
     def from_device_csr(cls, n_samples, n_features, indptr, indices, data):
