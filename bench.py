@@ -102,6 +102,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def profiled_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture (profiles/traffic.json); None when there is no capture."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -349,6 +359,8 @@ def run_sweep_workload(name, args, rank, world, local):
     }
     if result["geometry"]["sweep"] == "window" and name == "pcd":
         result["roofline"]["kernel"] = "wsweep_kernel (pcd_window.cu)"
+        result["roofline"]["traffic"] = profiled_traffic("wsweep_kernel")
+        result["roofline"]["algorithmic_bytes_per_launch"] = alg_bytes / args.steps / max(1, sweep_n // args.steps)
     del est, epoch, sync
     torch.cuda.empty_cache()
 
@@ -505,6 +517,7 @@ def run_psgd_workload(args, rank, world, local):
         yb_d.copy_(y_h[r0:r1], non_blocking=True)
         h2d[0] += (b_loc + 1) * 4 + (p1 - p0) * 12 + b_loc * 8
         dsb = DeviceDataset.from_device_csr(b_loc, d, ip_d, ix_d, dt_d)
+        dsb.adopt_hot_features(ds)                        # dense-feature table of the training set
         solvers.psgd_minibatch(dsb, yb_d, P, w, lams, 2, kw["alpha"], kw["beta"], kw["gamma"],
                                kw["regularizer"], kw["loss"], gP, gw, idx_b, True, kw["eta0"], 1,
                                kw["power_t"], 0, b_loc, b_loc * world, it[0], loss_dev, work, state, group)

@@ -143,6 +143,14 @@ class DeviceDataset:
         self.struct.hot_feat = self.hot_feat.data_ptr()
         self.struct.n_hot_feat = int(feats.numel())
 
+    def adopt_hot_features(self, other):
+        """Reuse another dataset's dense-feature table (same feature space)."""
+        if getattr(other, "feat_hot", None) is not None:
+            self.feat_hot, self.hot_feat = other.feat_hot, other.hot_feat
+            self.struct.feat_hot = other.struct.feat_hot
+            self.struct.hot_feat = other.struct.hot_feat
+            self.struct.n_hot_feat = other.struct.n_hot_feat
+
     @classmethod
     def from_device_csr(cls, n_samples, n_features, indptr, indices, data):
         """Wrap CSR tensors that already live on the device (no copy)."""
