@@ -287,21 +287,22 @@ def run_sweep_workload(name, args, rank, world, local):
 
     # ---- device-resident timing: inputs in HBM, W warm-up + K timed epochs, CUDA events
     est = cls(**kw)
-    if name == "allsub":
-        # all-subsets has no separate setup hook: time whole fits instead (see e2e) -- the
-        # device-resident number comes from the epoch events collected by the profiler
-        raise SystemExit("allsub device-resident timing: use --workload pcd/pbcd/psgd in this round")
     Xc, yc = est._check_X_y(X, y)
-    Xc = est._augment(Xc)
     from sklearn.utils import check_random_state
     rng = check_random_state(kw["random_state"])
-    est.w_ = np.zeros(Xc.shape[1])
-    n_orders = est.degree - 1 if est.fit_lower == "explicit" else 1
-    est.P_ = 0.01 * rng.randn(n_orders, est.n_components, Xc.shape[1])
-    est.lams_ = np.ones(est.n_components)
     lib.sp_set_device(local)
-    setup = est._pcd_setup if name == "pcd" else est._pbcd_setup
-    epoch, sync = setup(Xc, np.ascontiguousarray(yc), rng, dev)
+    if name == "allsub":
+        est.P_ = 0.01 * rng.randn(est.n_components, Xc.shape[1])
+        est.lams_ = np.ones(est.n_components)
+        setup = est._setup
+    else:
+        Xc = est._augment(Xc)
+        est.w_ = np.zeros(Xc.shape[1])
+        n_orders = est.degree - 1 if est.fit_lower == "explicit" else 1
+        est.P_ = 0.01 * rng.randn(n_orders, est.n_components, Xc.shape[1])
+        est.lams_ = np.ones(est.n_components)
+        setup = est._pcd_setup if name == "pcd" else est._pbcd_setup
+    epoch, sync = setup(Xc, np.ascontiguousarray(yc, dtype=np.float64), rng, dev)
     for _ in range(args.warmup):
         epoch()
     torch.cuda.synchronize()
@@ -333,12 +334,12 @@ def run_sweep_workload(name, args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     sec_per_epoch = ms_total / 1e3 / args.steps
-    cls_id = 2 if name == "pcd" else 3
+    cls_id = 3 if name == "pbcd" else 2
     sweep_ms, sweep_n = float(ms[cls_id]) + (float(ms[2]) if name == "pbcd" else 0.0), int(cnt[cls_id])
     alg_bytes = sweep_bytes(name, X.nnz, n, wl["k"], wl["degree"], True) * args.steps
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
-    coords = (d * (1 + wl["k"] * (wl["degree"] - 1))) if name == "pcd" else 2 * d
+    coords = (d * (1 + wl["k"] * (wl["degree"] - 1))) if name == "pcd" else (d * wl["k"] if name == "allsub" else 2 * d)
     result = {
         "value": sec_per_epoch, "ms_per_step": sec_per_epoch * 1e3,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -357,9 +358,10 @@ def run_sweep_workload(name, args, rank, world, local):
                      {"sweep": "cluster", "n_cta": est._dev_state["plan"].n_cta,
                       "threads": est._dev_state["plan"].threads}),
     }
-    if result["geometry"]["sweep"] == "window" and name == "pcd":
+    if result["geometry"]["sweep"] == "window" and name in ("pcd", "allsub"):
         result["roofline"]["kernel"] = "wsweep_kernel (pcd_window.cu)"
-        result["roofline"]["traffic"] = profiled_traffic("wsweep_kernel")
+        if name == "pcd" and args.scale == 1.0:
+            result["roofline"]["traffic"] = profiled_traffic("wsweep_kernel")
         result["roofline"]["algorithmic_bytes_per_launch"] = alg_bytes / args.steps / max(1, sweep_n // args.steps)
     del est, epoch, sync
     torch.cuda.empty_cache()
@@ -379,7 +381,7 @@ def run_sweep_workload(name, args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     result["e2e"] = {"value": e2e_s, "unit": "s/epoch", "h2d_bytes_per_step": int(est2._h2d_bytes / args.steps),
-                     "d2h_bytes_per_step": int((est2.P_.nbytes + est2.w_.nbytes) / args.steps + 8),
+                     "d2h_bytes_per_step": int((est2.P_.nbytes + getattr(est2, "w_", np.zeros(0)).nbytes) / args.steps + 8),
                      "note": f"fit(X_host, y_host) wall clock / {args.steps} epochs: host CSR->CSC, H2D, epochs, D2H"}
     if rank == 0 and not args.no_cpu:
         t_cpu, desc = cpu_reference_epoch_seconds(name, X, y, args.cpu_budget)

@@ -570,10 +570,31 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
             self.P_ = 0.01 * rng.randn(k, d)
         self._init_lambdas(rng)
         y = np.ascontiguousarray(y, dtype=np.float64)
-        beta, gamma = (n * self.beta, n * self.gamma) if self.mean else (self.beta, self.gamma)
+        epoch, sync = self._setup(X, y, rng, dev)
+        converged, it = False, 0
+        for it in range(self.max_iter):
+            viol = epoch()
+            if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
+                break
+            if viol < self.tol:
+                if self.verbose:
+                    print(f"Converged at iteration {it+1}")
+                converged = True
+                break
+        sync()
+        self.n_iter_ = it
+        if not converged:
+            warnings.warn("Objective did not converge. Increase max_iter.")
+        return self
 
+    def _setup(self, X, y, rng, dev):
+        """Move everything to the device and return (epoch, sync): epoch() runs one iteration of
+        the reference driver loop (sparse_all_subsets.py:104-133 / :160-199)."""
+        n, d = X.shape
+        k = self.n_components
+        beta, gamma = (n * self.beta, n * self.gamma) if self.mean else (self.beta, self.gamma)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
-        self._h2d_bytes = ds.h2d_bytes
+        self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes
         plan = SweepPlan(ds, self.solver,
                          rec_stride=solvers.rec_stride(-1) if self.solver == "pcd" else None)
         indices_feature = np.arange(d, dtype=np.int32)
@@ -590,6 +611,7 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
         P_dk = solvers.transpose(P_kd)
         solvers.poly_predict(ds, P_dk, lams, -1, out=rec, out_stride=stride)     # _get_output
         self._dev_state = dict(ds=ds, plan=plan, rec=rec, stride=stride, P=P_kd if pcd else P_dk)
+        self._y_pred_train = rec[0::stride]
         if not pcd:
             A = torch.empty(max(n * k, 1), dtype=_f64, device=dev)
             reg_norms = torch.zeros(max(d, 1), dtype=_f64, device=dev)
@@ -600,8 +622,7 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
             else:
                 self.P_[...] = solvers.transpose(P_dk).cpu().numpy()
 
-        converged, it = False, 0
-        for it in range(self.max_iter):
+        def epoch(read_back=True):
             viol_dev.zero_()
             if self.shuffle:
                 if pcd:
@@ -614,20 +635,9 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
             else:
                 solvers.pbcd_epoch(ds, plan, P_dk, lams, -1, beta, gamma, self.eta0, self.regularizer,
                                    self.loss, rec, A, reg_norms, regstate, viol_dev)
-            viol = viol_dev.item()
-            if self._after_epoch(it, viol, "Iteration {} violation sum {}", sync):
-                break
-            if viol < self.tol:
-                if self.verbose:
-                    print(f"Converged at iteration {it+1}")
-                converged = True
-                break
-        sync()
-        self._y_pred_train = rec[0::stride]
-        self.n_iter_ = it
-        if not converged:
-            warnings.warn("Objective did not converge. Increase max_iter.")
-        return self
+            return viol_dev.item() if read_back else None
+
+        return epoch, sync
 
     def _get_output(self, X):
         dev = _device()
