@@ -290,57 +290,74 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     for (int w = 0; w < a.nwin; w++) {
         const int t0 = w * B, nb = min(B, d - t0);
         const int wtag = w + 1;
-        if (tid == 0) {
-            wait_ge(a.base_cnt + w, nbulk);
-            if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
-        }
-        __syncthreads();
-        if (tid == 32) TP_MARK(TP_ENG_WAIT)
-        // ---- stage the window: per-position scalars, the hot nonzeros and the hot sample records
+        // ---- stage, part 1 (static plan data: issued before waiting for the bulk CTAs): per-position
+        //      scalars, the hot nonzeros, the sample index of every slot
         const int h0 = a.ht_ptr[t0];
+        const int ns = a.n_slots[w];
+        const int32_t *srow = a.slot_row + (size_t)w * a.slot_cap;
+        constexpr int SU = 4;                                // independent gathers in flight per thread
+        int rows0[SU];
+#pragma unroll
+        for (int u = 0; u < SU; u++) {
+            const int sl = u * WT + tid;
+            rows0[u] = sl < ns ? srow[sl] : -1;
+        }
         for (int tl = tid; tl < nb; tl += WT) {
             const int t = t0 + tl, j = a.idx_feat[t];
             pold_s[tl] = a.prow[j];
             cn_s[tl] = (KIND == KIND_LINEAR) ? a.cns[j] : 0.0;
-            base_s[tl] = __ldcg(a.base + t);
             hp_s[tl] = a.ht_ptr[t] - h0;
             cls_s[tl] = a.ht_cls[t];
             if (tl == nb - 1) hp_s[nb] = a.ht_ptr[t + 1] - h0;
         }
         {
             const int nh = a.ht_ptr[t0 + nb] - h0;
-            for (int e = tid; e < nh; e += WT) {
-                ent_x[e] = a.h_x[h0 + e];
-                ent_sd[e] = a.h_sd[h0 + e];
-            }
-        }
-        const int ns = a.n_slots[w];
-        const int32_t *srow = a.slot_row + (size_t)w * a.slot_cap;
-        {
-            constexpr int SU = (NCH <= 2) ? 8 : 4;           // independent record gathers in flight per thread
-            for (int s0 = 0; s0 < ns; s0 += WT * SU) {
-                int rows[SU];
-                double2 v[SU][NCH];
+            constexpr int EU = 4;
+            for (int e0 = 0; e0 < nh; e0 += WT * EU) {
+                double xv[EU];
+                int sv[EU];
 #pragma unroll
-                for (int u = 0; u < SU; u++) {
-                    const int sl = s0 + u * WT + tid;
-                    rows[u] = sl < ns ? srow[sl] : -1;
+                for (int u = 0; u < EU; u++) {
+                    const int e = e0 + u * WT + tid;
+                    if (e < nh) { xv[u] = a.h_x[h0 + e]; sv[u] = a.h_sd[h0 + e]; }
                 }
 #pragma unroll
-                for (int u = 0; u < SU; u++)
-                    if (rows[u] >= 0) {
-                        const double2 *src = reinterpret_cast<const double2 *>(a.rec + (size_t)rows[u] * stride);
-#pragma unroll
-                        for (int h = 0; h < NCH; h++) v[u][h] = __ldcg(src + h);
-                    }
-#pragma unroll
-                for (int u = 0; u < SU; u++)
-                    if (rows[u] >= 0) {
-                        double2 *dst = reinterpret_cast<double2 *>(recs + (size_t)(s0 + u * WT + tid) * stride);
-#pragma unroll
-                        for (int h = 0; h < NCH; h++) dst[h] = v[u][h];
-                    }
+                for (int u = 0; u < EU; u++) {
+                    const int e = e0 + u * WT + tid;
+                    if (e < nh) { ent_x[e] = xv[u]; ent_sd[e] = sv[u]; }
+                }
             }
+        }
+        if (tid == 0) {
+            wait_ge(a.base_cnt + w, nbulk);
+            if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
+        }
+        __syncthreads();
+        if (tid == 32) TP_MARK(TP_ENG_WAIT)
+        // ---- stage, part 2 (data the bulk CTAs produce): cold partial sums, hot sample records
+        for (int tl = tid; tl < nb; tl += WT) base_s[tl] = __ldcg(a.base + t0 + tl);
+        for (int s0 = 0; s0 < ns; s0 += WT * SU) {
+            int rows[SU];
+            double2 v[SU][NCH];
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const int sl = s0 + u * WT + tid;
+                rows[u] = (s0 == 0) ? rows0[u] : (sl < ns ? srow[sl] : -1);
+            }
+#pragma unroll
+            for (int u = 0; u < SU; u++)
+                if (rows[u] >= 0) {
+                    const double2 *src = reinterpret_cast<const double2 *>(a.rec + (size_t)rows[u] * stride);
+#pragma unroll
+                    for (int h = 0; h < NCH; h++) v[u][h] = __ldcg(src + h);
+                }
+#pragma unroll
+            for (int u = 0; u < SU; u++)
+                if (rows[u] >= 0) {
+                    double2 *dst = reinterpret_cast<double2 *>(recs + (size_t)(s0 + u * WT + tid) * stride);
+#pragma unroll
+                    for (int h = 0; h < NCH; h++) dst[h] = v[u][h];
+                }
         }
         __syncthreads();
         if (tid == 32) TP_MARK(TP_ENG_STAGE)
