@@ -186,11 +186,13 @@ int sp_get_eta(int learning_rate, double eta0, double alpha, double beta, double
  * psgd.py:47-91).  P_odk [n_orders,d,k]; grad_P same shape and grad_w [d] are accumulated
  * into (fp64 atomics); *loss_sum accumulates sum of losses at the pre-update parameters.
  * col_thresh (may be NULL): [n_orders*k] thresholds of a lazily applied prox -- the model is
- * soft_threshold(P_odk[o,:,s], col_thresh[o*k+s]) (see sp_psgd_update_prox). */
+ * soft_threshold(P_odk[o,:,s], col_thresh[o*k+s]) (see sp_psgd_update_prox).
+ * touched (may be NULL): [8*ceil(d/8)] bytes; touched[j] is set to 1 for every feature row whose
+ * gradient this call adds to, so that sp_psgd_update_prox can skip reading / zeroing the others. */
 int sp_psgd_grad(const sp_dataset *ds, const double *y, const double *P_odk, int n_orders, int k,
                  const double *w, const double *lams, int degree, int loss, int fit_linear,
                  const int32_t *idx_samples, int b0, int b1, double *grad_P, double *grad_w,
-                 double *loss_sum, const double *col_thresh, sp_stream stream);
+                 double *loss_sum, const double *col_thresh, unsigned char *touched, sp_stream stream);
 
 /* SGD step + zeroing of the gradients (psgd._update_params without the prox, psgd.py:94-117,
  * :195-196):  P = (P - (eta_P/batch)*grad_P) / (1 + eta_P*beta), same for w with alpha. */
@@ -207,10 +209,13 @@ int sp_prox(double *P_dk, int d, int k, int reg, double strength, double *work, 
  * then col_thresh = the new prox thresholds (l1: strength; squaredl12: 2*strength*S_s of
  * regularizer/utils.py:26-70, found by a warm-started fixed-point selection).  The soft threshold
  * is applied lazily by the readers; sp_psgd_finalize materialises it (P = model, col_thresh = 0).
- * col_thresh: [n_orders*k], zero-initialised before the first call; work: sp_psgd_lazy_work_doubles. */
+ * col_thresh: [n_orders*k], zero-initialised before the first call; work: sp_psgd_lazy_work_doubles.
+ * touched (may be NULL): the flags sp_psgd_grad set (after a multi-GPU gradient all-reduce: their
+ * element-wise maximum over the ranks); rows with flag 0 are treated as gradient 0 without reading
+ * grad_P; the flags are cleared. */
 int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
                         double beta, int batch, int reg, double strength, double *col_thresh,
-                        double *work, sp_stream stream);
+                        double *work, unsigned char *touched, sp_stream stream);
 int sp_psgd_finalize(double *P_odk, int n_orders, int d, int k, double *col_thresh, sp_stream stream);
 size_t sp_psgd_lazy_work_doubles(int n_orders, int k);
 

@@ -34,7 +34,8 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                  const double *__restrict__ lams, int loss, int fit_linear,
                  const int32_t *__restrict__ idx_samples, int b0, int b1, double *grad_P,
                  double *grad_w, double *loss_sum, const double *__restrict__ col_thresh, int dbg,
-                 const int8_t *__restrict__ feat_hot, int n_hot, const int32_t *__restrict__ hot_feat) {
+                 const int8_t *__restrict__ feat_hot, int n_hot, const int32_t *__restrict__ hot_feat,
+                 unsigned char *touched) {
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu
                                      : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -140,6 +141,8 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
         if (lane == 0) loss_acc += sp_loss_rt(loss, ypred, yi);     // psgd.py:155
         const double dL = sp_dloss_rt(loss, ypred, yi);
         // ---- _update_grads, psgd.py:60-91
+        if (touched != nullptr)                                  // rows whose gradient becomes nonzero
+            for (int e = st + lane; e < en; e += G) touched[indices[e]] = 1;
         if (fit_linear)
             for (int e = st + lane; e < en; e += G) {
                 const int j = indices[e];
@@ -375,6 +378,7 @@ struct UpArgs {
     double *psum, *pcnt;   // [nblk][n_orders*k] per-block partials
     double *colres;   // [2][n_orders*k] reduced (sum, cnt)
     int max_iter;
+    unsigned char *touched;   // [d] or NULL: rows with a nonzero gradient (others skip the G read / zero)
 };
 
 constexpr int UP_THREADS = 512;
@@ -412,12 +416,17 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         if (worker) {
             const long long step = (long long)nblk * rpp;
             long long r = (long long)blockIdx.x * rpp + row0;
+            const unsigned char *tch = a.touched;
+            const bool last_order = o == a.n_orders - 1;
             for (; r + 3 * step < d; r += 4 * step) {     // 8 independent loads in flight per thread
                 double pv[4], gv[4];
+                bool tv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) tv[u] = tch == nullptr || tch[r + u * step] != 0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const size_t e = (size_t)(r + u * step) * k + col;
-                    pv[u] = P[e]; gv[u] = G[e];
+                    pv[u] = P[e]; gv[u] = tv[u] ? G[e] : 0.0;   // untouched rows: gradient is exactly 0
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -427,19 +436,20 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
                     p = p - g;                        // P -= grad
                     p = p / a.den;                    // P /= 1 + eta*beta
                     P[e] = p;
-                    G[e] = 0.0;
+                    if (tv[u]) G[e] = 0.0;
                     const double v = fabs(p);
                     if (sel && v > th_old && v > 0.0) { lsum += v; lcnt += 1.0; }
                 }
             }
             for (; r < d; r += step) {
                 const size_t e = (size_t)r * k + col;
+                const bool tv = tch == nullptr || tch[r] != 0;
                 double p = sp_soft_threshold(P[e], th_old);
-                const double g = G[e] * a.c;
+                const double g = (tv ? G[e] : 0.0) * a.c;
                 p = p - g;
                 p = p / a.den;
                 P[e] = p;
-                G[e] = 0.0;
+                if (tv) G[e] = 0.0;
                 const double v = fabs(p);
                 if (sel && v > th_old && v > 0.0) { lsum += v; lcnt += 1.0; }
             }
@@ -447,6 +457,11 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         if (sel)
             block_col_reduce(lsum, lcnt, ssum, scnt, tpr, rpp, a.psum + (size_t)blockIdx.x * ncol + o * k,
                              a.pcnt + (size_t)blockIdx.x * ncol + o * k, 0, k);
+    }
+    if (a.touched != nullptr) {
+        grid.sync();                                  // every reader of the flags is done: clear them
+        for (size_t r = (size_t)blockIdx.x * T + tid; r < (size_t)((d + 7) / 8); r += (size_t)nblk * T)
+            reinterpret_cast<unsigned long long *>(a.touched)[r] = 0ull;
     }
     if (!sel) {                                       // l1: threshold = strength for every column
         grid.sync();                                  // every reader of the old thresholds is done
@@ -582,7 +597,8 @@ extern "C" size_t sp_prox_work_doubles(int d, int k) {
     const size_t cols = (size_t)(k > 1 ? k : 1);
     // the psgd epoch additionally keeps [n_orders*k] thresholds + the fused kernel's partials in
     // front (n_orders <= SP_MAXDEG-1)
-    return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64 + (size_t)(SP_MAXDEG) * cols * (2 * 148 * 2 + 3);
+    return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64 + (size_t)(SP_MAXDEG) * cols * (2 * 148 * 2 + 3) +
+           (size_t)(d + 7) / 8 + 1;
 }
 
 extern "C" int sp_get_eta(int lr, double eta0, double alpha, double beta, double power_t, int64_t it,
@@ -613,7 +629,7 @@ template <int DEG, int NORD>
 static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, const double *y,
                        const double *P, const double *w, const double *lams, int loss, int fit_linear,
                        const int32_t *idx, int b0, int b1, double *gP, double *gw, double *ls,
-                       const double *thr) {
+                       const double *thr, unsigned char *touched) {
     const int G = k <= 16 ? 16 : 32;
     const int per_block = PG_THREADS / G;
     long long blocks = ((long long)(b1 - b0) + per_block - 1) / per_block;
@@ -631,7 +647,7 @@ static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, cons
         }                                                                                         \
         psgd_grad_kernel<DEG, NORD, GG, KC><<<(int)blocks, PG_THREADS, sm, st>>>(k, d, ds->csr_indptr, \
             ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls, thr, dbg_flags(), \
-            ds->feat_hot, ds->n_hot_feat, ds->hot_feat); \
+            ds->feat_hot, ds->n_hot_feat, ds->hot_feat, touched); \
     }
     sp_prof_begin(SP_PROF_PSGD_GRAD, st);
     if (k <= 16) SP_GRAD(16, 1)
@@ -649,7 +665,7 @@ extern "C" int sp_psgd_grad(const sp_dataset *ds, const double *y, const double 
                             int k, const double *w, const double *lams, int degree, int loss,
                             int fit_linear, const int32_t *idx_samples, int b0, int b1,
                             double *grad_P, double *grad_w, double *loss_sum,
-                            const double *col_thresh, sp_stream stream) {
+                            const double *col_thresh, unsigned char *touched, sp_stream stream) {
     if (!ds || !ds->csr_indptr || !y || !P_odk || !w || !lams || !idx_samples || !grad_P || !grad_w ||
         !loss_sum || k <= 0 || b0 < 0 || b1 < b0) {
         sp_set_error("sp_psgd_grad: invalid argument");
@@ -668,7 +684,7 @@ extern "C" int sp_psgd_grad(const sp_dataset *ds, const double *y, const double 
     cudaStream_t st = (cudaStream_t)stream;
     const int d = ds->n_features;
     const bool ex = n_orders > 1;
-#define SP_CALL(D, N) return launch_grad<D, N>(st, k, d, ds, y, P_odk, w, lams, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum, col_thresh)
+#define SP_CALL(D, N) return launch_grad<D, N>(st, k, d, ds, y, P_odk, w, lams, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum, col_thresh, touched)
     switch (degree) {
     case 2: SP_CALL(2, 1);
     case 3: if (ex) SP_CALL(3, 2); else SP_CALL(3, 1);
@@ -758,7 +774,7 @@ extern "C" size_t sp_psgd_lazy_work_doubles(int n_orders, int k) {
 
 extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
                                    double beta, int batch, int reg, double strength, double *col_thresh,
-                                   double *work, sp_stream stream) {
+                                   double *work, unsigned char *touched, sp_stream stream) {
     if (!P_odk || !grad_P || !col_thresh || !work || batch <= 0 || n_orders <= 0 || k <= 0) {
         sp_set_error("sp_psgd_update_prox: invalid argument");
         return SP_ERR_INVALID;
@@ -784,7 +800,8 @@ extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, 
     a.c = eta_P / batch; a.den = 1.0 + eta_P * beta; a.strength = strength; a.reg = reg;
     a.thr = col_thresh;
     a.psum = work; a.pcnt = work + (size_t)nblk * ncol; a.colres = a.pcnt + (size_t)nblk * ncol;
-    a.max_iter = 500;
+    a.max_iter = (dbg_flags() & 2) ? ((dbg_flags() >> 4) & 15) : 500;   // (debug: cap the selection passes)
+    a.touched = touched;
     void *args[] = {(void *)&a};
     cudaStream_t st = (cudaStream_t)stream;
     sp_prof_begin(SP_PROF_PROX, st);
@@ -815,18 +832,21 @@ extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_od
     if (!ds || !it_io_host || batch_size <= 0 || !work) { sp_set_error("sp_psgd_epoch: invalid argument"); return SP_ERR_INVALID; }
     const int n = ds->n_samples, d = ds->n_features;
     const bool lazy = (reg == SP_REG_L1 || reg == SP_REG_SQL12) && k <= UP_THREADS && n_orders * k <= 4 * UP_THREADS;
-    // work layout: [n_orders*k] lazy thresholds | scratch
-    double *thr = work, *scratch = work + (size_t)n_orders * k;
+    // work layout: [n_orders*k] lazy thresholds | [ceil(d/8)] doubles of touched-row flags | scratch
+    double *thr = work;
+    unsigned char *touched = lazy ? reinterpret_cast<unsigned char *>(work + (size_t)n_orders * k) : nullptr;
+    double *scratch = work + (size_t)n_orders * k + (size_t)(d + 7) / 8;
     cudaStream_t st = (cudaStream_t)stream;
     if (lazy) {
-        zero_kernel<<<1, 256, 0, st>>>(thr, n_orders * k);
+        zero_kernel<<<ew_blocks((size_t)n_orders * k + (size_t)(d + 7) / 8), 256, 0, st>>>(
+            thr, (int)((size_t)n_orders * k + (size_t)(d + 7) / 8));
         SP_LAUNCH_CHECK("zero_kernel");
     }
     int64_t it = *it_io_host;
     for (int b0 = 0; b0 < n; b0 += batch_size) {           // psgd.py:150-198
         const int b1 = (n - b0 < batch_size) ? n : b0 + batch_size;
         int rc = sp_psgd_grad(ds, y, P_odk, n_orders, k, w, lams, degree, loss, fit_linear, idx_samples,
-                              b0, b1, grad_P, grad_w, loss_sum, lazy ? thr : nullptr, stream);
+                              b0, b1, grad_P, grad_w, loss_sum, lazy ? thr : nullptr, touched, stream);
         if (rc) return rc;
         double eta_P, eta_w;
         rc = sp_get_eta(learning_rate, eta0, alpha, beta, power_t, it, &eta_P, &eta_w);
@@ -835,7 +855,8 @@ extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_od
         if (lazy) {
             rc = sp_psgd_step(nullptr, nullptr, w, grad_w, 0, d, k, eta_P, eta_w, alpha, beta, b1 - b0, fit_linear, stream);
             if (rc) return rc;
-            rc = sp_psgd_update_prox(P_odk, grad_P, n_orders, d, k, eta_P, beta, b1 - b0, reg, strength, thr, scratch, stream);
+            rc = sp_psgd_update_prox(P_odk, grad_P, n_orders, d, k, eta_P, beta, b1 - b0, reg, strength, thr, scratch,
+                                     touched, stream);
             if (rc) return rc;
         } else {
             rc = sp_psgd_step(P_odk, grad_P, w, grad_w, n_orders, d, k, eta_P, eta_w, alpha, beta, b1 - b0,

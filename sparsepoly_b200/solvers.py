@@ -87,14 +87,14 @@ def prox(P_dk, reg, strength, work):
 
 
 def psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-              loss_sum, col_thresh=None):
+              loss_sum, col_thresh=None, touched=None):
     """psgd._pred + _update_grads for samples idx_samples[b0:b1] (psgd.py:47-91).  col_thresh:
     thresholds of a lazily applied prox (see psgd_update_prox)."""
     n_orders, _, k = P_odk.shape
     _lib.check(_L().sp_psgd_grad(ds.ref(), _ptr(y), _ptr(P_odk), int(n_orders), int(k), _ptr(w),
                                  _ptr(lams), int(degree), _lib.LOSS_IDS[loss], int(bool(fit_linear)),
                                  _ptr(idx_samples), int(b0), int(b1), _ptr(grad_P), _ptr(grad_w),
-                                 _ptr(loss_sum), _ptr(col_thresh), _stream()))
+                                 _ptr(loss_sum), _ptr(col_thresh), _ptr(touched), _stream()))
 
 
 def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_linear):
@@ -118,12 +118,13 @@ def psgd_step_w(w, grad_w, eta_w, alpha, batch, fit_linear):
                                  float(eta_w), float(alpha), 0.0, int(batch), int(bool(fit_linear)), _stream()))
 
 
-def psgd_update_prox(P_odk, grad_P, eta_P, beta, batch, reg, strength, col_thresh, work):
+def psgd_update_prox(P_odk, grad_P, eta_P, beta, batch, reg, strength, col_thresh, work, touched=None):
     """Fused P update + prox with a lazily applied soft threshold (l1 / squaredl12 only)."""
     n_orders, d, k = P_odk.shape
     _lib.check(_L().sp_psgd_update_prox(_ptr(P_odk), _ptr(grad_P), int(n_orders), int(d), int(k),
                                         float(eta_P), float(beta), int(batch), _lib.REG_IDS[reg],
-                                        float(strength), _ptr(col_thresh), _ptr(work), _stream()))
+                                        float(strength), _ptr(col_thresh), _ptr(work), _ptr(touched),
+                                        _stream()))
 
 
 def psgd_finalize(P_odk, col_thresh):
@@ -173,8 +174,11 @@ class PsgdLazyState:
         if self.lazy:
             self.thr = torch.zeros(n_orders * k, dtype=_f64, device=P_odk.device)
             self.work = lazy_work(n_orders, k, P_odk.device)
+            # touched-row flags (padded to a multiple of 8 bytes: cleared as 64-bit words)
+            self.touched = torch.zeros(8 * ((P_odk.shape[1] + 7) // 8), dtype=torch.uint8, device=P_odk.device)
         else:
             self.thr = None
+            self.touched = None
 
     def finalize(self, P_odk):
         if self.lazy:
@@ -188,17 +192,20 @@ def psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss,
     rank; b_global = number of samples in the minibatch over all ranks."""
     n_orders = P_odk.shape[0]
     psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-              loss_sum, state.thr)
+              loss_sum, state.thr, state.touched)
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(grad_P, group=group)
         if fit_linear:
             dist.all_reduce(grad_w, group=group)
+        if state.touched is not None:                   # union of the ranks' touched rows
+            dist.all_reduce(state.touched, op=dist.ReduceOp.MAX, group=group)
     eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
     strength = gamma * eta_P / (1 + eta_P * beta)
     if state.lazy:
         psgd_step_w(w, grad_w, eta_w, alpha, b_global, fit_linear)
-        psgd_update_prox(P_odk, grad_P, eta_P, beta, b_global, reg, strength, state.thr, state.work)
+        psgd_update_prox(P_odk, grad_P, eta_P, beta, b_global, reg, strength, state.thr, state.work,
+                         state.touched)
     else:
         psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, b_global, fit_linear)
         for o in range(n_orders):
