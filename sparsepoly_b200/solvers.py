@@ -106,6 +106,7 @@ def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_li
 
 
 LAZY_REGS = ("l1", "squaredl12")
+SPARSE_EXCHANGE_MAX_FRAC = 0.6      # above this fraction of touched rows the dense all-reduce is used
 
 
 def lazy_work(n_orders, k, device):
@@ -195,11 +196,24 @@ def psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss,
               loss_sum, state.thr, state.touched)
     if group is not None:
         import torch.distributed as dist
-        dist.all_reduce(grad_P, group=group)
         if fit_linear:
             dist.all_reduce(grad_w, group=group)
-        if state.touched is not None:                   # union of the ranks' touched rows
+        rows = None
+        if state.touched is not None:
+            # union of the ranks' touched rows; only those rows of the dense gradient are nonzero
+            # on any rank, so only they are exchanged ("exchange (row id, k doubles)
+            # lists instead when distinct rows << d")
             dist.all_reduce(state.touched, op=dist.ReduceOp.MAX, group=group)
+            d = P_odk.shape[1]
+            rows = torch.nonzero(state.touched[:d]).squeeze(1)        # identical on every rank
+            if rows.numel() > SPARSE_EXCHANGE_MAX_FRAC * d:
+                rows = None
+        if rows is None:
+            dist.all_reduce(grad_P, group=group)
+        elif rows.numel() > 0:
+            buf = torch.index_select(grad_P, 1, rows)
+            dist.all_reduce(buf, group=group)
+            grad_P.index_copy_(1, rows, buf)
     eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
     strength = gamma * eta_P / (1 + eta_P * beta)
     if state.lazy:
