@@ -34,6 +34,7 @@ extern "C" {
 
 #define SP_ABI_VERSION 2
 #define SP_MAX_HOT_FEATURES 16
+#define SP_PBCD_ENT_PER_SLOT 3  /* pbcd window plan: hot nonzeros per window <= 3*slot_cap (pcd: 2*slot_cap) */
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
 
 typedef void *sp_stream;
@@ -123,12 +124,18 @@ int sp_wplan_flag(const sp_dataset *ds, const int32_t *idx_feat, int window, int
                   int32_t *pos_scratch, int32_t *cflag, int32_t *hot_count, sp_stream stream);
 /* Window plan, step 2: fills h_sd / h_x [ht_ptr[d]] (tmp_sd / tmp_x: scratch of the same size),
  * ht_cls [d], n_slots [n_windows], slot_row [n_windows*slot_cap]; *overflow is set to 1 when a window
- * needs more than slot_cap slots, more than 2*slot_cap hot nonzeros, or a position has more than 32
+ * needs more than slot_cap slots, more than ent_per_slot*slot_cap hot nonzeros, or a position has more than 32
  * chain-warp nonzeros (retry with a smaller window). */
-int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap, int near,
+int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap, int ent_per_slot, int near,
                   const int32_t *cflag, const int32_t *ht_ptr, int32_t *tmp_sd, double *tmp_x,
                   int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots, int32_t *slot_row,
                   int32_t *overflow, sp_stream stream);
+/* same for the pbcd window sweep (records = A[i,:,:] + {y_pred, y}); 0 when n_components > 32 (the
+ * window engine handles k <= 32, wider models use the cluster sweep).  A pbcd window plan is
+ * built with near = 0, window <= 64, res of 2*d*k doubles and base of sp_pbcd_wplan_base_doubles(). */
+int sp_pbcd_wplan_slot_cap(int degree, int k);
+/* doubles the `base` buffer of a pbcd window plan must hold (ring of cold partial sums) */
+size_t sp_pbcd_wplan_base_doubles(void);
 /* debug: cycle counters of the window sweep's roles (zeros unless the library was built with
  * -DSP_WPROF); out_host [16] */
 int sp_wprof_read(unsigned long long *out_host);

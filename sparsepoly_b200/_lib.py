@@ -57,8 +57,10 @@ SIGNATURES = {
     "sp_plan_partition": (_i, [_DSP, _i, _vp, _vp]),
     "sp_plan_order": (_i, [_DSP, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sp_wplan_flag": (_i, [_DSP, _vp, _i, _i, _vp, _vp, _vp, _vp]),
-    "sp_wplan_fill": (_i, [_DSP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sp_wplan_fill": (_i, [_DSP, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sp_wplan_slot_cap": (_i, [_i]),
+    "sp_pbcd_wplan_slot_cap": (_i, [_i, _i]),
+    "sp_pbcd_wplan_base_doubles": (C.c_size_t, []),
     "sp_wprof_read": (_i, [C.POINTER(C.c_ulonglong)]),
     "sp_wtrace_read": (_i, [C.POINTER(C.c_longlong)]),
     "sp_transpose_f64": (_i, [_vp, _vp, _i, _i, _vp]),

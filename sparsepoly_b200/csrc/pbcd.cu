@@ -10,16 +10,19 @@
 #include "common.cuh"
 #include "cluster.cuh"
 #include "sparsepoly_b200.h"
+#include "pbcd_common.cuh"
 
 int sp_rows_precompute_all(const sp_dataset *ds, const double *P_dk, int k, int degree, double *A,
                            cudaStream_t st);
 int sp_launch_reg_cache(int mode, int degree, int d, const double *v, double *regstate, cudaStream_t st);
+int sp_pbcd_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat, double *P_dk, int k,
+                   const double *lams, int degree, double beta, double gamma, double eta, int reg, int loss,
+                   double *yrec, double *A, double *norms, double *regstate, double *viol, cudaStream_t st);
 
 namespace {
 
 constexpr int PB_MAX_THREADS = 256;
 constexpr int PB_MAX_CTAS = 16;
-enum { PK_FM = 1, PK_ALL = 2 };
 
 struct BlockArgs {
     int d, C, k;
@@ -46,47 +49,6 @@ __global__ void row_norms_kernel(int d, int k, const double *__restrict__ P, dou
         acc = sp_warp_allsum(acc);
         if (lane == 0) norms[j] = sqrt(acc);
     }
-}
-
-// e_t(norms) for t=0..deg computed identically by every warp (deterministic: strided fold per
-// lane, butterfly of truncated polynomial products, lane-0 broadcast).  `skip` is treated as 0.
-template <int MAXD>
-__device__ void warp_esp(const double *norms, int d, int skip, int deg, double (&out)[MAXD + 1]) {
-    const int lane = threadIdx.x & 31;
-    double e[MAXD + 1];
-#pragma unroll
-    for (int t = 0; t <= MAXD; t++) e[t] = (t == 0) ? 1.0 : 0.0;
-    for (int j = lane; j < d; j += 32) {
-        const double v = (j == skip) ? 0.0 : norms[j];
-#pragma unroll
-        for (int t = MAXD; t >= 1; t--)
-            if (t <= deg) e[t] += e[t - 1] * v;
-    }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        double o[MAXD + 1], r[MAXD + 1];
-#pragma unroll
-        for (int t = 0; t <= MAXD; t++) o[t] = sp_shfl_xor(e[t], m);
-#pragma unroll
-        for (int t = 0; t <= MAXD; t++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int u = 0; u <= MAXD; u++)
-                if (u <= t) acc += e[u] * o[t - u];
-            r[t] = acc;
-        }
-#pragma unroll
-        for (int t = 0; t <= MAXD; t++) e[t] = r[t];
-    }
-#pragma unroll
-    for (int t = 0; t <= MAXD; t++) out[t] = (t <= deg) ? sp_shfl(e[t], 0) : 0.0;
-}
-
-__device__ double warp_sum_array(const double *v, int d) {
-    double acc = 0.0;
-    for (int j = (threadIdx.x & 31); j < d; j += 32) acc += v[j];
-    acc = sp_warp_allsum(acc);
-    return sp_shfl(acc, 0);
 }
 
 template <int KIND, int DEG, int KCH>
@@ -517,13 +479,13 @@ extern "C" int sp_pbcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *
                              const double *lams, int degree, double beta, double gamma, double eta,
                              int reg, int loss, double *yrec, double *A, double *reg_norms,
                              double *regstate, double *viol, sp_stream stream) {
-    if (!ds || !plan || !ds->csc_data || !ds->csr_indptr || !plan->pos_ptr || !plan->flag_idx ||
-        !plan->idx_feat || !P_dk || !lams || !yrec || !A || !reg_norms || !regstate || !viol || k <= 0) {
+    if (!ds || !plan || !ds->csc_data || !ds->csr_indptr || !plan->idx_feat || !P_dk || !lams || !yrec || !A ||
+        !reg_norms || !regstate || !viol || k <= 0 || (!plan->win && (!plan->pos_ptr || !plan->flag_idx))) {
         sp_set_error("sp_pbcd_epoch: invalid argument");
         return SP_ERR_INVALID;
     }
-    if (plan->n_cta < 1 || plan->n_cta > PB_MAX_CTAS || (plan->n_cta & (plan->n_cta - 1)) ||
-        plan->threads < 32 || plan->threads > PB_MAX_THREADS || plan->threads % 32) {
+    if (!plan->win && (plan->n_cta < 1 || plan->n_cta > PB_MAX_CTAS || (plan->n_cta & (plan->n_cta - 1)) ||
+        plan->threads < 32 || plan->threads > PB_MAX_THREADS || plan->threads % 32)) {
         sp_set_error("sp_pbcd_epoch: bad plan (n_cta power of two <= %d, threads multiple of 32 <= %d)",
                      PB_MAX_CTAS, PB_MAX_THREADS);
         return SP_ERR_INVALID;
@@ -557,6 +519,9 @@ extern "C" int sp_pbcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *
         rc = sp_launch_reg_cache(mode, degree, d, reg_norms, regstate, st);
         if (rc) return rc;
     }
+    if (plan->win)
+        return sp_pbcd_wsweep(ds, plan->win, plan->idx_feat, P_dk, k, lams, degree, beta, gamma, eta, reg, loss, yrec,
+                              A, reg_norms, regstate, viol, st);
     BlockArgs a = {};
     a.d = d; a.C = plan->n_cta; a.k = k;
     a.pos_ptr = plan->pos_ptr; a.flag_idx = plan->flag_idx; a.idx_feat = plan->idx_feat;

@@ -71,7 +71,7 @@ __device__ __forceinline__ uint32_t hash_row(uint32_t row, int log2hs) {
 // one CTA per window.  smem: keys[HS] (row or -1), meta[HS] = slot | (last position + 1) << 16,
 // lastent[HS] = global index of the slot's previous hot nonzero
 __global__ void __launch_bounds__(FILL_THREADS)
-wfill_kernel(int d, int B, int slot_cap, int near, int log2hs, const int32_t *__restrict__ idx_feat,
+wfill_kernel(int d, int B, int slot_cap, int ent_cap, int near, int log2hs, const int32_t *__restrict__ idx_feat,
              const int32_t *__restrict__ csc_indptr, const double *__restrict__ csc_data,
              const int32_t *__restrict__ cflag, const int32_t *__restrict__ ht_ptr, int32_t *tmp_sd,
              double *tmp_x, int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots,
@@ -127,8 +127,8 @@ wfill_kernel(int d, int B, int slot_cap, int near, int log2hs, const int32_t *__
         int acc = 0;
         for (int i = 0; i < FILL_THREADS; i++) { const int v = scan[i]; scan[i] = acc; acc += v; }
         n_slots[w] = acc;
-        // the engine stages <= slot_cap records and <= 2*slot_cap hot nonzeros per window
-        if (acc > slot_cap || bad || ht_ptr[t0 + nb] - ht_ptr[t0] > 2 * slot_cap) { *overflow = 1; bad = 1; }
+        // the engine stages <= slot_cap records and <= ent_cap hot nonzeros per window
+        if (acc > slot_cap || bad || ht_ptr[t0 + nb] - ht_ptr[t0] > ent_cap) { *overflow = 1; bad = 1; }
     }
     __syncthreads();
     if (bad) return;                                  // the host retries with a smaller window
@@ -241,13 +241,14 @@ extern "C" int sp_wplan_flag(const sp_dataset *ds, const int32_t *idx_feat, int 
     return SP_OK;
 }
 
-extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap, int near,
+extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int window, int slot_cap,
+                             int ent_per_slot, int near,
                              const int32_t *cflag, const int32_t *ht_ptr, int32_t *tmp_sd, double *tmp_x,
                              int32_t *h_sd, double *h_x, int32_t *ht_cls, int32_t *n_slots,
                              int32_t *slot_row, int32_t *overflow, sp_stream stream) {
     if (!ds || !idx_feat || !cflag || !ht_ptr || !tmp_sd || !tmp_x || !h_sd || !h_x || !ht_cls || !n_slots ||
         !slot_row || !overflow || window < 1 || window > SP_WINDOW_MAX || slot_cap < 1 || slot_cap > 8192 ||
-        near < 0 || near > 16) {
+        near < 0 || near > 16 || ent_per_slot < 1 || ent_per_slot > 8) {
         sp_set_error("sp_wplan_fill: invalid argument");
         return SP_ERR_INVALID;
     }
@@ -261,7 +262,7 @@ extern "C" int sp_wplan_fill(const sp_dataset *ds, const int32_t *idx_feat, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int n_windows = (d + window - 1) / window;
     sp_prof_begin(SP_PROF_PLAN, st);
-    wfill_kernel<<<n_windows, FILL_THREADS, smem, st>>>(d, window, slot_cap, near, log2hs, idx_feat,
+    wfill_kernel<<<n_windows, FILL_THREADS, smem, st>>>(d, window, slot_cap, ent_per_slot * slot_cap, near, log2hs, idx_feat,
                                                         ds->csc_indptr, ds->csc_data, cflag, ht_ptr, tmp_sd,
                                                         tmp_x, h_sd, h_x, ht_cls, n_slots, slot_row, overflow);
     sp_prof_end(st);

@@ -232,17 +232,25 @@ class WindowPlan:
     csrc/pcd_window.cu).  build() returns False when no window size fits (then the cluster sweep
     is used)."""
 
-    def __init__(self, ds, rec_stride, window=None, horizon=None, min_window=8):
+    def __init__(self, ds, rec_stride, window=None, horizon=None, min_window=8, pbcd_shape=None):
         import os
         self.ds = ds
         self.lib = _lib.load()
-        self.slot_cap = min(8192, int(self.lib.sp_wplan_slot_cap(int(rec_stride))))
+        self.pbcd_shape = pbcd_shape            # (degree, k): plan of the block sweep (pbcd_window.cu)
+        if pbcd_shape is not None:
+            self.slot_cap = min(8192, int(self.lib.sp_pbcd_wplan_slot_cap(int(pbcd_shape[0]), int(pbcd_shape[1]))))
+        else:
+            self.slot_cap = min(8192, int(self.lib.sp_wplan_slot_cap(int(rec_stride))))
         env_b = os.environ.get("SPARSEPOLY_B200_WINDOW")
         env_h = os.environ.get("SPARSEPOLY_B200_HORIZON")
         self.window = int(env_b) if (window is None and env_b) else window
         self.horizon = int(env_h) if (horizon is None and env_h) else (0 if horizon is None else horizon)
         env_n = os.environ.get("SPARSEPOLY_B200_NEAR")
         self.near = int(env_n) if env_n else 1
+        vec = 1
+        if pbcd_shape is not None:
+            self.near = 0                       # the block engine resolves every dependency in the workers
+            vec = int(pbcd_shape[1])
         self.min_window = min_window
         self.max_hot_frac = 0.5
         dev, d = ds.device, ds.n_features
@@ -250,8 +258,9 @@ class WindowPlan:
         self.cflag = torch.empty(max(ds.nnz, 1), dtype=torch.int32, device=dev)
         self.hot_count = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
         self.ht_ptr = torch.zeros(d + 1, dtype=torch.int32, device=dev)
-        self.res = torch.zeros(2 * max(d, 1), dtype=torch.float64, device=dev)
-        self.base = torch.zeros(2 * max(d, 1), dtype=torch.float64, device=dev)
+        self.res = torch.zeros(2 * max(d, 1) * vec, dtype=torch.float64, device=dev)
+        n_base = 2 * max(d, 1) if pbcd_shape is None else int(self.lib.sp_pbcd_wplan_base_doubles())
+        self.base = torch.zeros(n_base, dtype=torch.float64, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.struct = None
         self.stats = {}
@@ -266,8 +275,10 @@ class WindowPlan:
         for B in WINDOW_SIZES:
             if B < self.min_window:
                 break
+            if self.pbcd_shape is not None and B > 64:
+                continue
             f = min(1.0, (2 * H + 1) * B * row / max(ds.n_features, 1))   # expected hot fraction
-            if f <= self.max_hot_frac and 0.75 * B * col * f <= self.slot_cap:
+            if f <= self.max_hot_frac and 0.5 * B * col * f <= self.slot_cap:
                 out.append(B)
         return out
 
@@ -290,7 +301,8 @@ class WindowPlan:
         self.slot_row = torch.empty(n_windows * self.slot_cap, dtype=torch.int32, device=dev)
         self.sync = torch.zeros(2 * (n_windows + 2) + 2, dtype=torch.int32, device=dev)
         self.overflow.zero_()
-        _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap, self.near, _ptr(self.cflag),
+        _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap,
+                                     2 if self.pbcd_shape is None else 3, self.near, _ptr(self.cflag),
                                      _ptr(self.ht_ptr), _ptr(tmp_sd), _ptr(tmp_x), _ptr(self.h_sd),
                                      _ptr(self.h_x), _ptr(self.ht_cls), _ptr(self.n_slots),
                                      _ptr(self.slot_row), _ptr(self.overflow), _stream()))
@@ -336,17 +348,23 @@ class SweepPlan:
     sweep; "auto" uses it when the columns are sparse enough for it to fit, "cluster" never.
     Environment override: SPARSEPOLY_B200_SWEEP."""
 
-    def __init__(self, ds, solver="pcd", n_cta=None, threads=None, rec_stride=None, sweep=None):
+    def __init__(self, ds, solver="pcd", n_cta=None, threads=None, rec_stride=None, sweep=None, pbcd_shape=None):
         import os
         self.ds = ds
         if sweep is None:
             sweep = os.environ.get("SPARSEPOLY_B200_SWEEP", "auto")
-        if solver != "pcd" or rec_stride is None:
+        if solver == "pcd" and rec_stride is None:
+            sweep = "cluster"
+        if solver == "pbcd" and (pbcd_shape is None or pbcd_shape[1] > 32):
             sweep = "cluster"
         self.sweep = sweep
         self.wplan = None
         if sweep in ("auto", "window"):
-            self.wplan = WindowPlan(ds, rec_stride, min_window=8 if sweep == "auto" else 1)
+            self.wplan = WindowPlan(ds, rec_stride, min_window=8 if sweep == "auto" else 1,
+                                    pbcd_shape=pbcd_shape if solver == "pbcd" else None)
+            if self.wplan.slot_cap < 1:
+                self.wplan = None
+        if self.wplan is not None:
             if sweep == "window" and self.wplan.window is None:
                 self.wplan.max_hot_frac = 2.0
         self.n_cta, self.threads = choose_geometry(ds, solver, n_cta, threads)

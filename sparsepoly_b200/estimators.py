@@ -291,11 +291,17 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         k, m = self.n_components, self.degree
         alpha, beta, gamma = self._scaled(n)
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
-        plan = SweepPlan(ds, "pbcd")
+        plan = SweepPlan(ds, "pbcd", pbcd_shape=(m, k))
+        plans_lower = {}                                   # explicit lower orders: own record shape
+        if self.fit_lower == "explicit":
+            for deg in range(2, m):
+                plans_lower[deg] = SweepPlan(ds, "pbcd", pbcd_shape=(deg, k))
         plan_lin = SweepPlan(ds, "pcd", rec_stride=2) if self.fit_linear else None
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         indices_feature = np.arange(d, dtype=np.int32)
         plan.set_order(indices_feature)
+        for pl in plans_lower.values():
+            pl.set_order(indices_feature)
         if plan_lin is not None:
             plan_lin.set_order(indices_feature)
         yrec = torch.zeros(n * 2, dtype=_f64, device=dev)
@@ -323,13 +329,15 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
             if self.shuffle:
                 rng.shuffle(indices_feature)
                 plan.set_order(indices_feature)
+                for pl in plans_lower.values():
+                    pl.set_order(indices_feature)
                 if plan_lin is not None:
                     plan_lin.set_order(indices_feature)
             if self.fit_linear:
                 solvers.cd_linear_epoch(ds, plan_lin, w, col_norm_sq, alpha, self.loss, yrec, 2, viol_dev)
             if self.fit_lower == "explicit":
                 for deg in range(2, m):
-                    solvers.pbcd_epoch(ds, plan, P[m - deg], lams, deg, beta, gamma, self.eta0,
+                    solvers.pbcd_epoch(ds, plans_lower[deg], P[m - deg], lams, deg, beta, gamma, self.eta0,
                                        self.regularizer, self.loss, yrec, A, reg_norms, regstate, viol_dev)
             solvers.pbcd_epoch(ds, plan, P[0], lams, m, beta, gamma, self.eta0, self.regularizer,
                                self.loss, yrec, A, reg_norms, regstate, viol_dev)
@@ -596,7 +604,8 @@ class _BaseSparseAllSubsets(_SparsePolyBase, metaclass=ABCMeta):
         ds = DeviceDataset(X, need_csr=True, need_csc=True, device=dev)
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes
         plan = SweepPlan(ds, self.solver,
-                         rec_stride=solvers.rec_stride(-1) if self.solver == "pcd" else None)
+                         rec_stride=solvers.rec_stride(-1) if self.solver == "pcd" else None,
+                         pbcd_shape=(-1, k) if self.solver == "pbcd" else None)
         indices_feature = np.arange(d, dtype=np.int32)
         indices_component = np.arange(k, dtype=np.int32)
         plan.set_order(indices_feature)

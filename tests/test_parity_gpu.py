@@ -138,6 +138,49 @@ def test_window_sweep_all_subsets_matches_oracle(horizon, monkeypatch):
     assert same_support(est.P_, out["P_"])
 
 
+@pytest.mark.parametrize("window,horizon", [(None, 0), (None, 1), (2, 1), (1, 0), (3, 0)])
+@pytest.mark.parametrize("name", [n for n in case_names() if n.startswith("pbcd")])
+def test_pbcd_window_sweep_matches_golden(name, window, horizon, monkeypatch):
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window")
+    monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    if window is not None:
+        monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
+    rec, X, arr = load_case(name)
+    est = _fit(_estimator(rec), X, arr["y"], arr.get("P_init"))
+    assert est._dev_state["plan"].mode == "window"
+    assert rel_err(est.P_, arr["P_"]) <= TOL
+    assert same_support(est.P_, arr["P_"])
+    if "w_" in arr:
+        assert rel_err(est.w_, arr["w_"]) <= TOL
+    assert est.n_iter_ == int(arr["n_iter_"])
+
+
+PBCD_WINDOW_ORACLE = [
+    ("fm2_omegacs", dict(degree=2, n_components=8, solver="pbcd", regularizer="omegacs", beta=1e-5, gamma=1e-7,
+                         alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True), 2, False),
+    ("fm3_l21_logistic_explicit", dict(degree=3, loss="logistic", n_components=5, solver="pbcd", regularizer="l21",
+                                       beta=1e-6, gamma=1e-7, alpha=1e-4, max_iter=2, tol=-1.0, random_state=0,
+                                       mean=True, fit_lower="explicit"), 3, True),
+    ("fm2_sql21_shuffle", dict(degree=2, n_components=32, solver="pbcd", regularizer="squaredl21", beta=1e-5,
+                               gamma=1e-8, alpha=1e-4, max_iter=2, tol=-1.0, random_state=0, mean=True,
+                               shuffle=True), 2, False),
+]
+
+
+@pytest.mark.parametrize("window,horizon", [(None, 0), (16, 1)])
+@pytest.mark.parametrize("tag,kw,degree,clf", PBCD_WINDOW_ORACLE, ids=[c[0] for c in PBCD_WINDOW_ORACLE])
+def test_pbcd_window_sweep_sparse_matches_oracle(tag, kw, degree, clf, window, horizon, monkeypatch):
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window" if window else "auto")
+    monkeypatch.setenv("SPARSEPOLY_B200_HORIZON", str(horizon))
+    if window is not None:
+        monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
+    X, y = _problem(n=100000, d=5000, r=10, seed=6, kernel="anova", degree=degree, clf=clf)
+    est, out, frac = _compare_fm(kw, X, y)
+    plan = est._dev_state["plan"]
+    assert plan.mode == "window", plan.wplan.stats
+    print(tag, plan.wplan.stats, "nonzero fraction of P_", frac)
+
+
 # ----------------------------------------------------------------------------- vs the C oracle
 def _problem(n, d, r, seed, kernel, degree, clf):
     from sparsepoly_b200 import synth
