@@ -151,28 +151,41 @@ __device__ void bw_bulk(const BWArgs &a, int b, int nbulk) {
                 const int ps = cs + (int)((long long)(ce - cs) * part / parts);
                 const int pe = cs + (int)((long long)(ce - cs) * (part + 1) / parts);
                 double g = 0.0, h = 0.0;
-                for (int e0 = ps + 2 * warp; e0 < pe; e0 += 2 * W) {   // two nonzeros in flight per warp
-                    int fi[2];
-                    double2 yy[2];
-                    double Av[2][NA], xv[2];
+                // the warp's nonzeros: e = ps + warp + W*q; lane q prefetches (cflag, x) of its q-th one,
+                // then 4 record gathers are kept in flight
+                const int cnt = pe - ps;
+                const int nq = cnt > warp ? (cnt - warp + W - 1) / W : 0;
+                for (int qb = 0; qb < nq; qb += 32) {
+                    int fl = -1;
+                    double xl = 0.0;
+                    if (qb + lane < nq) { const int e = ps + warp + W * (qb + lane); fl = a.cflag[e]; xl = a.data[e]; }
+                    const int nloc = min(32, nq - qb);
+                    for (int q0 = 0; q0 < nloc; q0 += 4) {
+                        int fi[4];
+                        double2 yy[4];
+                        double Av[4][NA], xv[4];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) fi[u] = (e0 + u < pe) ? a.cflag[e0 + u] : -1;
-#pragma unroll
-                    for (int u = 0; u < 2; u++)
-                        if (fi[u] >= 0) {
-                            yy[u] = __ldcg(reinterpret_cast<const double2 *>(a.yrec + (size_t)fi[u] * 2));
-                            xv[u] = a.data[e0 + u];
-#pragma unroll
-                            for (int r = 0; r < NA; r++)
-                                Av[u][r] = act ? __ldcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane) : 0.0;
+                        for (int u = 0; u < 4; u++) {
+                            fi[u] = __shfl_sync(0xffffffffu, fl, (q0 + u) & 31);
+                            xv[u] = sp_shfl(xl, (q0 + u) & 31);
+                            if (q0 + u >= nloc) fi[u] = -1;
                         }
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
-                        if (fi[u] >= 0) {
-                            const double dl = sp_dloss_rt(a.loss, yy[u].x, yy[u].y);
-                            const double last = dA_last<KIND, DEG, NA>(Av[u], xv[u], pold);
-                            if (act) { g += dl * last; h += last * last; }     // pbcd.py:65-67
-                        }
+                        for (int u = 0; u < 4; u++)
+                            if (fi[u] >= 0) {
+                                yy[u] = __ldcg(reinterpret_cast<const double2 *>(a.yrec + (size_t)fi[u] * 2));
+#pragma unroll
+                                for (int r = 0; r < NA; r++)
+                                    Av[u][r] = act ? __ldcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane) : 0.0;
+                            }
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (fi[u] >= 0) {
+                                const double dl = sp_dloss_rt(a.loss, yy[u].x, yy[u].y);
+                                const double last = dA_last<KIND, DEG, NA>(Av[u], xv[u], pold);
+                                if (act) { g += dl * last; h += last * last; }     // pbcd.py:65-67
+                            }
+                    }
                 }
                 red[0][warp][lane] = g; red[1][warp][lane] = h;
                 __syncthreads();
@@ -205,44 +218,55 @@ __device__ void bw_bulk(const BWArgs &a, int b, int nbulk) {
                 const int cs = a.indptr[j], ce = a.indptr[j + 1];
                 const int ps = cs + (int)((long long)(ce - cs) * part / parts);
                 const int pe = cs + (int)((long long)(ce - cs) * (part + 1) / parts);
-                for (int e0 = ps + 2 * warp; e0 < pe; e0 += 2 * W) {
-                    int fi[2];
-                    double Av[2][NA], xv[2], ypv[2], dy[2], dy2[2];
+                const int cnt = pe - ps;
+                const int nq = cnt > warp ? (cnt - warp + W - 1) / W : 0;
+                for (int qb = 0; qb < nq; qb += 32) {
+                    int fl = -1;
+                    double xl = 0.0;
+                    if (qb + lane < nq) { const int e = ps + warp + W * (qb + lane); fl = a.cflag[e]; xl = a.data[e]; }
+                    const int nloc = min(32, nq - qb);
+                    for (int q0 = 0; q0 < nloc; q0 += 4) {
+                        int fi[4];
+                        double Av[4][NA], xv[4], ypv[4], dy[4], dy2[4];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) fi[u] = (e0 + u < pe) ? a.cflag[e0 + u] : -1;
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        dy[u] = 0.0; dy2[u] = 0.0; ypv[u] = 0.0;
-                        if (fi[u] >= 0) {
-                            xv[u] = a.data[e0 + u];
-                            ypv[u] = __ldcg(a.yrec + (size_t)fi[u] * 2);
-#pragma unroll
-                            for (int r = 0; r < NA; r++)
-                                Av[u][r] = act ? __ldcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane) : 0.0;
+                        for (int u = 0; u < 4; u++) {
+                            fi[u] = __shfl_sync(0xffffffffu, fl, (q0 + u) & 31);
+                            xv[u] = sp_shfl(xl, (q0 + u) & 31);
+                            if (q0 + u >= nloc) fi[u] = -1;
                         }
-                    }
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
-                        if (fi[u] >= 0) {
-                            sync_one<KIND, DEG, NA>(Av[u], xv[u], pold, upd, pnew, lam, dy[u], dy2[u]);
-                            if (act) {
+                        for (int u = 0; u < 4; u++) {
+                            dy[u] = 0.0; dy2[u] = 0.0; ypv[u] = 0.0;
+                            if (fi[u] >= 0) {
+                                ypv[u] = __ldcg(a.yrec + (size_t)fi[u] * 2);
 #pragma unroll
                                 for (int r = 0; r < NA; r++)
-                                    __stcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane, Av[u][r]);
-                            } else { dy[u] = 0.0; dy2[u] = 0.0; }
+                                    Av[u][r] = act ? __ldcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane) : 0.0;
+                            }
                         }
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        dy[u] = sp_warp_allsum(dy[u]);
-                        if (KIND == PK_ALL) dy2[u] = sp_warp_allsum(dy2[u]);
+                        for (int u = 0; u < 4; u++)
+                            if (fi[u] >= 0) {
+                                sync_one<KIND, DEG, NA>(Av[u], xv[u], pold, upd, pnew, lam, dy[u], dy2[u]);
+                                if (act) {
+#pragma unroll
+                                    for (int r = 0; r < NA; r++)
+                                        __stcg(a.A + (size_t)fi[u] * strideA + (size_t)r * k + lane, Av[u][r]);
+                                } else { dy[u] = 0.0; dy2[u] = 0.0; }
+                            }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            dy[u] = sp_warp_allsum(dy[u]);
+                            if (KIND == PK_ALL) dy2[u] = sp_warp_allsum(dy2[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (fi[u] >= 0 && lane == 0) {
+                                double yp = ypv[u] - dy[u];
+                                if (KIND == PK_ALL) yp = yp + dy2[u];
+                                __stcg(a.yrec + (size_t)fi[u] * 2, yp);
+                            }
                     }
-#pragma unroll
-                    for (int u = 0; u < 2; u++)
-                        if (fi[u] >= 0 && lane == 0) {
-                            double yp = ypv[u] - dy[u];
-                            if (KIND == PK_ALL) yp = yp + dy2[u];
-                            __stcg(a.yrec + (size_t)fi[u] * 2, yp);
-                        }
                 }
             }
             __syncthreads();
