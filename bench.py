@@ -44,7 +44,9 @@ WORKLOADS = {
                          shuffle=False, random_state=0, tol=-1.0)),
     "allsub": dict(tag="C4", n=500_000, d=20_000, r=20, seed=3, k=16, degree=-1, clf=True,
                    kw=dict(loss="squared_hinge", n_components=16, solver="pcd", regularizer="omegati",
-                           beta=1e-6, gamma=1e-7, mean=True, shuffle=False, random_state=0, tol=-1.0)),
+                           # OmegaTI for all-subsets multiplies gamma by prod_j (1 + |p_sj|) ~ e^160 at
+                           # d=20k (reference omegati.py:19-34): only an absurdly small gamma leaves ~10 % of P_
+                           beta=1e-6, gamma=1e-100, mean=True, shuffle=False, random_state=0, tol=-1.0)),
     "psgd": dict(tag="C5", n_per_gpu=6_250_000, d=1_000_000, r=39, seed=4, k=32, degree=2, clf=True,
                  kw=dict(degree=2, loss="logistic", n_components=32, solver="psgd",
                          regularizer="squaredl12", alpha=1e-7, beta=1e-7, gamma=1e-6, fit_linear=True,
