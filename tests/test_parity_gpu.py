@@ -344,3 +344,65 @@ def test_callback_verbose_and_warm_start(capsys):
     assert not np.array_equal(P_before, est.P_)
     with pytest.raises(Exception):
         S.SparseFactorizationMachineRegressor().predict(X)
+
+
+def test_device_csc_transpose_matches_scipy():
+    """DeviceDataset builds the CSC copy on the device (stable sort by column): bit-identical to scipy."""
+    import torch
+    from sparsepoly_b200 import synth
+    from sparsepoly_b200.dataset import DeviceDataset
+    X = synth.uniform_sparse(5000, 700, 13, 21)
+    X[17] = 0                                     # an empty row; column 3 emptied below
+    X = sp.csr_matrix(X)
+    X[:, 3] = 0
+    X.eliminate_zeros()
+    ds = DeviceDataset(X, need_csr=True, need_csc=True)
+    Xc = sp.csc_matrix(X)
+    Xc.sort_indices()
+    ip, ix, dt = (t.cpu().numpy() for t in ds.csc)
+    assert np.array_equal(ip, Xc.indptr) and np.array_equal(ix, Xc.indices) and np.array_equal(dt, Xc.data)
+
+
+def test_psgd_hot_features_and_touched_rows_do_not_change_results():
+    """dense-feature pre-reduction + touched-row flags (psgd.cu) against the plain dense path."""
+    import torch
+    from sparsepoly_b200 import solvers, synth
+    from sparsepoly_b200.dataset import DeviceDataset
+    X = synth.criteo_like(4000, 3000, 7)
+    rng = np.random.RandomState(0)
+    y = np.where(rng.rand(4000) < 0.3, 1.0, -1.0)
+    ds = DeviceDataset(X, need_csr=True, need_csc=False)
+    assert ds.struct.n_hot_feat >= 13                          # the 13 numeric columns are dense
+    dev = ds.device
+    k = 8
+    P0 = torch.from_numpy(0.05 * rng.randn(1, 3000, k)).to(dev)
+    lams = torch.ones(k, dtype=torch.float64, device=dev)
+    idx = torch.arange(4000, dtype=torch.int32, device=dev)
+    yd = torch.from_numpy(y).to(dev)
+
+    def run(use_hot, use_touched):
+        P = P0.clone(); w = torch.zeros(3000, dtype=torch.float64, device=dev)
+        gP = torch.zeros_like(P); gw = torch.zeros_like(w)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        st = solvers.PsgdLazyState(P, "squaredl12")
+        if not use_touched:
+            st.touched = None
+        saved = ds.struct.n_hot_feat
+        if not use_hot:
+            ds.struct.n_hot_feat = 0
+        work = solvers.prox_work(3000, k, dev)
+        it = 1
+        for b0 in range(0, 4000, 500):
+            solvers.psgd_minibatch(ds, yd, P, w, lams, 2, 1e-4, 1e-4, 1e-3, "squaredl12", "logistic", gP, gw, idx,
+                                   True, 0.1, 1, 1.0, b0, b0 + 500, 500, it, loss, work, st)
+            it += 1
+        st.finalize(P)
+        ds.struct.n_hot_feat = saved
+        return P.cpu().numpy(), w.cpu().numpy(), float(loss.item())
+
+    ref = run(False, False)
+    for cfg in ((True, False), (False, True), (True, True)):
+        got = run(*cfg)
+        assert rel_err(got[0], ref[0]) <= 1e-10 and rel_err(got[1], ref[1]) <= 1e-10, cfg
+        assert np.array_equal(got[0] != 0, ref[0] != 0), cfg
+        assert abs(got[2] - ref[2]) <= 1e-9 * abs(ref[2])
