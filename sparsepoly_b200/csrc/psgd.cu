@@ -379,7 +379,17 @@ struct UpArgs {
     double *colres;   // [2][n_orders*k] reduced (sum, cnt)
     int max_iter;
     unsigned char *touched;   // [d] or NULL: rows with a nonzero gradient (others skip the G read / zero)
+    // band buffer of the squared-l1,2 selection: the values |p| within +-UP_BAND_DELTA of the
+    // PREDICTED threshold (previous threshold x strength ratio) are collected during the update pass,
+    // so that the fixed point can be located exactly without further passes over P
+    double *band;      // [ncol][UP_BAND_CAP]
+    int *band_n;       // [ncol] (zeroed before the launch)  + [ncol] fallback flag at band_n[ncol]
+    double *state;     // persistent: [0] previous strength, [1] calls so far, [2]/[3] band hits / generic
+                       // (debug), [4] band half-width, [8 + c] threshold before the previous call (trend)
 };
+
+constexpr int UP_BAND_CAP = 2048;
+constexpr double UP_BAND_DELTA = 0.02;   // initial half-width; adapted (state[4]): /2 on overflow, x2 when the iterate leaves
 
 constexpr int UP_THREADS = 512;
 
@@ -395,6 +405,19 @@ __device__ __forceinline__ void block_col_reduce(double lsum, double lcnt, doubl
         ocnt[col0 + tid] = n;
     }
     __syncthreads();
+}
+
+// predicted threshold of column c: geometric continuation of the last two thresholds (the
+// thresholds decay smoothly while P sparsifies), or the strength ratio when only one is known
+__device__ __forceinline__ double up_predict(const UpArgs &a, int c, double th_old) {
+    const int ncol = a.n_orders * a.k;
+    const double older = a.state[8 + c];
+    double ratio = a.strength / a.state[0];
+    if (a.state[1] >= 2.0 && older > 0.0) ratio = th_old / older;
+    if (ratio < 0.5) ratio = 0.5;
+    if (ratio > 2.0) ratio = 2.0;
+    (void)ncol;
+    return th_old * ratio;
 }
 
 __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpArgs a) {
@@ -413,6 +436,15 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         double *P = a.P + (size_t)o * d * k, *G = a.G + (size_t)o * d * k;
         const double th_old = worker ? a.thr[o * k + col] : 0.0;
         double lsum = 0.0, lcnt = 0.0;
+        // statistics threshold: th_old without a band; the band's upper edge with one
+        const double s_prev = a.state[0];
+        const bool band_on = sel && s_prev > 0.0 && a.strength > 0.0 && th_old > 0.0;
+        const double tau_pred = band_on ? up_predict(a, o * k + col, th_old) : 0.0;
+        const double bdelta = a.state[4] > 0.0 ? a.state[4] : UP_BAND_DELTA;
+        const double b_hi = band_on ? tau_pred * (1.0 + bdelta) : th_old;
+        const double b_lo = band_on ? tau_pred * (1.0 - bdelta) : th_old;
+        double *bandc = a.band + (size_t)(o * k + col) * UP_BAND_CAP;
+        int *bandn = a.band_n + (o * k + col);
         if (worker) {
             const long long step = (long long)nblk * rpp;
             long long r = (long long)blockIdx.x * rpp + row0;
@@ -438,7 +470,11 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
                     P[e] = p;
                     if (tv[u]) G[e] = 0.0;
                     const double v = fabs(p);
-                    if (sel && v > th_old && v > 0.0) { lsum += v; lcnt += 1.0; }
+                    if (sel && v > b_hi && v > 0.0) { lsum += v; lcnt += 1.0; }
+                    else if (band_on && v > b_lo) {
+                        const int bi = atomicAdd(bandn, 1);
+                        if (bi < UP_BAND_CAP) bandc[bi] = v;
+                    }
                 }
             }
             for (; r < d; r += step) {
@@ -451,7 +487,11 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
                 P[e] = p;
                 if (tv) G[e] = 0.0;
                 const double v = fabs(p);
-                if (sel && v > th_old && v > 0.0) { lsum += v; lcnt += 1.0; }
+                if (sel && v > b_hi && v > 0.0) { lsum += v; lcnt += 1.0; }
+                else if (band_on && v > b_lo) {
+                    const int bi = atomicAdd(bandn, 1);
+                    if (bi < UP_BAND_CAP) bandc[bi] = v;
+                }
             }
         }
         if (sel)
@@ -467,6 +507,129 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         grid.sync();                                  // every reader of the old thresholds is done
         if (blockIdx.x == 0) for (int cidx = tid; cidx < ncol; cidx += T) a.thr[cidx] = a.strength;
         return;
+    }
+    // ---- band path: locate every column's fixed point from (statistics above the band) + (the
+    //      band's values), no further pass over P.  Any column that cannot (no prediction yet, band
+    //      overflow, iterate leaves the band) sends the whole launch to the generic passes below,
+    //      which start from the same statistics.
+    {
+        __shared__ double sband[UP_BAND_CAP], spref[UP_BAND_CAP];
+        __shared__ int s_m;
+        int *fallback = a.band_n + ncol;              // [0] any column failed, [1] a band overflowed
+        const double bdelta = a.state[4] > 0.0 ? a.state[4] : UP_BAND_DELTA;
+        const double s_prev = a.state[0];
+        const bool band_on = s_prev > 0.0 && a.strength > 0.0;
+        grid.sync();                                  // partials, band lists and counters are complete
+        if (!band_on) {
+            if (blockIdx.x == 0 && tid == 0) *fallback = 1;
+        } else {
+            for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
+                // statistics above the band (fixed-order reduction of the per-block partials)
+                double s = 0.0, n = 0.0;
+                for (int b = tid; b < nblk; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
+                ssum[tid] = s; scnt[tid] = n;
+                __syncthreads();
+                for (int off = T / 2; off > 0; off >>= 1) {
+                    if (tid < off) { ssum[tid] += ssum[tid + off]; scnt[tid] += scnt[tid + off]; }
+                    __syncthreads();
+                }
+                const double sumA = ssum[0], cntA = scnt[0];
+                __syncthreads();
+                const int nbv = a.band_n[cidx];
+                const double th_old = a.thr[cidx];
+                const double tau_pred = up_predict(a, cidx, th_old);
+                const double b_hi = tau_pred * (1.0 + bdelta), b_lo = tau_pred * (1.0 - bdelta);
+                bool ok = th_old > 0.0 && nbv <= UP_BAND_CAP;
+                if (nbv > UP_BAND_CAP && tid == 0) fallback[1] = 1;
+                if (ok) {
+                    // sort the band descending (bitonic, padded with -1) so that sums are order-free
+                    int np2 = 1;
+                    while (np2 < nbv) np2 <<= 1;
+                    for (int q = tid; q < np2; q += T) sband[q] = q < nbv ? a.band[(size_t)cidx * UP_BAND_CAP + q] : -1.0;
+                    __syncthreads();
+                    for (int kk = 2; kk <= np2; kk <<= 1)
+                        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                            for (int q = tid; q < np2; q += T) {
+                                const int x = q ^ jj;
+                                if (x > q) {
+                                    const double va = sband[q], vb = sband[x];
+                                    const bool desc = (q & kk) == 0;
+                                    if (desc ? (va < vb) : (va > vb)) { sband[q] = vb; sband[x] = va; }
+                                }
+                            }
+                            __syncthreads();
+                        }
+                    // inclusive prefix sums of the sorted values (fixed order: chunk per thread, then
+                    // the chunk totals scanned by one thread)
+                    {
+                        const int per = (np2 + T - 1) / T;
+                        const int q0 = tid * per, q1 = min(np2, q0 + per);
+                        double acc = 0.0;
+                        for (int q = q0; q < q1; q++) acc += (q < nbv) ? sband[q] : 0.0;
+                        ssum[tid] = acc;
+                        __syncthreads();
+                        if (tid == 0) {
+                            double run = 0.0;
+                            for (int b = 0; b < T; b++) { const double v = ssum[b]; ssum[b] = run; run += v; }
+                        }
+                        __syncthreads();
+                        acc = ssum[tid];
+                        for (int q = q0; q < q1; q++) { acc += (q < nbv) ? sband[q] : 0.0; spref[q] = acc; }
+                        __syncthreads();
+                    }
+                    if (tid == 0) {
+                        // Michelot iteration on (statistics above the band) + (band prefix)
+                        double tau = b_hi;
+                        int m_prev = -1;
+                        bool good = true;
+                        double thr_new = 0.0;
+                        for (int it = 0; it < 200; it++) {
+                            int lo_i = 0, hi_i = nbv;                  // m = #{band > tau} (sorted descending)
+                            while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (sband[mid] > tau) lo_i = mid + 1; else hi_i = mid; }
+                            const int m = lo_i;
+                            const double sum = m > 0 ? sumA + spref[m - 1] : sumA;
+                            const double cnt = cntA + (double)m;
+                            const double tnew = 2.0 * a.strength * sum / (1.0 + 2.0 * a.strength * cnt);
+                            if (!(tnew > b_lo) || tnew > b_hi) { good = false; break; }
+                            if (m == m_prev) { thr_new = tnew; break; }
+                            if (it == 199) good = false;
+                            m_prev = m;
+                            tau = tnew;
+                        }
+                        s_m = good ? 1 : 0;
+                        if (good) a.colres[cidx] = thr_new;          // parked until every column is known to be good
+                    }
+                    __syncthreads();
+                    ok = s_m != 0;
+                    __syncthreads();
+                }
+                if (!ok && tid == 0) *fallback = 1;
+            }
+        }
+        grid.sync();
+        const bool fb = *reinterpret_cast<volatile int *>(fallback) != 0;
+        // (every block is past its reads of the trend state: it can be advanced now)
+        if (blockIdx.x == 0) {
+            for (int cidx = tid; cidx < ncol; cidx += T) a.state[8 + cidx] = a.thr[cidx];
+            if (tid == 0) {
+                a.state[0] = a.strength; a.state[1] = a.state[1] + 1.0;
+                a.state[fb ? 3 : 2] += 1.0;                 // (debug counters: band hits / generic passes)
+                if (fb && band_on) {                        // adapt the half-width
+                    const bool over = reinterpret_cast<volatile int *>(fallback)[1] != 0;
+                    double nd = over ? bdelta * 0.5 : bdelta * 2.0;
+                    if (nd < 0.002) nd = 0.002;
+                    if (nd > 0.1) nd = 0.1;
+                    a.state[4] = nd;
+                }
+            }
+        }
+        if (!fb) {
+            if (blockIdx.x == 0) {
+                __syncthreads();
+                for (int cidx = tid; cidx < ncol; cidx += T) a.thr[cidx] = a.colres[cidx];
+            }
+            return;
+        }
     }
     double prev_cnt[4] = {-1.0, -1.0, -1.0, -1.0};   // per owned column (ncol <= 4*T)
     for (int it = 0; it < a.max_iter; it++) {
@@ -598,7 +761,7 @@ extern "C" size_t sp_prox_work_doubles(int d, int k) {
     // the psgd epoch additionally keeps [n_orders*k] thresholds + the fused kernel's partials in
     // front (n_orders <= SP_MAXDEG-1)
     return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64 + (size_t)(SP_MAXDEG) * cols * (2 * 148 * 2 + 3) +
-           (size_t)(d + 7) / 8 + 1;
+           (size_t)(d + 7) / 8 + 1 + (size_t)(SP_MAXDEG) * cols * (UP_BAND_CAP + 4) + 128;
 }
 
 extern "C" int sp_get_eta(int lr, double eta0, double alpha, double beta, double power_t, int64_t it,
@@ -769,7 +932,9 @@ extern "C" int sp_prox(double *P_dk, int d, int k, int reg, double strength, dou
 extern "C" size_t sp_psgd_lazy_work_doubles(int n_orders, int k) {
     // per-block partials 2*nblk*ncol (nblk <= 148*2) + reduced 2*ncol
     const size_t ncol = (size_t)n_orders * k;
-    return 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64;
+    // + persistent tail: state[2] | band counters | band[ncol][UP_BAND_CAP]  (must be zero-initialised
+    // before the first sp_psgd_update_prox call of a fit)
+    return 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64 + 8 + ncol + (ncol + 3) / 2 + 1 + ncol * (size_t)UP_BAND_CAP + 8;
 }
 
 extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
@@ -800,10 +965,19 @@ extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, 
     a.c = eta_P / batch; a.den = 1.0 + eta_P * beta; a.strength = strength; a.reg = reg;
     a.thr = col_thresh;
     a.psum = work; a.pcnt = work + (size_t)nblk * ncol; a.colres = a.pcnt + (size_t)nblk * ncol;
+    // persistent tail of the work buffer (laid out for the largest grid so that it does not move):
+    // state[2] | band_n[ncol+1] ints (padded) | band[ncol][UP_BAND_CAP]
+    {
+        double *tail = work + 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64;
+        a.state = tail;                                                  // [8 + ncol]
+        a.band_n = reinterpret_cast<int *>(tail + 8 + ncol);             // [ncol + 2] ints
+        a.band = tail + 8 + ncol + (ncol + 3) / 2 + 1;
+    }
     a.max_iter = (dbg_flags() & 2) ? ((dbg_flags() >> 4) & 15) : 500;   // (debug: cap the selection passes)
     a.touched = touched;
     void *args[] = {(void *)&a};
     cudaStream_t st = (cudaStream_t)stream;
+    SP_CUDA(cudaMemsetAsync(a.band_n, 0, sizeof(int) * (ncol + 2), st));
     sp_prof_begin(SP_PROF_PROX, st);
     cudaError_t e = cudaLaunchCooperativeKernel((void *)psgd_update_prox_kernel, dim3(nblk), dim3(UP_THREADS), args, 0, st);
     sp_prof_end(st);
@@ -841,6 +1015,9 @@ extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_od
         zero_kernel<<<ew_blocks((size_t)n_orders * k + (size_t)(d + 7) / 8), 256, 0, st>>>(
             thr, (int)((size_t)n_orders * k + (size_t)(d + 7) / 8));
         SP_LAUNCH_CHECK("zero_kernel");
+        // persistent selection state (previous strength) of sp_psgd_update_prox: none yet
+        const size_t ncol = (size_t)n_orders * k;
+        SP_CUDA(cudaMemsetAsync(scratch + 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64, 0, (8 + ncol) * sizeof(double), st));
     }
     int64_t it = *it_io_host;
     for (int b0 = 0; b0 < n; b0 += batch_size) {           // psgd.py:150-198

@@ -110,7 +110,8 @@ SPARSE_EXCHANGE_MAX_FRAC = 0.3      # above this fraction of touched rows the de
 
 
 def lazy_work(n_orders, k, device):
-    return torch.empty(int(_L().sp_psgd_lazy_work_doubles(int(n_orders), int(k))), dtype=_f64, device=device)
+    # zero-initialised: the tail holds the persistent selection state of sp_psgd_update_prox
+    return torch.zeros(int(_L().sp_psgd_lazy_work_doubles(int(n_orders), int(k))), dtype=_f64, device=device)
 
 
 def psgd_step_w(w, grad_w, eta_w, alpha, batch, fit_linear):
