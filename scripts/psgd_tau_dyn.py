@@ -32,7 +32,7 @@ for m in range(50):
     prev = thr
     if m % 5 == 0:
         ncol = k
-        tail = 2 * 148 * 2 * ncol + 2 * ncol + 64
+        tail = 2 * 148 * 8 * ncol + 2 * ncol + 64
         stt = st.work[tail:tail + 8].cpu().numpy()
         bn = st.work[tail + 8 + ncol: tail + 8 + ncol + (ncol + 3) // 2 + 1].view(torch.int32)[:ncol + 2].cpu().numpy()
         print("   state: calls %d band hits %d generic %d delta %.4f; band counts (this call) min/max %d/%d fallback flags %d %d" % (stt[1], stt[2], stt[3], stt[4], bn[:ncol].min(), bn[:ncol].max(), bn[ncol], bn[ncol + 1]), flush=True)

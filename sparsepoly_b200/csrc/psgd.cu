@@ -378,6 +378,7 @@ struct UpArgs {
     double *psum, *pcnt;   // [nblk][n_orders*k] per-block partials
     double *colres;   // [2][n_orders*k] reduced (sum, cnt)
     int max_iter;
+    int nblk_part;     // blocks of the update pass (rows of psum / pcnt it wrote)
     unsigned char *touched;   // [d] or NULL: rows with a nonzero gradient (others skip the G read / zero)
     // band buffer of the squared-l1,2 selection: the values |p| within +-UP_BAND_DELTA of the
     // PREDICTED threshold (previous threshold x strength ratio) are collected during the update pass,
@@ -389,6 +390,10 @@ struct UpArgs {
 };
 
 constexpr int UP_BAND_CAP = 2048;
+constexpr int UP_PART_MAX = 148 * 8;          // most blocks of the update pass (rows of the partial sums)
+// doubles of the fused kernel's work buffer in front of its persistent tail: partial sums / counts
+// [UP_PART_MAX][ncol] each, reduced (sum, cnt) [2][ncol]
+static inline size_t up_tail_offset(size_t ncol) { return 2 * (size_t)UP_PART_MAX * ncol + 2 * ncol + 64; }
 constexpr double UP_BAND_DELTA = 0.02;   // initial half-width; adapted (state[4]): /2 on overflow, x2 when the iterate leaves
 
 constexpr int UP_THREADS = 512;
@@ -420,11 +425,11 @@ __device__ __forceinline__ double up_predict(const UpArgs &a, int c, double th_o
     return th_old * ratio;
 }
 
-__global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double ssum[UP_THREADS], scnt[UP_THREADS];
-    __shared__ int s_changed;
-    const int tid = threadIdx.x, T = UP_THREADS, nblk = gridDim.x, k = a.k, d = a.d;
+// phase 0: fused SGD update + statistics above the band / at the warm-start thresholds + band
+// collection.  Runs either inside the cooperative kernel (legacy path) or as its own streaming
+// kernel with many resident blocks (psgd_update_stats_kernel).
+__device__ __forceinline__ void up_phase0(const UpArgs &a, double *ssum, double *scnt) {
+    const int tid = threadIdx.x, T = blockDim.x, nblk = gridDim.x, k = a.k, d = a.d;
     const int ncol = a.n_orders * k;
     const int tpr = k < T ? k : T;                   // threads per row (host guarantees k <= T)
     const int rpp = T / tpr;
@@ -498,13 +503,35 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
             block_col_reduce(lsum, lcnt, ssum, scnt, tpr, rpp, a.psum + (size_t)blockIdx.x * ncol + o * k,
                              a.pcnt + (size_t)blockIdx.x * ncol + o * k, 0, k);
     }
-    if (a.touched != nullptr) {
-        grid.sync();                                  // every reader of the flags is done: clear them
+}
+
+__global__ void __launch_bounds__(256, 4) psgd_update_stats_kernel(const UpArgs a) {
+    __shared__ double ssum[256], scnt[256];
+    up_phase0(a, ssum, scnt);
+}
+
+__global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double ssum[UP_THREADS], scnt[UP_THREADS];
+    __shared__ int s_changed;
+    const int tid = threadIdx.x, T = UP_THREADS, nblk = gridDim.x, k = a.k, d = a.d;
+    const int ncol = a.n_orders * k;
+    const int tpr = k < T ? k : T;                   // threads per row (host guarantees k <= T)
+    const int rpp = T / tpr;
+    const int col = tid % tpr, row0 = tid / tpr;
+    const bool worker = tid < tpr * rpp;
+    const bool sel = a.reg == SP_REG_SQL12;
+    int npart = a.nblk_part;                         // rows of psum / pcnt the update pass wrote
+    if (npart == 0) {                                // wide model: update pass here
+        up_phase0(a, ssum, scnt);
+        npart = nblk;
+        grid.sync();
+    }
+    if (a.touched != nullptr) {                       // (the update pass, their only reader, is a finished launch)
         for (size_t r = (size_t)blockIdx.x * T + tid; r < (size_t)((d + 7) / 8); r += (size_t)nblk * T)
             reinterpret_cast<unsigned long long *>(a.touched)[r] = 0ull;
     }
     if (!sel) {                                       // l1: threshold = strength for every column
-        grid.sync();                                  // every reader of the old thresholds is done
         if (blockIdx.x == 0) for (int cidx = tid; cidx < ncol; cidx += T) a.thr[cidx] = a.strength;
         return;
     }
@@ -519,14 +546,13 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         const double bdelta = a.state[4] > 0.0 ? a.state[4] : UP_BAND_DELTA;
         const double s_prev = a.state[0];
         const bool band_on = s_prev > 0.0 && a.strength > 0.0;
-        grid.sync();                                  // partials, band lists and counters are complete
         if (!band_on) {
             if (blockIdx.x == 0 && tid == 0) *fallback = 1;
         } else {
             for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
                 // statistics above the band (fixed-order reduction of the per-block partials)
                 double s = 0.0, n = 0.0;
-                for (int b = tid; b < nblk; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
+                for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
                 ssum[tid] = s; scnt[tid] = n;
                 __syncthreads();
                 for (int off = T / 2; off > 0; off >>= 1) {
@@ -637,7 +663,7 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
         // ---- reduce the per-block partials: block b owns columns b, b+nblk, ...
         for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
             double s = 0.0, n = 0.0;
-            for (int b = tid; b < nblk; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
+            for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
             ssum[tid] = s; scnt[tid] = n;
             __syncthreads();
             for (int off = T / 2; off > 0; off >>= 1) {
@@ -648,6 +674,7 @@ __global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpAr
             __syncthreads();
         }
         grid.sync();
+        npart = nblk;                                  // from now on the partials come from this grid's passes
         // ---- new thresholds (identical in every block) and the convergence test
         if (tid == 0) s_changed = 0;
         __syncthreads();
@@ -761,7 +788,7 @@ extern "C" size_t sp_prox_work_doubles(int d, int k) {
     // the psgd epoch additionally keeps [n_orders*k] thresholds + the fused kernel's partials in
     // front (n_orders <= SP_MAXDEG-1)
     return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64 + (size_t)(SP_MAXDEG) * cols * (2 * 148 * 2 + 3) +
-           (size_t)(d + 7) / 8 + 1 + (size_t)(SP_MAXDEG) * cols * (UP_BAND_CAP + 4) + 128;
+           (size_t)(d + 7) / 8 + 1 + up_tail_offset((size_t)SP_MAXDEG * cols) + (size_t)(SP_MAXDEG) * cols * (UP_BAND_CAP + 4) + 128;
 }
 
 extern "C" int sp_get_eta(int lr, double eta0, double alpha, double beta, double power_t, int64_t it,
@@ -934,7 +961,7 @@ extern "C" size_t sp_psgd_lazy_work_doubles(int n_orders, int k) {
     const size_t ncol = (size_t)n_orders * k;
     // + persistent tail: state[2] | band counters | band[ncol][UP_BAND_CAP]  (must be zero-initialised
     // before the first sp_psgd_update_prox call of a fit)
-    return 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64 + 8 + ncol + (ncol + 3) / 2 + 1 + ncol * (size_t)UP_BAND_CAP + 8;
+    return up_tail_offset(ncol) + 8 + ncol + (ncol + 3) / 2 + 1 + ncol * (size_t)UP_BAND_CAP + 8;
 }
 
 extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
@@ -960,15 +987,20 @@ extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, 
     const long long need = ((long long)d + rpp - 1) / rpp;
     if (nblk > need) nblk = (int)need;
     const size_t ncol = (size_t)n_orders * k;
+    // update pass: plain streaming launch, 256 threads, up to UP_PART_MAX blocks
+    const int rppA = 256 / (k < 256 ? k : 256);
+    long long nblkA = ((long long)d + rppA - 1) / rppA;
+    if (nblkA > UP_PART_MAX) nblkA = UP_PART_MAX;
+    if (k > 256) nblkA = 0;                          // (wide models: update pass inside the cooperative kernel)
     UpArgs a;
     a.P = P_odk; a.G = grad_P; a.n_orders = n_orders; a.d = d; a.k = k;
     a.c = eta_P / batch; a.den = 1.0 + eta_P * beta; a.strength = strength; a.reg = reg;
     a.thr = col_thresh;
-    a.psum = work; a.pcnt = work + (size_t)nblk * ncol; a.colres = a.pcnt + (size_t)nblk * ncol;
-    // persistent tail of the work buffer (laid out for the largest grid so that it does not move):
-    // state[2] | band_n[ncol+1] ints (padded) | band[ncol][UP_BAND_CAP]
+    a.psum = work; a.pcnt = work + (size_t)UP_PART_MAX * ncol; a.colres = a.pcnt + (size_t)UP_PART_MAX * ncol;
+    a.nblk_part = (int)nblkA;
+    // persistent tail of the work buffer: state | band counters | band[ncol][UP_BAND_CAP]
     {
-        double *tail = work + 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64;
+        double *tail = work + up_tail_offset(ncol);
         a.state = tail;                                                  // [8 + ncol]
         a.band_n = reinterpret_cast<int *>(tail + 8 + ncol);             // [ncol + 2] ints
         a.band = tail + 8 + ncol + (ncol + 3) / 2 + 1;
@@ -979,6 +1011,11 @@ extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, 
     cudaStream_t st = (cudaStream_t)stream;
     SP_CUDA(cudaMemsetAsync(a.band_n, 0, sizeof(int) * (ncol + 2), st));
     sp_prof_begin(SP_PROF_PROX, st);
+    if (nblkA > 0) {
+        psgd_update_stats_kernel<<<(int)nblkA, 256, 0, st>>>(a);
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) { sp_prof_end(st); return sp_check_cuda(e0, "psgd_update_stats_kernel launch"); }
+    }
     cudaError_t e = cudaLaunchCooperativeKernel((void *)psgd_update_prox_kernel, dim3(nblk), dim3(UP_THREADS), args, 0, st);
     sp_prof_end(st);
     return sp_check_cuda(e, "psgd_update_prox_kernel launch");
@@ -1017,7 +1054,7 @@ extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_od
         SP_LAUNCH_CHECK("zero_kernel");
         // persistent selection state (previous strength) of sp_psgd_update_prox: none yet
         const size_t ncol = (size_t)n_orders * k;
-        SP_CUDA(cudaMemsetAsync(scratch + 2 * (size_t)148 * 2 * ncol + 2 * ncol + 64, 0, (8 + ncol) * sizeof(double), st));
+        SP_CUDA(cudaMemsetAsync(scratch + up_tail_offset(ncol), 0, (8 + ncol) * sizeof(double), st));
     }
     int64_t it = *it_io_host;
     for (int b0 = 0; b0 < n; b0 += batch_size) {           // psgd.py:150-198
