@@ -224,7 +224,7 @@ def choose_geometry(ds, solver, n_cta=None, threads=None):
     return int(n_cta), int(threads)
 
 
-WINDOW_SIZES = (256, 128, 64, 32, 16, 8, 4, 2, 1)
+WINDOW_SIZES = (256, 192, 128, 96, 64, 48, 32, 24, 16, 12, 8, 4, 2, 1)
 
 
 class WindowPlan:
@@ -275,7 +275,7 @@ class WindowPlan:
         for B in WINDOW_SIZES:
             if B < self.min_window:
                 break
-            if self.pbcd_shape is not None and B > 64:
+            if self.pbcd_shape is not None and B > 32:   # measured at C3: 16-32 positions per window is best
                 continue
             f = min(1.0, (2 * H + 1) * B * row / max(ds.n_features, 1))   # expected hot fraction
             if f <= self.max_hot_frac and 0.5 * B * col * f <= self.slot_cap:
