@@ -237,6 +237,34 @@ int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_or
                   int fit_linear, double eta0, int learning_rate, double power_t, int batch_size,
                   int64_t *it_io_host, double *loss_sum, double *work, sp_stream stream);
 
+/* ------------------------------------------------------------------------------ objective */
+/* The quantity the reference's update rules minimise but never evaluate
+ * (sparse_factorization_machines.py:181-188, :265-272):
+ *     sum_i loss(y_pred_i, y_i) + alpha/2 |w|^2 + beta/2 |P|^2 + gamma * Omega(P).
+ * Three device reductions give its parts; each overwrites out[0] (device) and is deterministic.
+ *
+ * sp_loss_sum: sum_i loss(y_pred[i*pred_stride], y[i*y_stride])   (loss.py:19-20, :34-41, :61-65);
+ *              the strides let it read the pcd sample records {y_pred, y, ...} in place.
+ * sp_sqnorm  : sum_i v[i]^2.
+ * work for both: sp_sum_work_doubles() doubles. */
+int sp_loss_sum(const double *y_pred, int pred_stride, const double *y, int y_stride, int n, int loss,
+                double *work, double *out, sp_stream stream);
+int sp_sqnorm(const double *v, int64_t len, double *work, double *out, sp_stream stream);
+size_t sp_sum_work_doubles(void);
+
+/* Omega(P) of one order, P_dk feature-major [d,k] -- the regularizer classes' `eval`:
+ *   l1         sum_js |p_js|                                  (l1.py:17-18, entrywise)
+ *   l21        sum_j |p_j|_2                                  (l21.py:19-21)
+ *   squaredl12 sum_s (sum_j |p_js|)^2                         (squaredl12.py:20-22)
+ *   squaredl21 (sum_j |p_j|_2)^2                              (squaredl21.py:23-25)
+ *   omegati    sum_s e_degree(|p_1s|..|p_ds|); degree=-1: sum_s prod_j (1+|p_js|)  (omegati.py:19-47)
+ *   omegacs    e_degree(|p_1|_2..|p_d|_2);     degree=-1: prod_j (1+|p_j|_2)      (omegacs.py:22-39)
+ * (e_m = m-th elementary symmetric polynomial).  degree is ignored by the first four.
+ * work: sp_reg_eval_work_doubles(d, k) doubles. */
+int sp_reg_eval(const double *P_dk, int d, int k, int reg, int degree, double *work, double *out,
+                sp_stream stream);
+size_t sp_reg_eval_work_doubles(int d, int k);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,10 @@ def lib():
         L.sp_oracle_kernel_rows.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp]
         L.sp_oracle_get_eta.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_int64, _dp, _dp]
+        L.sp_oracle_loss_sum.restype = C.c_double
+        L.sp_oracle_loss_sum.argtypes = [C.c_int, C.c_int, _dp, _dp]
+        L.sp_oracle_reg_eval.restype = C.c_double
+        L.sp_oracle_reg_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp]
         _LIB = L
     return _LIB
 
@@ -492,3 +496,52 @@ def fit_all_subsets(X, y, loss="squared", n_components=2, solver="pcd", beta=1, 
         raise ValueError(f"Solver {solver} is not supported.")
     out.update(P_=P_, y_pred=y_pred, n_iter_=it, converged=converged)
     return out
+
+
+# --------------------------------------------------------------------------- objective
+def loss_sum(y_pred, y, loss):
+    """sum_i loss(y_pred_i, y_i) (loss.py:19-20, :34-41, :61-65), ascending i."""
+    y_pred = np.ascontiguousarray(y_pred, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return float(lib().sp_oracle_loss_sum(len(y), LOSS_IDS[loss], _d(y_pred), _d(y)))
+
+
+def reg_eval(P_kd, regularizer, degree):
+    """Omega(P) of one order given as the reference stores it, P_kd [k,d] (regularizer `eval`
+    methods: l1.py:17-18, l21.py:19-21, squaredl12.py:20-22, squaredl21.py:23-25, omegati.py:19-47,
+    omegacs.py:22-39); degree=-1 for the all-subsets model."""
+    P_dk = np.ascontiguousarray(np.asarray(P_kd, dtype=np.float64).T)
+    d, k = P_dk.shape
+    return float(lib().sp_oracle_reg_eval(REG_IDS[regularizer], int(degree), d, k, _d(P_dk)))
+
+
+def objective_fm(X, y, P_, w_, lams_, degree=2, loss="squared", regularizer="squaredl12", alpha=1,
+                 beta=1, gamma=1, mean=False, fit_lower="explicit", fit_linear=True):
+    """sum_i loss + alpha/2 |w|^2 + beta/2 |P|^2 + gamma Omega(P), the quantity the update rules of
+    sparse_factorization_machines.py:175-353 minimise (alpha, beta, gamma times n when mean=True,
+    :181-188).  Order o of P_ has degree `degree - o` (explicit lower orders, :207-225).
+    Returns a dict of the parts and the total."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    X = _augment(X, fit_lower, fit_linear, degree)
+    n = X.shape[0]
+    a_, b_, g_ = (alpha * n, beta * n, gamma * n) if mean else (alpha, beta, gamma)
+    y_pred = fm_output(X, P_, w_, lams_, degree, fit_linear, fit_lower)
+    parts = {"loss": loss_sum(y_pred, y, loss),
+             "l2_w": float(np.dot(w_, w_)) if fit_linear else 0.0,
+             "l2_P": float(sum(np.sum(P_[o] ** 2) for o in range(P_.shape[0]))),
+             "omega": float(sum(reg_eval(P_[o], regularizer, degree - o) for o in range(P_.shape[0])))}
+    parts["total"] = parts["loss"] + 0.5 * a_ * parts["l2_w"] + 0.5 * b_ * parts["l2_P"] + g_ * parts["omega"]
+    return parts
+
+
+def objective_all_subsets(X, y, P_, lams_, loss="squared", regularizer="omegati", beta=1, gamma=1,
+                          mean=False):
+    """As objective_fm for sparse_all_subsets.py:80-201 (no linear term, degree = -1)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = X.shape[0]
+    b_, g_ = (beta * n, gamma * n) if mean else (beta, gamma)
+    y_pred = np.ascontiguousarray(poly_predict(X, P_, lams_, "all-subsets"))
+    parts = {"loss": loss_sum(y_pred, y, loss), "l2_w": 0.0, "l2_P": float(np.sum(P_ ** 2)),
+             "omega": reg_eval(P_, regularizer, -1)}
+    parts["total"] = parts["loss"] + 0.5 * b_ * parts["l2_P"] + g_ * parts["omega"]
+    return parts

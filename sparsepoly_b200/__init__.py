@@ -6,8 +6,10 @@ from .estimators import (
     SparseFactorizationMachineClassifier,
     SparseFactorizationMachineRegressor,
 )
+from .objective import objective
 
 __all__ = [
+    "objective",
     "SparseAllSubsetsClassifier",
     "SparseAllSubsetsRegressor",
     "SparseFactorizationMachineClassifier",

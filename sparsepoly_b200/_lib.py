@@ -83,6 +83,11 @@ SIGNATURES = {
     "sp_prox": (_i, [_vp, _i, _i, _i, _d, _vp, _vp]),
     "sp_psgd_epoch": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp,
                            _i, _d, _i, _d, _i, C.POINTER(C.c_int64), _vp, _vp, _vp]),
+    "sp_loss_sum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sp_sqnorm": (_i, [_vp, C.c_int64, _vp, _vp, _vp]),
+    "sp_sum_work_doubles": (C.c_size_t, []),
+    "sp_reg_eval": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sp_reg_eval_work_doubles": (C.c_size_t, [_i, _i]),
 }
 
 _LIB = None

@@ -225,3 +225,36 @@ def psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss,
         psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, b_global, fit_linear)
         for o in range(n_orders):
             prox(P_odk[o], reg, strength, work)
+
+
+# ------------------------------------------------------------------------------ objective
+def _sum_work(device):
+    return torch.empty(int(_L().sp_sum_work_doubles()), dtype=_f64, device=device)
+
+
+def loss_sum(y_pred, y, loss, n, pred_stride=1, y_stride=1):
+    """sum_i loss(y_pred[i*pred_stride], y[i*y_stride]) (loss.py:19-20, :34-41, :61-65) as a
+    1-element device tensor; the strides let it read the sweep records {y_pred, y, ...} in place."""
+    out = torch.empty(1, dtype=_f64, device=y_pred.device)
+    _lib.check(_L().sp_loss_sum(_ptr(y_pred), int(pred_stride), _ptr(y), int(y_stride), int(n),
+                                _lib.LOSS_IDS[loss], _ptr(_sum_work(y_pred.device)), _ptr(out), _stream()))
+    return out
+
+
+def sqnorm(t):
+    """sum of squares of a contiguous fp64 device tensor (1-element device tensor)."""
+    out = torch.empty(1, dtype=_f64, device=t.device)
+    _lib.check(_L().sp_sqnorm(_ptr(t), int(t.numel()), _ptr(_sum_work(t.device)), _ptr(out), _stream()))
+    return out
+
+
+def reg_eval(P_dk, reg, degree):
+    """Omega(P) of one order, P_dk feature-major [d,k] (the regularizer classes' `eval`:
+    l1.py:17-18, l21.py:19-21, squaredl12.py:20-22, squaredl21.py:23-25, omegati.py:19-47,
+    omegacs.py:22-39); degree=-1: all-subsets.  1-element device tensor."""
+    d, k = P_dk.shape
+    out = torch.empty(1, dtype=_f64, device=P_dk.device)
+    work = torch.empty(int(_L().sp_reg_eval_work_doubles(int(d), int(k))), dtype=_f64, device=P_dk.device)
+    _lib.check(_L().sp_reg_eval(_ptr(P_dk), int(d), int(k), _lib.REG_IDS[reg], int(degree), _ptr(work),
+                                _ptr(out), _stream()))
+    return out

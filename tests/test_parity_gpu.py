@@ -50,6 +50,29 @@ def test_matches_reference_golden(name):
         assert est.it_ == int(arr["it_"])
     pred = est.decision_function(arr["Xte"]) if rec["clf"] else est.predict(arr["Xte"])
     assert rel_err(pred, arr["pred_te"]) <= TOL
+    _check_objective(est, X, arr["y"], arr["P_"], arr.get("w_"))
+
+
+def _check_objective(est, X, y_pm1, P_ref, w_ref, tol=TOL):
+    """Objective of the CUDA fit (device evaluator, sparsepoly_b200.objective) against the oracle's
+    evaluation of the REFERENCE's (or the oracle's) fitted parameters: 1e-9 relative (north_star)."""
+    from sparsepoly_b200.objective import objective
+    from oracle import oracle as O
+    y_user = est.label_binarizer_.inverse_transform(y_pm1 > 0) if hasattr(est, "label_binarizer_") else y_pm1
+    got = objective(est, X, y_user)
+    if hasattr(est, "degree"):
+        w = w_ref if w_ref is not None else np.zeros(P_ref.shape[2])
+        want = O.objective_fm(X, y_pm1, P_ref, w, est.lams_, degree=est.degree, loss=est.loss,
+                              regularizer=est.regularizer, alpha=est.alpha, beta=est.beta,
+                              gamma=est.gamma, mean=est.mean, fit_lower=est.fit_lower,
+                              fit_linear=est.fit_linear)
+    else:
+        want = O.objective_all_subsets(X, y_pm1, P_ref, est.lams_, loss=est.loss,
+                                       regularizer=est.regularizer, beta=est.beta, gamma=est.gamma,
+                                       mean=est.mean)
+    for part in ("loss", "l2_w", "l2_P", "omega", "total"):
+        assert abs(got[part] - want[part]) <= tol * max(abs(want[part]), 1e-300), (part, got, want)
+    return got
 
 
 @pytest.mark.parametrize("n_cta,threads", [(2, 32), (4, 64), (8, 32), (16, 32), (1, 256), (2, 128)])
@@ -209,6 +232,7 @@ def _compare_fm(kw, X, y, tol=TOL):
     assert rel_err(est.P_, out["P_"]) <= tol
     assert same_support(est.P_, out["P_"])
     assert rel_err(est.w_, out["w_"]) <= tol
+    _check_objective(est, X, y, out["P_"], out["w_"], tol)
     frac = float(np.mean(out["P_"] != 0))
     return est, out, frac
 
@@ -249,6 +273,50 @@ def test_all_subsets_c4_scaled_matches_oracle():
     out = O.fit_all_subsets(X, y, **kw)
     assert rel_err(est.P_, out["P_"]) <= TOL
     assert same_support(est.P_, out["P_"])
+    _check_objective(est, X, y, out["P_"], None)
+
+
+@pytest.mark.parametrize("d,k", [(1, 1), (37, 3), (500, 16), (5000, 32), (3000, 100), (100000, 8), (0, 4)])
+def test_reg_eval_kernels_match_oracle(d, k):
+    """sp_reg_eval (objective.cu) for every regularizer x degree against the oracle's sequential
+    folds; tree-ordered sums of non-negative terms: 1e-12."""
+    import torch
+    from sparsepoly_b200 import solvers
+    from oracle import oracle as O
+    rng = np.random.RandomState(d + k)
+    scale = 0.5 / max(d, 1) ** 0.5                      # keeps prod_j (1 + |p_j|) finite
+    P_dk = scale * rng.randn(d, k) * (rng.rand(d, k) < 0.6)
+    P_dev = torch.from_numpy(P_dk).cuda()
+    P_kd = np.ascontiguousarray(P_dk.T)
+    for reg in ("l1", "l21", "squaredl12", "squaredl21"):
+        got = solvers.reg_eval(P_dev, reg, 2).item()
+        want = O.reg_eval(P_kd, reg, 2)
+        assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300), (reg, got, want)
+    for reg in ("omegati", "omegacs"):
+        for degree in (1, 2, 3, 4, 5, -1):
+            got = solvers.reg_eval(P_dev, reg, degree).item()
+            want = O.reg_eval(P_kd, reg, degree)
+            assert abs(got - want) <= 1e-12 * max(abs(want), 1e-300), (reg, degree, got, want)
+    with pytest.raises(ValueError):
+        solvers.reg_eval(P_dev, "omegati", 9)
+
+
+@pytest.mark.parametrize("loss", ["squared", "logistic", "squared_hinge"])
+def test_loss_sum_and_sqnorm_match_oracle(loss):
+    import torch
+    from sparsepoly_b200 import solvers
+    from oracle import oracle as O
+    rng = np.random.RandomState(3)
+    for n in (1, 1000, 300001):
+        p = 8.0 * rng.randn(n)
+        y = np.where(rng.rand(n) < 0.5, -1.0, 1.0)
+        rec = np.zeros((n, 4))
+        rec[:, 0], rec[:, 1] = p, y
+        rec_dev = torch.from_numpy(rec).cuda().reshape(-1)
+        got = solvers.loss_sum(rec_dev, rec_dev[1:], loss, n, pred_stride=4, y_stride=4).item()
+        want = O.loss_sum(p, y, loss)
+        assert abs(got - want) <= 1e-12 * abs(want)
+        assert abs(solvers.sqnorm(torch.from_numpy(p).cuda()).item() - float(np.dot(p, p))) <= 1e-12 * np.dot(p, p)
 
 
 def test_predict_matches_oracle_and_kernels_module():
