@@ -312,6 +312,9 @@ def run_sweep_workload(name, args, rank, world, local):
         import torch.distributed as dist
         dist.barrier()
     lib.sp_profile_enable(1)
+    import ctypes as C
+    _z = (C.c_ulonglong * 2)()
+    lib.sp_wspec_read(_z)                       # reset the speculation counters
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -329,8 +332,12 @@ def run_sweep_workload(name, args, rank, world, local):
     cnt = (C.c_longlong * 8)()
     lib.sp_profile_collect(ms, cnt)
     lib.sp_profile_enable(0)
+    wspec = (C.c_ulonglong * 2)()
+    lib.sp_wspec_read(wspec)
     sync()
     nz_frac = float(np.mean(est.P_ != 0))
+    nz_by_order = ([float(np.mean(est.P_[o] != 0)) for o in range(est.P_.shape[0])]
+                   if est.P_.ndim == 3 else [nz_frac])
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,7 +361,9 @@ def run_sweep_workload(name, args, rank, world, local):
                      "us_per_sequential_step": sweep_ms * 1e3 / args.steps / coords},
         "gpu_launches": int(sum(cnt)),
         "kernel_ms": {"rows": ms[0], "regcache": ms[1], "sweep_pcd": ms[2], "sweep_pbcd": ms[3]},
-        "clocks": clocks, "p_nonzero_frac": nz_frac,
+        "clocks": clocks, "p_nonzero_frac": nz_frac, "p_nonzero_frac_by_order": nz_by_order,
+        "zero_update_speculation": {"positions": int(wspec[0]), "rejected": int(wspec[1]),
+                                    "note": "window-sweep positions evaluated without per-record waits (pcd_window.cu)"},
         "geometry": ({"sweep": "window", **est._dev_state["plan"].wplan.stats}
                      if getattr(est._dev_state["plan"], "mode", "cluster") == "window" else
                      {"sweep": "cluster", "n_cta": est._dev_state["plan"].n_cta,
@@ -450,6 +459,9 @@ def run_psgd_workload(args, rank, world, local):
     if group is not None:
         dist.barrier()
     lib.sp_profile_enable(1)
+    import ctypes as C
+    _z = (C.c_ulonglong * 2)()
+    lib.sp_wspec_read(_z)                       # reset the speculation counters
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -36,6 +36,7 @@ extern "C" {
 #define SP_MAX_HOT_FEATURES 16
 #define SP_PBCD_ENT_PER_SLOT 3  /* pbcd window plan: hot nonzeros per window <= 3*slot_cap (pcd: 2*slot_cap) */
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
+#define SP_WPLAN_NO_SPECULATION 1   /* sp_wplan.flags: workers always wait for the write-backs they depend on */
 
 typedef void *sp_stream;
 
@@ -82,8 +83,8 @@ typedef struct sp_plan {
  * all other CTAs in bulk. */
 typedef struct sp_wplan {
     int32_t window, horizon, n_windows, slot_cap;
-    int32_t near, reserved;   /* hot nonzeros whose slot was last touched <= near positions back are
-                                 "late": evaluated by the engine's chain warp itself */
+    int32_t near, flags;      /* hot nonzeros whose slot was last touched <= near positions back are
+                                 "late": evaluated by the engine's chain warp itself; flags: SP_WPLAN_* */
     const int32_t *cflag;     /* [nnz] CSC row index | 0x80000000 when the nonzero is hot */
     const int32_t *ht_ptr;    /* [d+1] offsets of the hot nonzeros of position t */
     const int32_t *ht_cls;    /* [d] per position: #late-only | #late+fwd << 8 | #fwd-only << 16 (the
@@ -139,6 +140,9 @@ size_t sp_pbcd_wplan_base_doubles(void);
 /* debug: cycle counters of the window sweep's roles (zeros unless the library was built with
  * -DSP_WPROF); out_host [16] */
 int sp_wprof_read(unsigned long long *out_host);
+/* zero-update speculation of the window sweep: out_host[0] = positions evaluated speculatively,
+ * out_host[1] = speculations rejected (redone exactly), since the last call */
+int sp_wspec_read(unsigned long long *out_host /*[2]*/);
 /* debug: per-position timestamps of window 100 of the last sweep; out_host [SP_WINDOW_MAX*8] */
 int sp_wtrace_read(long long *out_host);
 /* slots (hot sample records) the engine CTA can hold in shared memory for records of this stride */

@@ -31,7 +31,7 @@ class SpDataset(C.Structure):
 class SpWPlan(C.Structure):
     """struct sp_wplan (include/sparsepoly_b200.h)."""
     _fields_ = [("window", C.c_int32), ("horizon", C.c_int32), ("n_windows", C.c_int32),
-                ("slot_cap", C.c_int32), ("near", C.c_int32), ("reserved", C.c_int32), ("cflag", _vp),
+                ("slot_cap", C.c_int32), ("near", C.c_int32), ("flags", C.c_int32), ("cflag", _vp),
                 ("ht_ptr", _vp), ("ht_cls", _vp), ("h_sd", _vp), ("h_x", _vp), ("n_slots", _vp),
                 ("slot_row", _vp), ("sync", _vp), ("res", _vp), ("base", _vp)]
 
@@ -63,6 +63,7 @@ SIGNATURES = {
     "sp_pbcd_wplan_base_doubles": (C.c_size_t, []),
     "sp_wprof_read": (_i, [C.POINTER(C.c_ulonglong)]),
     "sp_wtrace_read": (_i, [C.POINTER(C.c_longlong)]),
+    "sp_wspec_read": (_i, [C.POINTER(C.c_ulonglong)]),
     "sp_transpose_f64": (_i, [_vp, _vp, _i, _i, _vp]),
     "sp_rec_stride": (_i, [_i]),
     "sp_predict": (_i, [_DSP, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),

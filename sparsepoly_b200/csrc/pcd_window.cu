@@ -15,6 +15,14 @@
 //     H = 1 a cold record is untouched for a whole window on either side, so BASE(w) runs while
 //     the engine is still in window w-1 and the engine never waits for the bulk CTAs.
 //   * windows are handed over through three counters in global memory (release / acquire).
+//   * ZERO-UPDATE SPECULATION (ANOVA sweeps, windows whose coordinates are almost all zero -- the
+//     regime the sparsity-inducing regularizers drive the fit into): a coordinate whose update is 0
+//     changes no record, so nothing depends on it.  Workers then do not wait for the write-backs of
+//     the positions their records depend on: they snapshot the chain warp's progress C (all nonzero
+//     updates decided before C are applied: counter nz_done), read the records, and send C with their
+//     sums; the chain warp accepts them iff no position in [C, t) had a nonzero update, else the
+//     worker redoes the position once the chain is parked on it.  Results are identical to the
+//     non-speculative path (same operations on the same record values).
 // Per-sample terms are computed exactly as the reference does; only the order in which a column's
 // terms are summed differs (as in any parallel reduction).
 #include "common.cuh"
@@ -29,7 +37,7 @@ constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 4 * 4 + 2 * 8
 constexpr int W_REC_BYTES = 196608;            // shared memory reserved for the hot record slots
 
 struct WArgs {
-    int d, B, H, nwin, slot_cap, stride, reg;
+    int d, B, H, nwin, slot_cap, stride, reg, spec;
     const int32_t *indptr;       // CSC
     const int32_t *cflag;
     const double *data;
@@ -60,6 +68,7 @@ enum { TP_ENG_WAIT = 0, TP_ENG_STAGE, TP_ENG_ROLE, TP_ENG_FLUSH, TP_CH_WAIT, TP_
        TP_WK_TERMS, TP_WK_RED, TP_WK_RESWAIT, TP_WK_WB, TP_BULK_WAITB, TP_BULK_BASE, TP_BULK_WAITW, TP_BULK_WB,
        TP_N };
 __device__ unsigned long long g_wprof[TP_N];
+__device__ unsigned long long g_wspec[2];            // speculated positions, rejected speculations
 __device__ long long g_wtrace[SP_WINDOW_MAX * 8];   // per-position timestamps of window 100 (SP_WPROF)
 #if defined(SP_WPROF) && SP_WPROF >= 2
 #define TP_DECL unsigned long long tp_acc[TP_N] = {}; long long tp_t0 = clock64();
@@ -121,6 +130,24 @@ __device__ __forceinline__ void cell_store_a(uint32_t addr, double v, int tag) {
                  "l"((long long)tag)
                  : "memory");
 }
+// cell with the full 64-bit tag: position in the low word, the worker's progress snapshot in the high
+__device__ __forceinline__ void cell_load_a64(uint32_t addr, double &v, long long &tag) {
+    unsigned long long a, b;
+    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+    v = __longlong_as_double((long long)a);
+    tag = (long long)b;
+}
+__device__ __forceinline__ unsigned long long lds_u64_volatile(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u64_volatile(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+#define SP_CS_EXACT 0x7fff          // "snapshot" of a cell computed without speculation
+#define SP_TAG_REDO (-2)            // result cell: speculation rejected, recompute
+__device__ __forceinline__ long long cell_tag(int t, int cs) { return (long long)(unsigned)t | ((long long)cs << 32); }
 __device__ __forceinline__ double lds_f64_a(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -279,7 +306,12 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     // chain-warp state (viol, regularizer cache): lives in shared memory between windows so that it
     // only occupies registers inside the chain loop
     __shared__ double chain_state[1 + SP_MAXDEG];
+    __shared__ unsigned long long prog_s;      // chain progress in this window: decided positions | nonzero updates << 32
+    __shared__ int nzdone_s;                   // nonzero updates of this window whose write-back is complete
+    __shared__ int specoff_s;                  // too many rejections: the rest of the window runs exactly
+    __shared__ unsigned long long spec_cnt_s[2];
     if (tid == 0) {
+        spec_cnt_s[0] = 0; spec_cnt_s[1] = 0;
         chain_state[0] = *a.viol;
 #pragma unroll
         for (int t = 0; t < NC; t++) chain_state[1 + t] = (KIND == KIND_LINEAR) ? 0.0 : a.regstate[t];
@@ -302,9 +334,12 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             const int sl = u * WT + tid;
             rows0[u] = sl < ns ? srow[sl] : -1;
         }
+        int my_nz = 0;
         for (int tl = tid; tl < nb; tl += WT) {
             const int t = t0 + tl, j = a.idx_feat[t];
-            pold_s[tl] = a.prow[j];
+            const double pv = a.prow[j];
+            pold_s[tl] = pv;
+            my_nz |= pv != 0.0;
             cn_s[tl] = (KIND == KIND_LINEAR) ? a.cns[j] : 0.0;
             hp_s[tl] = a.ht_ptr[t] - h0;
             cls_s[tl] = a.ht_cls[t];
@@ -329,10 +364,14 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             }
         }
         if (tid == 0) {
+            prog_s = 0ull; nzdone_s = 0; specoff_s = 0;
             wait_ge(a.base_cnt + w, nbulk);
             if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
         }
-        __syncthreads();
+        // speculate when (almost) every coordinate of the window starts at zero: under l1 / squaredl12 /
+        // omegati such coordinates nearly always stay there (nb <= WT: one position per thread)
+        const int nz_old = __syncthreads_count(my_nz);
+        const bool win_spec = KIND == KIND_FM && a.spec && nz_old * 32 <= nb;
         if (tid == 32) TP_MARK(TP_ENG_WAIT)
         // ---- stage, part 2 (data the bulk CTAs produce): cold partial sums, hot sample records
         for (int tl = tid; tl < nb; tl += WT) base_s[tl] = __ldcg(a.base + t0 + tl);
@@ -374,10 +413,12 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             double2 *resg = a.res + t0;
             const bool lane0 = lane == 0;
             double va, vb = 0.0, pold;
-            int ta, tb;
-            cell_load_a(pa, va, ta);
-            cell_load_a(pb, vb, tb);
+            long long ta, tb;
+            cell_load_a64(pa, va, ta);
+            cell_load_a64(pb, vb, tb);
             pold = lds_f64_a(pp);
+            int last_nz = -1, nz_issued = 0, n_rej = 0;
+            unsigned long long n_spec = 0;
             for (int tl = 0; tl < nb; tl++) {
                 const int t = t0 + tl;
                 // ---- this position's chain nonzeros, one per lane: [late only][late+fwd][fwd only].
@@ -410,17 +451,34 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     }
                 }
                 const double cn = (KIND == KIND_LINEAR && nL > 0) ? cn_s[tl] : 0.0;
-                while (ta != t) cell_load_a(pa, va, ta);
+                while ((int)ta != t) cell_load_a64(pa, va, ta);
                 if (KIND != KIND_LINEAR) {
-                    while (tb != t) cell_load_a(pb, vb, tb);
+                    while ((int)tb != t) cell_load_a64(pb, vb, tb);
+                }
+                bool redone = false;
+                if (KIND == KIND_FM) {
+                    const int cs = (int)(ta >> 32);
+                    n_spec += cs != SP_CS_EXACT;
+                    if (last_nz >= cs) {
+                        // a position the worker had not seen decided changed records: have it redo this one
+                        // (it finds the chain parked here, i.e. everything before applied)
+                        if (lane0) {
+                            cell_store_a(pr, 0.0, SP_TAG_REDO);
+                            mbar_arrive(pm);
+                            if (++n_rej == 4) flag_store(&specoff_s, 1);
+                        }
+                        redone = true;
+                        do cell_load_a64(pa, va, ta); while ((int)ta != t || (int)(ta >> 32) != SP_CS_EXACT);
+                        do cell_load_a64(pb, vb, tb); while ((int)tb != t || (int)(tb >> 32) != SP_CS_EXACT);
+                    }
                 }
                 TR(w, tl, 3)
                 // inputs of the next position: in flight while this one is computed (stale tags of an
                 // earlier window never match)
                 double nva, nvb, npold;
-                int nta, ntb;
-                cell_load_a(pa + 16, nva, nta);
-                cell_load_a(pb + 16, nvb, ntb);
+                long long nta, ntb;
+                cell_load_a64(pa + 16, nva, nta);
+                cell_load_a64(pb + 16, nvb, ntb);
                 npold = lds_f64_a(pp + 8);
                 if (lane >= nL && lane < nC) {
                     // fwd-only records: their last writer may have been a worker, whose write-back is
@@ -468,10 +526,13 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     }
                     __syncwarp();
                 }
+                if (upd != 0.0) { last_nz = tl; nz_issued++; }
                 if (lane0) {
                     cell_store_a(pr, KIND == KIND_ALL ? pnew : upd, t);
-                    mbar_arrive(pm);
+                    if (!redone) mbar_arrive(pm);
                     __stcg(resg + tl, make_double2(upd, pnew));
+                    // after this warp's own record write-backs above (program order + __syncwarp)
+                    sts_u64_volatile(&prog_s, (unsigned long long)(unsigned)(tl + 1) | ((unsigned long long)(unsigned)nz_issued << 32));
                 }
                 viol += fabs(upd);
                 va = nva; vb = nvb; ta = nta; tb = ntb; pold = npold;
@@ -482,6 +543,8 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 chain_state[0] = viol;
 #pragma unroll
                 for (int q = 0; q < NC; q++) chain_state[1 + q] = cache[q];
+                spec_cnt_s[0] += n_spec;
+                spec_cnt_s[1] += (unsigned long long)n_rej;
             }
         } else {
             // =========================================================== workers
@@ -496,12 +559,26 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 const double cn = cn_s[tl];
                 const int cls = cls_s[tl];
                 const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff);
-                double tg = 0.0, th = 0.0;
                 TR(w, tl, 0)
                 int k_slot[KR];                                 // kept for the write-back (-1: none / not ours)
                 double k_x[KR], k_r[KR][R], k_dA[KR][ND];
+                double upd, pnew;
+              for (int attempt = 0;; attempt++) {
+                double tg = 0.0, th = 0.0;
 #pragma unroll
                 for (int u = 0; u < KR; u++) k_slot[u] = -1;
+                // speculative (or redone) evaluation: no per-record waits; instead every nonzero update the
+                // chain warp had decided when the snapshot was taken must have been applied
+                const bool spec = KIND == KIND_FM && (attempt > 0 || (win_spec && flag_load(&specoff_s) == 0));
+                int csnap = SP_CS_EXACT;
+                if (spec) {
+                    unsigned long long pg = 0;
+                    if (lane == 0) pg = lds_u64_volatile(&prog_s);
+                    pg = __shfl_sync(0xffffffffu, pg, 0);
+                    const int nzi = (int)(pg >> 32);
+                    while (flag_load(&nzdone_s) < nzi) {}
+                    if (attempt == 0) csnap = (int)(pg & 0xffffffffu);
+                }
                 for (int q0 = 0; q0 < ne; q0 += 32 * KR) {
                     int slot[KR], mydep[KR];
                     double x[KR];
@@ -515,7 +592,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                             slot[u] = sd & 0xffff;
                             if (sd & SP_ENT_FWD) slot[u] |= 0x10000;   // term ours, write-back the chain warp's
                             x[u] = ent_x[hs + e];
-                            if (dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
+                            if (!spec && dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
                         }
                     }
                     // wait (warp-uniformly: divergent waits would leave the warp fragmented for the
@@ -573,21 +650,27 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     v1 = eta * gamma / inv;
                 }
                 if (lane == 0) {
-                    if (KIND != KIND_LINEAR) cell_store(&cellB[tl], v1, t);
-                    cell_store(&cellA[tl], v0, t);
+                    if (KIND != KIND_LINEAR) cell_store(&cellB[tl], v1, cell_tag(t, csnap));
+                    cell_store(&cellA[tl], v0, cell_tag(t, csnap));
                 }
                 TRD(w, tl, 2, v0 + v1)
-#ifdef SP_SPIN_WAIT
                 Cell rc;
-                do { rc = cell_load(&rcell[tl]); } while ((int)rc.tag != t);
+                if (attempt == 0) {
+#ifdef SP_SPIN_WAIT
+                    do { rc = cell_load(&rcell[tl]); } while ((int)rc.tag != t && (int)rc.tag != SP_TAG_REDO);
 #else
-                mbar_wait(smem_u32(&mb_res[tl]), wpar);
-                const Cell rc = cell_load(&rcell[tl]);
+                    mbar_wait(smem_u32(&mb_res[tl]), wpar);
+                    rc = cell_load(&rcell[tl]);
 #endif
+                } else {
+                    do { rc = cell_load(&rcell[tl]); } while ((int)rc.tag != t);
+                }
+                if (KIND == KIND_FM && (int)rc.tag == SP_TAG_REDO) continue;
                 TR(w, tl, 5)
-                double upd, pnew;
                 if (KIND == KIND_ALL) { pnew = rc.v; upd = pold - pnew; }
                 else { upd = rc.v; pnew = 0.0; }
+                break;
+              }
                 if (KIND == KIND_ALL || upd != 0.0) {
 #pragma unroll
                     for (int u = 0; u < KR; u++) {
@@ -620,6 +703,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();                      // the write-back above before the flag
+                    if (upd != 0.0) atomicAdd_block(&nzdone_s, 1);
                     flag_store(&wbflag[tl], wtag);
                     mbar_arrive(smem_u32(&mb_wb[tl]));          // wakes the warps sleeping on this position
                 }
@@ -641,6 +725,8 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     }
     TP_FLUSH(tid == 0 || tid == 32)
     if (tid == 0) {
+        if (spec_cnt_s[0]) atomicAdd(&g_wspec[0], spec_cnt_s[0]);
+        if (spec_cnt_s[1]) atomicAdd(&g_wspec[1], spec_cnt_s[1]);
         *a.viol = chain_state[0];
         if (KIND != KIND_LINEAR) {
 #pragma unroll
@@ -715,6 +801,15 @@ extern "C" int sp_wprof_read(unsigned long long *out_host /*[16]*/) {
     return SP_OK;
 }
 
+// {positions evaluated speculatively, speculations rejected} since the last call
+extern "C" int sp_wspec_read(unsigned long long *out_host /*[2]*/) {
+    unsigned long long z[2] = {};
+    SP_CUDA(cudaDeviceSynchronize());
+    SP_CUDA(cudaMemcpyFromSymbol(out_host, g_wspec, sizeof(z)));
+    SP_CUDA(cudaMemcpyToSymbol(g_wspec, z, sizeof(z)));
+    return SP_OK;
+}
+
 extern "C" int sp_wtrace_read(long long *out_host /*[SP_WINDOW_MAX*8]*/) {
     SP_CUDA(cudaDeviceSynchronize());
     SP_CUDA(cudaMemcpyFromSymbol(out_host, g_wtrace, sizeof(long long) * SP_WINDOW_MAX * 8));
@@ -744,6 +839,7 @@ int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat,
     WArgs a = {};
     a.d = ds->n_features; a.B = wp->window; a.H = wp->horizon; a.nwin = wp->n_windows;
     a.slot_cap = wp->slot_cap; a.stride = rec_stride; a.reg = reg;
+    a.spec = (wp->flags & SP_WPLAN_NO_SPECULATION) ? 0 : 1;
     a.indptr = ds->csc_indptr; a.cflag = wp->cflag; a.data = ds->csc_data; a.idx_feat = idx_feat;
     a.ht_ptr = wp->ht_ptr; a.ht_cls = wp->ht_cls; a.h_sd = wp->h_sd; a.h_x = wp->h_x;
     a.n_slots = wp->n_slots; a.slot_row = wp->slot_row;

@@ -8,6 +8,7 @@ is stored with every entry, like the reference's ContiguousDataset / FortranData
 (dataset.py:18-57).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -311,6 +312,8 @@ class WindowPlan:
         s = _lib.SpWPlan()
         s.window, s.horizon, s.n_windows, s.slot_cap = B, self.horizon, n_windows, self.slot_cap
         s.near = self.near
+        # SPARSEPOLY_B200_SPEC=0: never speculate on zero updates (debug / A-B measurements)
+        s.flags = 1 if os.environ.get("SPARSEPOLY_B200_SPEC", "1") == "0" else 0
         s.cflag, s.ht_ptr, s.ht_cls = self.cflag.data_ptr(), self.ht_ptr.data_ptr(), self.ht_cls.data_ptr()
         s.h_sd, s.h_x = self.h_sd.data_ptr(), self.h_x.data_ptr()
         s.n_slots, s.slot_row = self.n_slots.data_ptr(), self.slot_row.data_ptr()

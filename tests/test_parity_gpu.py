@@ -145,6 +145,54 @@ def test_window_sweep_sparse_matches_oracle(tag, kernel, degree, clf, kw, window
     print(tag, plan.wplan.stats, "nonzero fraction of P_", frac)
 
 
+SPEC_CASES = [
+    # (tag, degree of the planted target, clf, estimator kwargs): regimes in which (almost) every coordinate
+    # sits at zero after the first epoch -> the window engine speculates on zero updates
+    ("sql12_1pct", 2, False, dict(degree=2, n_components=4, solver="pcd", regularizer="squaredl12", beta=1e-5,
+                                  gamma=4e-6, alpha=1e-3, max_iter=4, tol=-1.0, random_state=0, mean=True)),
+    ("sql12_5pct", 2, False, dict(degree=2, n_components=4, solver="pcd", regularizer="squaredl12", beta=1e-5,
+                                  gamma=1e-6, alpha=1e-3, max_iter=3, tol=-1.0, random_state=0, mean=True)),
+    ("omegati_1pct", 2, False, dict(degree=2, n_components=4, solver="pcd", regularizer="omegati", beta=1e-5,
+                                    gamma=1e-5, alpha=1e-3, max_iter=4, tol=-1.0, random_state=0, mean=True)),
+    ("l1_all_zero", 2, False, dict(degree=2, n_components=4, solver="pcd", regularizer="l1", beta=1e-5,
+                                   gamma=1e-4, alpha=1e-3, max_iter=3, tol=-1.0, random_state=0, mean=True)),
+    ("fm3_omegati_logistic", 3, True,
+     dict(degree=3, loss="logistic", n_components=4, solver="pcd", regularizer="omegati", beta=1e-6, gamma=1e-7,
+          alpha=1e-4, max_iter=3, tol=-1.0, random_state=0, mean=True, fit_lower="explicit", shuffle=True)),
+]
+
+
+def _wspec_read():
+    import ctypes as C
+    from sparsepoly_b200 import _lib
+    out = (C.c_ulonglong * 2)()
+    _lib.check(_lib.load().sp_wspec_read(out))
+    return int(out[0]), int(out[1])
+
+
+@pytest.mark.parametrize("window", [None, 32])
+@pytest.mark.parametrize("tag,degree,clf,kw", SPEC_CASES, ids=[c[0] for c in SPEC_CASES])
+def test_window_sweep_zero_update_speculation(tag, degree, clf, kw, window, monkeypatch):
+    """Sparse regimes: the engine's workers skip the per-record waits and the chain warp validates
+    (pcd_window.cu, ZERO-UPDATE SPECULATION).  Results must equal the oracle's to 1e-9 AND be bitwise
+    those of the non-speculative sweep (same operations on the same record values)."""
+    monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window" if window else "auto")
+    if window is not None:
+        monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
+    X, y = _problem(n=100000, d=5000, r=10, seed=5, kernel="anova", degree=degree, clf=clf)
+    _wspec_read()
+    est, out, frac = _compare_fm(kw, X, y)
+    n_spec, n_rej = _wspec_read()
+    assert est._dev_state["plan"].mode == "window"
+    assert n_spec > 0, "speculation never engaged"
+    assert n_rej < n_spec
+    print(tag, "nonzero fraction", frac, "speculated positions", n_spec, "rejected", n_rej)
+    monkeypatch.setenv("SPARSEPOLY_B200_SPEC", "0")
+    est0, _, _ = _compare_fm(kw, X, y)
+    assert _wspec_read() == (0, 0)
+    assert np.array_equal(est.P_, est0.P_) and np.array_equal(est.w_, est0.w_)
+
+
 @pytest.mark.parametrize("horizon", [0, 1])
 def test_window_sweep_all_subsets_matches_oracle(horizon, monkeypatch):
     import sparsepoly_b200 as S
