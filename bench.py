@@ -391,6 +391,10 @@ def run_sweep_workload(name, args, rank, world, local):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    if rank == 0:
+        # objective the fit reached (device evaluator, csrc/objective.cu; outside every timed region)
+        from sparsepoly_b200.objective import objective
+        result["objective"] = objective(est2, X, y)
     result["e2e"] = {"value": e2e_s, "unit": "s/epoch", "h2d_bytes_per_step": int(est2._h2d_bytes / args.steps),
                      "d2h_bytes_per_step": int((est2.P_.nbytes + getattr(est2, "w_", np.zeros(0)).nbytes) / args.steps + 8),
                      "note": f"fit(X_host, y_host) wall clock / {args.steps} epochs: host CSR->CSC, H2D, epochs, D2H"}

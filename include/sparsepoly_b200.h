@@ -94,7 +94,7 @@ typedef struct sp_wplan {
     const double *h_x;        /* [n_hot] value */
     const int32_t *n_slots;   /* [n_windows] distinct hot samples */
     const int32_t *slot_row;  /* [n_windows*slot_cap] sample index of every slot */
-    int32_t *sync;            /* [2*(n_windows+2)+2] scratch counters (zeroed by every sweep) */
+    int32_t *sync;            /* [4*(n_windows+2)+2] scratch counters (zeroed by every sweep) */
     double *res;              /* [2*d] scratch: (update, new value) per position */
     double *base;             /* [2*d] scratch: cold partial sums (g, h) per position */
 } sp_wplan;

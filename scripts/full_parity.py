@@ -24,6 +24,13 @@ for sweep in sys.argv[4:] or ["auto"]:
     ndiff = int(np.sum(sd))
     ndust = int(np.sum(sd & (np.maximum(np.abs(est.P_), np.abs(out["P_"])) < 1e-12 * den)))
     pl = est._dev_state["plan"]
+    from sparsepoly_b200.objective import objective
+    ob = objective(est, X, y)
+    y_pm1 = est.label_binarizer_.transform(y).ravel().astype(np.float64) if hasattr(est, "label_binarizer_") else y
+    okw = {k: kw[k] for k in ("degree", "regularizer", "alpha", "beta", "gamma", "mean", "fit_lower", "fit_linear") if k in kw}
+    oo = O.objective_fm(X, y_pm1, out["P_"], out["w_"], est.lams_, loss=kw.get("loss", "squared"), **okw)
+    print("objective (device, CUDA fit)", ob, "\nobjective (oracle, oracle fit)", oo,
+          f"\nrelative difference of the total {abs(ob['total'] - oo['total']) / abs(oo['total']):.3e}", flush=True)
     print(f"{name} scale {scale} epochs {epochs} sweep={sweep} mode={pl.mode} {getattr(pl.wplan, 'stats', None) if pl.mode=='window' else ''}: "
           f"rel err P_ {errP:.3e}, w_ {errw:.3e}; supports identical: {sup} ({ndiff} of {est.P_.size} differ, {ndust} of them dust < 1e-12 max|P|); "
           f"nonzero frac {float(np.mean(out['P_'] != 0)):.4f}; gpu fit {t_gpu:.2f} s, oracle {t_cpu:.1f} s (1 core)", flush=True)

@@ -53,6 +53,7 @@ struct WArgs {
     double *regstate, *viol;
     double2 *res, *base;
     int *base_cnt, *wb_cnt, *eng_done;
+    int *early_cnt, *nzwin;      // early (speculative) BASE hand-over, record-changing updates per window
 };
 
 struct __align__(16) Cell { double v; long long tag; };
@@ -185,61 +186,93 @@ template <int R> __device__ __forceinline__ void store_rec_cg(double *p, const d
 }
 
 // ---------------------------------------------------------------------------------- bulk CTAs
+// BASE(w): (g, h) sums over the cold nonzeros of every column of window w this CTA owns -> a.base
+template <int KIND, int DEG, int LOSS>
+__device__ __forceinline__ void bulk_base(const WArgs &a, int w, int b, int nbulk, double (*red)[WT / 32]) {
+    constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
+    constexpr int R = 2 + NA;
+    constexpr int ND = (KIND == KIND_FM) ? DEG : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = a.stride;
+    const int t0 = w * a.B, nb = min(a.B, a.d - t0);
+    for (int tl = b; tl < nb; tl += nbulk) {
+        const int t = t0 + tl, j = a.idx_feat[t];
+        const double pold = a.prow[j];
+        double tg = 0.0, th = 0.0;
+        for (int g = a.indptr[j] + tid; g < a.indptr[j + 1]; g += WT) {
+            const int fi = a.cflag[g];
+            if (fi >= 0) {
+                double r[R], dA[ND];
+                load_rec_cg<R>(a.rec + (size_t)fi * stride, r);
+                nz_terms<KIND, DEG, LOSS, R, ND>(r, a.data[g], pold, dA, tg, th);
+            }
+        }
+        tg = sp_warp_allsum(tg);
+        th = sp_warp_allsum(th);
+        if (lane == 0) { red[0][warp] = tg; red[1][warp] = th; }
+        __syncthreads();
+        if (tid == 0) {
+            double sg = 0.0, sh = 0.0;
+#pragma unroll
+            for (int q = 0; q < WT / 32; q++) { sg += red[0][q]; sh += red[1][q]; }
+            __stcg(a.base + t, make_double2(sg, sh));
+        }
+        __syncthreads();
+    }
+}
+
+// With horizon 0 and speculation enabled the bulk CTAs also compute BASE(w+1) EARLY, while the engine
+// is still in window w, on the assumption that window w changes no record (all its updates are 0: the
+// sparse regime).  The engine publishes the number of record-changing updates of a window (nzwin)
+// with its hand-over; if it is 0 the early sums stand and the engine starts window w+1 without
+// waiting for any bulk work, otherwise WB(w) and an exact BASE(w+1) follow as usual.
 template <int KIND, int DEG, int LOSS>
 __device__ void bulk_role(const WArgs &a, int b, int nbulk) {
     constexpr int NA = (KIND == KIND_FM) ? DEG - 1 : (KIND == KIND_ALL ? 1 : 0);
     constexpr int R = 2 + NA;
     constexpr int ND = (KIND == KIND_FM) ? DEG : 1;
     __shared__ double red[2][WT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int nz_s;
+    const int tid = threadIdx.x;
     const int stride = a.stride;
     const double lam = (KIND == KIND_LINEAR) ? 1.0 : *a.lam_ptr;
+    const bool early = a.H == 0 && a.spec;
+    bool early_valid = false;                 // a.base of window w already holds valid early sums
     TP_DECL
     for (int w = 0; w < a.nwin + a.H; w++) {
         if (w < a.nwin) {
-            // ---- BASE(w): cold records of window w were last written in window <= w-H-1
-            if (tid == 0) {
-                if (w - 1 - a.H >= 0) wait_ge_sleep(a.wb_cnt + (w - 1 - a.H), nbulk);
-                wait_ge_sleep(a.eng_done, w - a.H);
-            }
-            __syncthreads();
-            TP_MARK(TP_BULK_WAITB)
-            const int t0 = w * a.B, nb = min(a.B, a.d - t0);
-            for (int tl = b; tl < nb; tl += nbulk) {
-                const int t = t0 + tl, j = a.idx_feat[t];
-                const double pold = a.prow[j];
-                double tg = 0.0, th = 0.0;
-                for (int g = a.indptr[j] + tid; g < a.indptr[j + 1]; g += WT) {
-                    const int fi = a.cflag[g];
-                    if (fi >= 0) {
-                        double r[R], dA[ND];
-                        load_rec_cg<R>(a.rec + (size_t)fi * stride, r);
-                        nz_terms<KIND, DEG, LOSS, R, ND>(r, a.data[g], pold, dA, tg, th);
-                    }
-                }
-                tg = sp_warp_allsum(tg);
-                th = sp_warp_allsum(th);
-                if (lane == 0) { red[0][warp] = tg; red[1][warp] = th; }
-                __syncthreads();
+            if (!early_valid) {
+                // ---- BASE(w): cold records of window w were last written in window <= w-H-1
                 if (tid == 0) {
-                    double sg = 0.0, sh = 0.0;
-#pragma unroll
-                    for (int q = 0; q < WT / 32; q++) { sg += red[0][q]; sh += red[1][q]; }
-                    __stcg(a.base + t, make_double2(sg, sh));
+                    if (w - 1 - a.H >= 0) wait_ge_sleep(a.wb_cnt + (w - 1 - a.H), nbulk);
+                    wait_ge_sleep(a.eng_done, w - a.H);
                 }
                 __syncthreads();
+                TP_MARK(TP_BULK_WAITB)
+                bulk_base<KIND, DEG, LOSS>(a, w, b, nbulk, red);
+                if (tid == 0) { __threadfence(); red_release_add(a.base_cnt + w, 1); }
+                TP_MARK(TP_BULK_BASE)
             }
-            if (tid == 0) { __threadfence(); red_release_add(a.base_cnt + w, 1); }
-            TP_MARK(TP_BULK_BASE)
+            if (early && w + 1 < a.nwin) {
+                // ---- early BASE(w+1): everything up to window w-1 is applied (waited for above, or
+                //      nothing was written since)
+                bulk_base<KIND, DEG, LOSS>(a, w + 1, b, nbulk, red);
+                if (tid == 0) { __threadfence(); red_release_add(a.early_cnt + w + 1, 1); }
+                TP_MARK(TP_BULK_BASE)
+            }
         }
         const int wv = w - a.H;
         if (wv >= 0) {
             // ---- WB(wv): apply the published updates to the cold records of window wv
-            if (tid == 0) wait_ge_sleep(a.eng_done, wv + 1);
+            if (tid == 0) {
+                wait_ge_sleep(a.eng_done, wv + 1);
+                nz_s = early ? ld_acquire(a.nzwin + wv) : 1;
+            }
             __syncthreads();
             TP_MARK(TP_BULK_WAITW)
+            early_valid = early && nz_s == 0;
             const int t0 = wv * a.B, nb = min(a.B, a.d - t0);
-            for (int tl = b; tl < nb; tl += nbulk) {
+            for (int tl = b; tl < nb && !early_valid; tl += nbulk) {
                 const int t = t0 + tl, j = a.idx_feat[t];
                 const double2 rs = __ldcg(a.res + t);
                 const double upd = rs.x, pnew = rs.y;
@@ -309,9 +342,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     __shared__ unsigned long long prog_s;      // chain progress in this window: decided positions | nonzero updates << 32
     __shared__ int nzdone_s;                   // nonzero updates of this window whose write-back is complete
     __shared__ int specoff_s;                  // too many rejections: the rest of the window runs exactly
+    __shared__ int winnz_s;                    // record-changing updates of the window just finished
     __shared__ unsigned long long spec_cnt_s[2];
     if (tid == 0) {
         spec_cnt_s[0] = 0; spec_cnt_s[1] = 0;
+        winnz_s = 1;
         chain_state[0] = *a.viol;
 #pragma unroll
         for (int t = 0; t < NC; t++) chain_state[1 + t] = (KIND == KIND_LINEAR) ? 0.0 : a.regstate[t];
@@ -365,8 +400,13 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         }
         if (tid == 0) {
             prog_s = 0ull; nzdone_s = 0; specoff_s = 0;
-            wait_ge(a.base_cnt + w, nbulk);
-            if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
+            if (a.H == 0 && a.spec && w > 0 && winnz_s == 0) {
+                // the previous window changed no record: the early sums of the bulk CTAs stand
+                wait_ge(a.early_cnt + w, nbulk);
+            } else {
+                wait_ge(a.base_cnt + w, nbulk);
+                if (w - 1 - a.H >= 0) wait_ge(a.wb_cnt + (w - 1 - a.H), nbulk);
+            }
         }
         // speculate when (almost) every coordinate of the window starts at zero: under l1 / squaredl12 /
         // omegati such coordinates nearly always stay there (nb <= WT: one position per thread)
@@ -423,7 +463,8 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 const int t = t0 + tl;
                 // ---- this position's chain nonzeros, one per lane: [late only][late+fwd][fwd only].
                 //      Late terms read records the PREVIOUS steps of this warp just wrote back.
-                const int cls = cls_s[tl];
+                // (speculative windows: every hot nonzero goes through the workers, see there)
+                const int cls = win_spec ? 0 : cls_s[tl];
                 const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff), nC = nL + ((cls >> 16) & 0xff);
                 double tgl = 0.0, thl = 0.0, cx = 0.0, cr[R], cdA[ND];
                 int cslot = -1;
@@ -526,7 +567,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     }
                     __syncwarp();
                 }
-                if (upd != 0.0) { last_nz = tl; nz_issued++; }
+                if (KIND == KIND_ALL || upd != 0.0) { last_nz = tl; nz_issued++; }
                 if (lane0) {
                     cell_store_a(pr, KIND == KIND_ALL ? pnew : upd, t);
                     if (!redone) mbar_arrive(pm);
@@ -545,6 +586,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 for (int q = 0; q < NC; q++) chain_state[1 + q] = cache[q];
                 spec_cnt_s[0] += n_spec;
                 spec_cnt_s[1] += (unsigned long long)n_rej;
+                winnz_s = nz_issued;
             }
         } else {
             // =========================================================== workers
@@ -557,8 +599,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 const double pold = pold_s[tl];
                 const double2 bs = base_s[tl];
                 const double cn = cn_s[tl];
-                const int cls = cls_s[tl];
+                // In a speculative window the late / fwd classes of the plan are ignored: the workers evaluate
+                // and write back every hot nonzero (no waits to shorten, and the chain warp stays minimal).
+                const int cls = win_spec ? 0 : cls_s[tl];
                 const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff);
+                const int fwd_mask = win_spec ? 0 : SP_ENT_FWD;
                 TR(w, tl, 0)
                 int k_slot[KR];                                 // kept for the write-back (-1: none / not ours)
                 double k_x[KR], k_r[KR][R], k_dA[KR][ND];
@@ -590,7 +635,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                             const int sd = ent_sd[hs + e];
                             const int dep = ((sd >> 16) & 0x1ff) - 1;
                             slot[u] = sd & 0xffff;
-                            if (sd & SP_ENT_FWD) slot[u] |= 0x10000;   // term ours, write-back the chain warp's
+                            if (sd & fwd_mask) slot[u] |= 0x10000;     // term ours, write-back the chain warp's
                             x[u] = ent_x[hs + e];
                             if (!spec && dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
                         }
@@ -687,7 +732,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     for (int e = lane; e < ne; e += 32) {
                         if (e >= nLo && e < 32 * KR) continue;
                         const int sd = ent_sd[hs + e];
-                        if (sd & SP_ENT_FWD) continue;
+                        if (sd & fwd_mask) continue;
                         const int slot = sd & 0xffff;
                         const double x = ent_x[hs + e];
                         double r[R], dA[ND];
@@ -703,7 +748,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();                      // the write-back above before the flag
-                    if (upd != 0.0) atomicAdd_block(&nzdone_s, 1);
+                    if (KIND == KIND_ALL || upd != 0.0) atomicAdd_block(&nzdone_s, 1);
                     flag_store(&wbflag[tl], wtag);
                     mbar_arrive(smem_u32(&mb_wb[tl]));          // wakes the warps sleeping on this position
                 }
@@ -720,7 +765,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             for (int h = 0; h < NCH; h++) __stcg(dst + h, src[h]);
         }
         __syncthreads();
-        if (tid == 0) { __threadfence(); st_release(a.eng_done, w + 1); }
+        if (tid == 0) {
+            a.nzwin[w] = winnz_s;
+            __threadfence();
+            st_release(a.eng_done, w + 1);
+        }
         if (tid == 32) TP_MARK(TP_ENG_FLUSH)
     }
     TP_FLUSH(tid == 0 || tid == 32)
@@ -767,7 +816,7 @@ int launch_wsweep(WArgs a, double *prow_out, cudaStream_t st) {
     int nbulk = a.B < a.d ? a.B : a.d;
     if (nbulk > g_sm_count - 1) nbulk = g_sm_count - 1;
     if (nbulk < 1) nbulk = 1;
-    SP_CUDA(cudaMemsetAsync(a.base_cnt, 0, sizeof(int) * (2 * (size_t)(a.nwin + 2) + 2), st));
+    SP_CUDA(cudaMemsetAsync(a.base_cnt, 0, sizeof(int) * (4 * (size_t)(a.nwin + 2) + 2), st));
     void *params[] = {(void *)&a};
     sp_prof_begin(SP_PROF_SWEEP_PCD, st);
     cudaError_t le = cudaLaunchCooperativeKernel((void *)kern, dim3(nbulk + 1), dim3(WT), params, smem, st);
@@ -850,6 +899,8 @@ int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat,
     a.base_cnt = wp->sync;
     a.wb_cnt = wp->sync + (a.nwin + 2);
     a.eng_done = wp->sync + 2 * (a.nwin + 2);
+    a.early_cnt = wp->sync + 2 * (a.nwin + 2) + 2;
+    a.nzwin = a.early_cnt + (a.nwin + 2);
     switch (degree) {
     case 1: return wdispatch_loss<KIND_LINEAR, 1>(loss, a, prow, st);
     case -1: return wdispatch_loss<KIND_ALL, 1>(loss, a, prow, st);

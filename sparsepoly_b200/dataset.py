@@ -300,7 +300,7 @@ class WindowPlan:
         self.ht_cls = torch.zeros(max(d, 1), dtype=torch.int32, device=dev)
         self.n_slots = torch.zeros(n_windows, dtype=torch.int32, device=dev)
         self.slot_row = torch.empty(n_windows * self.slot_cap, dtype=torch.int32, device=dev)
-        self.sync = torch.zeros(2 * (n_windows + 2) + 2, dtype=torch.int32, device=dev)
+        self.sync = torch.zeros(4 * (n_windows + 2) + 2, dtype=torch.int32, device=dev)
         self.overflow.zero_()
         _lib.check(lib.sp_wplan_fill(ds.ref(), _ptr(idx_feat), B, self.slot_cap,
                                      2 if self.pbcd_shape is None else 3, self.near, _ptr(self.cflag),

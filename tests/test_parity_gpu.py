@@ -174,8 +174,8 @@ def _wspec_read():
 @pytest.mark.parametrize("tag,degree,clf,kw", SPEC_CASES, ids=[c[0] for c in SPEC_CASES])
 def test_window_sweep_zero_update_speculation(tag, degree, clf, kw, window, monkeypatch):
     """Sparse regimes: the engine's workers skip the per-record waits and the chain warp validates
-    (pcd_window.cu, ZERO-UPDATE SPECULATION).  Results must equal the oracle's to 1e-9 AND be bitwise
-    those of the non-speculative sweep (same operations on the same record values)."""
+    (pcd_window.cu, ZERO-UPDATE SPECULATION).  Results must equal the oracle's to 1e-9 and those of the
+    non-speculative sweep to rounding, with identical supports."""
     monkeypatch.setenv("SPARSEPOLY_B200_SWEEP", "window" if window else "auto")
     if window is not None:
         monkeypatch.setenv("SPARSEPOLY_B200_WINDOW", str(window))
@@ -190,7 +190,10 @@ def test_window_sweep_zero_update_speculation(tag, degree, clf, kw, window, monk
     monkeypatch.setenv("SPARSEPOLY_B200_SPEC", "0")
     est0, _, _ = _compare_fm(kw, X, y)
     assert _wspec_read() == (0, 0)
-    assert np.array_equal(est.P_, est0.P_) and np.array_equal(est.w_, est0.w_)
+    # same arithmetic per nonzero; only the order in which a column's hot terms are summed differs (in a
+    # speculative window the workers sum all of them, otherwise the chain warp adds the "late" ones)
+    assert rel_err(est.P_, est0.P_) <= 1e-11 and rel_err(est.w_, est0.w_) <= 1e-11
+    assert np.array_equal(est.P_ != 0, est0.P_ != 0)
 
 
 @pytest.mark.parametrize("horizon", [0, 1])
