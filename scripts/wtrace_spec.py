@@ -18,12 +18,39 @@ scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 X, y = bench.make_problem("pcd", scale, 0)
 kw = dict(bench.WORKLOADS["pcd"]["kw"], max_iter=epochs)
+only_top = len(sys.argv) > 3 and sys.argv[3] == "top"
+if only_top:                      # epochs of 16 top-degree sweeps only (all speculative after the first)
+    kw.update(fit_lower=None, fit_linear=False)
 lib = _lib.load()
 warnings.simplefilter("ignore")
 est = S.SparseFactorizationMachineClassifier(**kw)
 ws = (C.c_ulonglong * 2)()
 lib.sp_wspec_read(ws)
-est.fit(X, y)
+NAMES = ["eng_wait", "eng_stage", "eng_role", "eng_flush", "ch_wait", "ch_comp", "wk_load", "wk_dep", "wk_terms",
+         "wk_red", "wk_reswait", "wk_wb", "bulk_waitb", "bulk_base", "bulk_waitw", "bulk_wb"]
+buf = (C.c_ulonglong * 16)()
+if only_top:
+    import torch, time
+    from sklearn.utils import check_random_state
+    Xc, yc = est._check_X_y(X, y)
+    rng = check_random_state(kw["random_state"])
+    est.w_ = np.zeros(Xc.shape[1])
+    est.P_ = 0.01 * rng.randn(1, est.n_components, Xc.shape[1])
+    est.lams_ = np.ones(est.n_components)
+    epoch, sync = est._pcd_setup(Xc, np.ascontiguousarray(yc, dtype=np.float64), rng, torch.device("cuda", 0))
+    for e in range(epochs):
+        lib.sp_wprof_read(buf)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        epoch()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        lib.sp_wprof_read(buf)
+        sync()
+        nzf = float(np.mean(est.P_ != 0))
+        coords = Xc.shape[1] * est.n_components
+        print(f"epoch {e}: {dt:.3f} s, {dt / coords * 1e6:.3f} us/coordinate, nonzero {nzf:.4f}; engine cycles per coordinate:",
+              {n: round(int(v) / coords, 1) for n, v in zip(NAMES, buf) if int(v)})
+else:
+    est.fit(X, y)
 lib.sp_wspec_read(ws)
 plan = est._dev_state["plan"]
 print("plan", plan.mode, plan.wplan.stats, "speculated", ws[0], "rejected", ws[1],

@@ -442,7 +442,89 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         if (tid == 32) TP_MARK(TP_ENG_STAGE)
         if (tid != 32) TP_MARK(TP_ENG_WAIT)
 
-        if (warp == 0) {
+        if (warp == 0 && KIND == KIND_FM && win_spec) {
+            // =========================================================== scalar chain, 32 positions per step
+            // A coordinate that stays at zero leaves the regularizer state bit-for-bit unchanged, so in a
+            // sparse window the chain steps of consecutive positions are independent: lane l evaluates
+            // position tl+l against the current state; everything up to and including the first position
+            // that moves (update != 0 or state changed) is committed, the rest is re-evaluated next round.
+            double viol = chain_state[0], cache[NC];
+#pragma unroll
+            for (int q = 0; q < NC; q++) cache[q] = chain_state[1 + q];
+            const int reg = a.reg;
+            int last_nz = -1, nz_issued = 0, n_rej = 0, redo_tl = -1;
+            unsigned long long n_spec = 0;
+            int tl = 0;
+            while (tl < nb) {
+                const int my = tl + lane, t = t0 + my;
+                const bool inw = my < nb;
+                double va = 0.0, vb = 0.0;
+                long long ta = -1, tb = -1;
+                if (inw) {
+                    cell_load_a64(smem_u32(&cellA[my]), va, ta);      // (the worker stores B before A)
+                    cell_load_a64(smem_u32(&cellB[my]), vb, tb);
+                }
+                const int cs = (int)(ta >> 32);
+                bool ready = inw && (int)ta == t && (int)tb == t && (int)(tb >> 32) == cs;
+                if (my == redo_tl) ready = ready && cs == SP_CS_EXACT;
+                const unsigned rmask = __ballot_sync(0xffffffffu, ready);
+                int n = (rmask == 0xffffffffu) ? 32 : __ffs(~rmask) - 1;     // ready run starting at lane 0
+                if (n == 0) continue;
+                const unsigned rejmask = __ballot_sync(0xffffffffu, lane < n && last_nz >= cs);
+                if (rejmask) {
+                    const int r = __ffs(rejmask) - 1;
+                    if (r == 0) {
+                        // position tl was evaluated against records a later-decided update changed: redo
+                        if (lane == 0) {
+                            cell_store(&rcell[tl], 0.0, SP_TAG_REDO);
+                            mbar_arrive(smem_u32(&mb_res[tl]));
+                            if (++n_rej == 4) flag_store(&specoff_s, 1);
+                        }
+                        n_spec += 1;
+                        redo_tl = tl;
+                        continue;
+                    }
+                    n = r;
+                }
+                const double pold = inw ? pold_s[my] : 0.0;
+                double mc[NC];
+#pragma unroll
+                for (int q = 0; q < NC; q++) mc[q] = cache[q];
+                const double pnew = prox_chain<KIND, DEG, NC>(reg, va, vb, pold, mc);
+                const double upd = pold - pnew;                      // pcd.py:121
+                bool same = true;
+#pragma unroll
+                for (int q = 0; q < NC; q++) same = same && (__double_as_longlong(mc[q]) == __double_as_longlong(cache[q]));
+                const unsigned mmask = __ballot_sync(0xffffffffu, lane < n && !(upd == 0.0 && same));
+                const int f = mmask ? __ffs(mmask) - 1 : -1;
+                const int c = mmask ? f + 1 : n;
+                if (lane < c) {
+                    cell_store(&rcell[my], upd, t);
+                    if (my != redo_tl) mbar_arrive(smem_u32(&mb_res[my]));
+                    __stcg(a.res + t, make_double2(upd, pnew));
+                }
+                n_spec += (unsigned long long)__popc(__ballot_sync(0xffffffffu, lane < c && cs != SP_CS_EXACT && my != redo_tl));
+                if (mmask) {
+#pragma unroll
+                    for (int q = 0; q < NC; q++) cache[q] = sp_shfl(mc[q], f);
+                    const double uf = sp_shfl(upd, f);
+                    if (uf != 0.0) { last_nz = tl + f; nz_issued++; }
+                    viol += fabs(uf);                                // (the committed zeros add +0.0)
+                }
+                __syncwarp();
+                if (lane == 0)
+                    sts_u64_volatile(&prog_s, (unsigned long long)(unsigned)(tl + c) | ((unsigned long long)(unsigned)nz_issued << 32));
+                tl += c;
+            }
+            if (lane == 0) {
+                chain_state[0] = viol;
+#pragma unroll
+                for (int q = 0; q < NC; q++) chain_state[1 + q] = cache[q];
+                spec_cnt_s[0] += n_spec;
+                spec_cnt_s[1] += (unsigned long long)n_rej;
+                winnz_s = nz_issued;
+            }
+        } else if (warp == 0) {
             // =========================================================== scalar chain, in order
             double viol = chain_state[0], cache[NC];
 #pragma unroll
