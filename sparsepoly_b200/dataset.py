@@ -278,6 +278,8 @@ class WindowPlan:
                 break
             if self.pbcd_shape is not None and B > 32:   # measured at C3: 16-32 positions per window is best
                 continue
+            if self.pbcd_shape is None and B > 96:       # measured at C2 (64 / 80 / 96 / 112 / 128 / 160): 96
+                continue
             f = min(1.0, (2 * H + 1) * B * row / max(ds.n_features, 1))   # expected hot fraction
             if f <= self.max_hot_frac and 0.5 * B * col * f <= self.slot_cap:
                 out.append(B)
