@@ -281,6 +281,8 @@ def run_sweep_workload(name, args, rank, world, local):
     X, y = make_problem(name, args.scale, rank)
     n, d = X.shape
     kw = dict(wl["kw"], max_iter=args.steps)
+    if args.gamma is not None:
+        kw["gamma"] = args.gamma
     if name == "allsub":
         cls = S.SparseAllSubsetsClassifier
     else:
@@ -624,6 +626,7 @@ def main():
                     help="psgd global minibatch: 'auto' (= d/nnz_row split over the ranks), 'weak' "
                          "(auto x n_gpus: per-GPU work fixed) or an integer")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--gamma", type=float, default=None, help="override the workload's gamma (debug: other sparsity regimes)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     global ROWS_OVERRIDE

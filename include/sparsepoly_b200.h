@@ -36,7 +36,9 @@ extern "C" {
 #define SP_MAX_HOT_FEATURES 16
 #define SP_PBCD_ENT_PER_SLOT 3  /* pbcd window plan: hot nonzeros per window <= 3*slot_cap (pcd: 2*slot_cap) */
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
-#define SP_WPLAN_NO_SPECULATION 1   /* sp_wplan.flags: workers always wait for the write-backs they depend on */
+#define SP_WPLAN_NO_SPECULATION 1   /* sp_wplan.flags: workers always wait for the write-backs they depend on;
+                                       bits 8..15 (debug): a window speculates when <= 1/value of its
+                                       coordinates start nonzero (0 = built-in default: <= 2/3) */
 
 typedef void *sp_stream;
 

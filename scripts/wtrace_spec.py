@@ -60,8 +60,9 @@ lib.sp_wtrace_read(tr)
 B = plan.wplan.stats["window"]
 T = np.array(list(tr), dtype=np.int64).reshape(256, 8)[:B]
 base = T[:, 0].min()
+mv = np.zeros(B, dtype=bool)
 print(" tl  start  terms_done  cell_out  ch_seen  ch_done  res_seen  wb_flag  allsum_done | ch_done-prev")
-for tl in range(min(B, 48)):
+for tl in range(min(B, 96)):
     r = T[tl] - base
     print(f"{tl:3d} {r[0]:6d} {r[1]:10d} {r[2]:9d} {r[3]:8d} {r[4]:8d} {r[5]:9d} {r[6]:8d} {r[7]:11d} | "
           f"{int(T[tl, 4] - T[tl - 1, 4]) if tl else 0:6d}")

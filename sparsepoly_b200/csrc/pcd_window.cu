@@ -37,7 +37,7 @@ constexpr int W_AUX_BYTES = SP_WINDOW_MAX * (3 * 16 + 2 * 8 + 16 + 4 * 4 + 2 * 8
 constexpr int W_REC_BYTES = 196608;            // shared memory reserved for the hot record slots
 
 struct WArgs {
-    int d, B, H, nwin, slot_cap, stride, reg, spec;
+    int d, B, H, nwin, slot_cap, stride, reg, spec, spec_denom;
     const int32_t *indptr;       // CSC
     const int32_t *cflag;
     const double *data;
@@ -80,8 +80,11 @@ __device__ long long g_wtrace[SP_WINDOW_MAX * 8];   // per-position timestamps o
 #define TP_MARK(id) {}
 #define TP_FLUSH(cond) {}
 #endif
+#ifndef SP_TRACE_DEG
+#define SP_TRACE_DEG DEG            /* trace only the sweeps of this degree (debug builds) */
+#endif
 #ifdef SP_WPROF
-#define TR(w_, tl_, k_) if ((w_) == 100 && lane == 0) g_wtrace[(tl_) * 8 + (k_)] = clock64();
+#define TR(w_, tl_, k_) if (DEG == SP_TRACE_DEG && (w_) == 100 && lane == 0) g_wtrace[(tl_) * 8 + (k_)] = clock64();
 #define TRD(w_, tl_, k_, v_) { asm volatile("" ::"d"(v_) : "memory"); TR(w_, tl_, k_) }
 #else
 #define TR(w_, tl_, k_) {}
@@ -318,6 +321,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
     double *recs = reinterpret_cast<double *>(smem_raw);                       // [slot_cap*stride]
     double *ent_x = recs + (size_t)a.slot_cap * stride;                        // [2*slot_cap] values
     int *ent_sd = reinterpret_cast<int *>(ent_x + 2 * (size_t)a.slot_cap);     // [2*slot_cap] slot | (dep+1)<<16
+    unsigned *slot_mv = reinterpret_cast<unsigned *>(ent_sd + 2 * (size_t)a.slot_cap);   // [slot_cap][4] mover masks
     Cell *cellA = reinterpret_cast<Cell *>(smem_raw + W_REC_BYTES);            // [BM] worker -> chain
     Cell *cellB = cellA + BM;                                                  // [BM]
     Cell *rcell = cellB + BM;                                                  // [BM] chain -> worker
@@ -411,7 +415,24 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         // speculate when (almost) every coordinate of the window starts at zero: under l1 / squaredl12 /
         // omegati such coordinates nearly always stay there (nb <= WT: one position per thread)
         const int nz_old = __syncthreads_count(my_nz);
-        const bool win_spec = KIND == KIND_FM && a.spec && nz_old * 32 <= nb;
+        // measured at C2 (windows of 96): speculative windows win up to ~50 % known movers (6 % at 45-52 %,
+        // 15 % at 20 %, 2.8x in all-zero sweeps); with (almost) every coordinate moving the plain path with its
+        // chain-warp shortcut for adjacent positions is the better one
+        const bool win_spec = KIND == KIND_FM && a.spec && nb <= 128 &&
+                              (a.spec_denom ? nz_old * a.spec_denom <= nb : nz_old * 3 <= nb * 2);
+        if (win_spec) {
+            // slot_mv[slot] = bit mask of the window positions that touch the slot AND start nonzero (known
+            // movers: they will change the record).  A speculating worker waits for the write-back of the
+            // last such position before its own -- the only true dependency it can know in advance.
+            for (int i = tid; i < ns * 4; i += WT) slot_mv[i] = 0u;
+            __syncthreads();
+            for (int tl = warp; tl < nb; tl += WT / 32) {
+                if (pold_s[tl] == 0.0) continue;
+                const int hs = hp_s[tl], ne = hp_s[tl + 1] - hs;
+                for (int e = lane; e < ne; e += 32)
+                    atomicOr(&slot_mv[(ent_sd[hs + e] & 0xffff) * 4 + (tl >> 5)], 1u << (tl & 31));
+            }
+        }
         if (tid == 32) TP_MARK(TP_ENG_WAIT)
         // ---- stage, part 2 (data the bulk CTAs produce): cold partial sums, hot sample records
         for (int tl = tid; tl < nb; tl += WT) base_s[tl] = __ldcg(a.base + t0 + tl);
@@ -452,6 +473,8 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
 #pragma unroll
             for (int q = 0; q < NC; q++) cache[q] = chain_state[1 + q];
             const int reg = a.reg;
+            // last_nz: last SURPRISE (a coordinate that started at zero and moved); known movers are waited
+            // for by the workers (slot_mv), so only surprises invalidate a speculative evaluation
             int last_nz = -1, nz_issued = 0, n_rej = 0, redo_tl = -1;
             unsigned long long n_spec = 0;
             int tl = 0;
@@ -498,6 +521,12 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 const unsigned mmask = __ballot_sync(0xffffffffu, lane < n && !(upd == 0.0 && same));
                 const int f = mmask ? __ffs(mmask) - 1 : -1;
                 const int c = mmask ? f + 1 : n;
+#ifdef SP_WPROF
+                if (DEG == SP_TRACE_DEG && w == 100 && lane < c) {
+                    g_wtrace[my * 8 + 4] = clock64();
+                    g_wtrace[my * 8 + 3] = (long long)c;          // (size of the committed run, not a time)
+                }
+#endif
                 if (lane < c) {
                     cell_store(&rcell[my], upd, t);
                     if (my != redo_tl) mbar_arrive(smem_u32(&mb_res[my]));
@@ -508,7 +537,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
 #pragma unroll
                     for (int q = 0; q < NC; q++) cache[q] = sp_shfl(mc[q], f);
                     const double uf = sp_shfl(upd, f);
-                    if (uf != 0.0) { last_nz = tl + f; nz_issued++; }
+                    const double pf = sp_shfl(pold, f);
+                    if (uf != 0.0) {
+                        nz_issued++;
+                        if (pf == 0.0) last_nz = tl + f;
+                    }
                     viol += fabs(uf);                                // (the committed zeros add +0.0)
                 }
                 __syncwarp();
@@ -719,7 +752,18 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                             slot[u] = sd & 0xffff;
                             if (sd & fwd_mask) slot[u] |= 0x10000;     // term ours, write-back the chain warp's
                             x[u] = ent_x[hs + e];
-                            if (!spec && dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
+                            if (!spec) {
+                                if (dep >= 0 && flag_load(&wbflag[dep]) != wtag) mydep[u] = dep;
+                            } else if (attempt == 0 && dep >= 0) {
+                                // last known mover that touched this slot before this position
+                                const uint4 mk = *reinterpret_cast<const uint4 *>(&slot_mv[(sd & 0xffff) * 4]);
+                                const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                                int wi = tl >> 5, lmt = -1;
+                                unsigned m = mw[wi] & ((1u << (tl & 31)) - 1u);
+                                while (m == 0u && wi > 0) m = mw[--wi];
+                                if (m) lmt = (wi << 5) + 31 - __clz(m);
+                                if (lmt >= 0 && flag_load(&wbflag[lmt]) != wtag) mydep[u] = lmt;
+                            }
                         }
                     }
                     // wait (warp-uniformly: divergent waits would leave the warp fragmented for the
@@ -949,7 +993,7 @@ extern "C" int sp_wtrace_read(long long *out_host /*[SP_WINDOW_MAX*8]*/) {
 
 extern "C" int sp_wplan_slot_cap(int rec_stride) {
     if (rec_stride < 2) rec_stride = 2;
-    return W_REC_BYTES / (rec_stride * 8 + 24);    // + room for 2 hot nonzeros (12 B each) per slot
+    return W_REC_BYTES / (rec_stride * 8 + 40);    // + room for 2 hot nonzeros (12 B each) and a 128-bit mover mask per slot
 }
 
 // degree: 1 = linear (cd_linear), -1 = all-subsets, 2..SP_MAXDEG = ANOVA
@@ -971,6 +1015,7 @@ int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat,
     a.d = ds->n_features; a.B = wp->window; a.H = wp->horizon; a.nwin = wp->n_windows;
     a.slot_cap = wp->slot_cap; a.stride = rec_stride; a.reg = reg;
     a.spec = (wp->flags & SP_WPLAN_NO_SPECULATION) ? 0 : 1;
+    a.spec_denom = (wp->flags >> 8) & 0xff;                   // debug override of the density threshold
     a.indptr = ds->csc_indptr; a.cflag = wp->cflag; a.data = ds->csc_data; a.idx_feat = idx_feat;
     a.ht_ptr = wp->ht_ptr; a.ht_cls = wp->ht_cls; a.h_sd = wp->h_sd; a.h_x = wp->h_x;
     a.n_slots = wp->n_slots; a.slot_row = wp->slot_row;

@@ -316,6 +316,7 @@ class WindowPlan:
         s.near = self.near
         # SPARSEPOLY_B200_SPEC=0: never speculate on zero updates (debug / A-B measurements)
         s.flags = 1 if os.environ.get("SPARSEPOLY_B200_SPEC", "1") == "0" else 0
+        s.flags |= (int(os.environ.get("SPARSEPOLY_B200_SPEC_DENOM", "0")) & 0xff) << 8   # debug: density threshold
         s.cflag, s.ht_ptr, s.ht_cls = self.cflag.data_ptr(), self.ht_ptr.data_ptr(), self.ht_cls.data_ptr()
         s.h_sd, s.h_x = self.h_sd.data_ptr(), self.h_x.data_ptr()
         s.n_slots, s.slot_row = self.n_slots.data_ptr(), self.slot_row.data_ptr()
