@@ -38,7 +38,7 @@ extern "C" {
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
 #define SP_WPLAN_NO_SPECULATION 1   /* sp_wplan.flags: workers always wait for the write-backs they depend on;
                                        bits 8..15 (debug): a window speculates when <= 1/value of its
-                                       coordinates start nonzero (0 = built-in default: <= 2/3) */
+                                       coordinates start nonzero (0 = built-in default: <= 55 %) */
 
 typedef void *sp_stream;
 

@@ -415,11 +415,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         // speculate when (almost) every coordinate of the window starts at zero: under l1 / squaredl12 /
         // omegati such coordinates nearly always stay there (nb <= WT: one position per thread)
         const int nz_old = __syncthreads_count(my_nz);
-        // measured at C2 (windows of 96): speculative windows win up to ~50 % known movers (6 % at 45-52 %,
-        // 15 % at 20 %, 2.8x in all-zero sweeps); with (almost) every coordinate moving the plain path with its
-        // chain-warp shortcut for adjacent positions is the better one
+        // measured at C2 (windows of 96, profiles/r01b_bench_pcd_launches_summary.txt): speculative windows win
+        // below ~55 % known movers (13 % at 45 %, 2.7x in all-zero sweeps) and lose above (60-66 %: 87-96 ms per
+        // sweep against 82 ms): there the plain path with its chain-warp shortcut for adjacent positions is better
         const bool win_spec = KIND == KIND_FM && a.spec && nb <= 128 &&
-                              (a.spec_denom ? nz_old * a.spec_denom <= nb : nz_old * 3 <= nb * 2);
+                              (a.spec_denom ? nz_old * a.spec_denom <= nb : nz_old * 20 <= nb * 11);
         if (win_spec) {
             // slot_mv[slot] = bit mask of the window positions that touch the slot AND start nonzero (known
             // movers: they will change the record).  A speculating worker waits for the write-back of the
