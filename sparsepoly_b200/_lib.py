@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsparsepoly_b200.so")
+LIB_PATH = os.environ.get("SPARSEPOLY_B200_LIB") or os.path.join(_HERE, "libsparsepoly_b200.so")   # (override: A/B builds)
 
 LOSS_IDS = {"squared": 0, "logistic": 1, "squared_hinge": 2}
 REG_IDS = {"l1": 0, "l21": 1, "squaredl12": 2, "squaredl21": 3, "omegati": 4, "omegacs": 5}
