@@ -883,8 +883,8 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
         }
         __syncthreads();
         if (tid == 32) TP_MARK(TP_ENG_ROLE)
-        // ---- flush the hot records, publish the window
-        for (int s = tid; s < ns; s += WT) {
+        // ---- flush the hot records (unless no update of this window changed a record), publish the window
+        for (int s = tid; s < ns && winnz_s != 0; s += WT) {
             double2 *dst = reinterpret_cast<double2 *>(a.rec + (size_t)srow[s] * stride);
             const double2 *src = reinterpret_cast<const double2 *>(recs + (size_t)s * stride);
 #pragma unroll
