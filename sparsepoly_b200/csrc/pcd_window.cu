@@ -15,14 +15,18 @@
 //     H = 1 a cold record is untouched for a whole window on either side, so BASE(w) runs while
 //     the engine is still in window w-1 and the engine never waits for the bulk CTAs.
 //   * windows are handed over through three counters in global memory (release / acquire).
-//   * ZERO-UPDATE SPECULATION (ANOVA sweeps, windows whose coordinates are almost all zero -- the
-//     regime the sparsity-inducing regularizers drive the fit into): a coordinate whose update is 0
-//     changes no record, so nothing depends on it.  Workers then do not wait for the write-backs of
-//     the positions their records depend on: they snapshot the chain warp's progress C (all nonzero
-//     updates decided before C are applied: counter nz_done), read the records, and send C with their
-//     sums; the chain warp accepts them iff no position in [C, t) had a nonzero update, else the
-//     worker redoes the position once the chain is parked on it.  Results are identical to the
-//     non-speculative path (same operations on the same record values).
+//   * ZERO-UPDATE SPECULATION (ANOVA sweeps, windows in which at most 55 % of the coordinates start
+//     nonzero -- the regime the sparsity-inducing regularizers drive the fit into): a coordinate whose
+//     update is 0 changes no record and leaves the regularizer state unchanged, so nothing depends on
+//     it.  Workers then wait only for the last KNOWN MOVER (coordinate that starts nonzero) touching
+//     each of their records (per-slot masks slot_mv) and guard against SURPRISES (a zero coordinate
+//     that moves) with a snapshot of the chain warp's progress C (all record-changing updates decided
+//     before C are applied: counter nz_done) sent with their sums; the chain warp -- 32 positions per
+//     step, committing up to the first one that moves -- accepts a cell iff no surprise happened in
+//     [C, t), else the worker redoes the position once the chain is parked on it.  Bulk CTAs compute
+//     BASE(w+1) early; after a window without record-changing updates the engine starts the next one
+//     without any bulk hand-over.  Committed values are those of the non-speculative path (same
+//     operations on the same record values; only the summation order of a column's hot terms differs).
 // Per-sample terms are computed exactly as the reference does; only the order in which a column's
 // terms are summed differs (as in any parallel reduction).
 #include "common.cuh"
@@ -123,12 +127,6 @@ __device__ __forceinline__ void cell_store(Cell *c, double v, long long tag) {
                  : "memory");
 }
 // same, on precomputed shared-window addresses (saves the cvta sequence in the hot loops)
-__device__ __forceinline__ void cell_load_a(uint32_t addr, double &v, int &tag) {
-    unsigned long long a, b;
-    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
-    v = __longlong_as_double((long long)a);
-    tag = (int)b;
-}
 __device__ __forceinline__ void cell_store_a(uint32_t addr, double v, int tag) {
     asm volatile("st.volatile.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(__double_as_longlong(v)),
                  "l"((long long)tag)
@@ -559,6 +557,7 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             }
         } else if (warp == 0) {
             // =========================================================== scalar chain, in order
+            // (windows that do not speculate: every cell was computed after the per-record waits)
             double viol = chain_state[0], cache[NC];
 #pragma unroll
             for (int q = 0; q < NC; q++) cache[q] = chain_state[1 + q];
@@ -572,14 +571,12 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
             cell_load_a64(pa, va, ta);
             cell_load_a64(pb, vb, tb);
             pold = lds_f64_a(pp);
-            int last_nz = -1, nz_issued = 0, n_rej = 0;
-            unsigned long long n_spec = 0;
+            int nz_issued = 0;
             for (int tl = 0; tl < nb; tl++) {
                 const int t = t0 + tl;
                 // ---- this position's chain nonzeros, one per lane: [late only][late+fwd][fwd only].
                 //      Late terms read records the PREVIOUS steps of this warp just wrote back.
-                // (speculative windows: every hot nonzero goes through the workers, see there)
-                const int cls = win_spec ? 0 : cls_s[tl];
+                const int cls = cls_s[tl];
                 const int nLo = cls & 0xff, nL = nLo + ((cls >> 8) & 0xff), nC = nL + ((cls >> 16) & 0xff);
                 double tgl = 0.0, thl = 0.0, cx = 0.0, cr[R], cdA[ND];
                 int cslot = -1;
@@ -610,23 +607,6 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 while ((int)ta != t) cell_load_a64(pa, va, ta);
                 if (KIND != KIND_LINEAR) {
                     while ((int)tb != t) cell_load_a64(pb, vb, tb);
-                }
-                bool redone = false;
-                if (KIND == KIND_FM) {
-                    const int cs = (int)(ta >> 32);
-                    n_spec += cs != SP_CS_EXACT;
-                    if (last_nz >= cs) {
-                        // a position the worker had not seen decided changed records: have it redo this one
-                        // (it finds the chain parked here, i.e. everything before applied)
-                        if (lane0) {
-                            cell_store_a(pr, 0.0, SP_TAG_REDO);
-                            mbar_arrive(pm);
-                            if (++n_rej == 4) flag_store(&specoff_s, 1);
-                        }
-                        redone = true;
-                        do cell_load_a64(pa, va, ta); while ((int)ta != t || (int)(ta >> 32) != SP_CS_EXACT);
-                        do cell_load_a64(pb, vb, tb); while ((int)tb != t || (int)(tb >> 32) != SP_CS_EXACT);
-                    }
                 }
                 TR(w, tl, 3)
                 // inputs of the next position: in flight while this one is computed (stale tags of an
@@ -682,13 +662,11 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                     }
                     __syncwarp();
                 }
-                if (KIND == KIND_ALL || upd != 0.0) { last_nz = tl; nz_issued++; }
+                if (KIND == KIND_ALL || upd != 0.0) nz_issued++;     // record-changing updates of the window
                 if (lane0) {
                     cell_store_a(pr, KIND == KIND_ALL ? pnew : upd, t);
-                    if (!redone) mbar_arrive(pm);
+                    mbar_arrive(pm);
                     __stcg(resg + tl, make_double2(upd, pnew));
-                    // after this warp's own record write-backs above (program order + __syncwarp)
-                    sts_u64_volatile(&prog_s, (unsigned long long)(unsigned)(tl + 1) | ((unsigned long long)(unsigned)nz_issued << 32));
                 }
                 viol += fabs(upd);
                 va = nva; vb = nvb; ta = nta; tb = ntb; pold = npold;
@@ -699,8 +677,6 @@ __device__ void engine_role(const WArgs &a, unsigned char *smem_raw, int nbulk) 
                 chain_state[0] = viol;
 #pragma unroll
                 for (int q = 0; q < NC; q++) chain_state[1 + q] = cache[q];
-                spec_cnt_s[0] += n_spec;
-                spec_cnt_s[1] += (unsigned long long)n_rej;
                 winnz_s = nz_issued;
             }
         } else {

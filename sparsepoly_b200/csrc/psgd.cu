@@ -454,7 +454,6 @@ __device__ __forceinline__ void up_phase0(const UpArgs &a, double *ssum, double 
             const long long step = (long long)nblk * rpp;
             long long r = (long long)blockIdx.x * rpp + row0;
             const unsigned char *tch = a.touched;
-            const bool last_order = o == a.n_orders - 1;
             for (; r + 3 * step < d; r += 4 * step) {     // 8 independent loads in flight per thread
                 double pv[4], gv[4];
                 bool tv[4];
