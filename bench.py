@@ -99,9 +99,12 @@ class ClockSampler:
                         reasons.add(nm)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None,
+               "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if not sm:
+            out["note"] = "timed region shorter than the 200 ms sampling period of nvidia-smi"
+        return out
 
 
 def profiled_traffic(kernel_key):
@@ -371,6 +374,8 @@ def run_sweep_workload(name, args, rank, world, local):
                      {"sweep": "cluster", "n_cta": est._dev_state["plan"].n_cta,
                       "threads": est._dev_state["plan"].threads}),
     }
+    if result["geometry"]["sweep"] == "window" and name == "pbcd":
+        result["roofline"]["kernel"] = "pbcd_wsweep_kernel (pbcd_window.cu)"
     if result["geometry"]["sweep"] == "window" and name in ("pcd", "allsub"):
         result["roofline"]["kernel"] = "wsweep_kernel (pcd_window.cu)"
         if name == "pcd" and args.scale == 1.0:
