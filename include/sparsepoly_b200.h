@@ -148,6 +148,8 @@ int sp_wspec_read(unsigned long long *out_host /*[2]*/);
 /* debug: per-position timestamps of window 100 of the last sweep; out_host [SP_WINDOW_MAX*8] */
 int sp_wtrace_read(long long *out_host);
 /* slots (hot sample records) the engine CTA can hold in shared memory for records of this stride */
+/* most hot-record slots per window the engine CTA can stage for this record stride (always even;
+ * sp_wplan.slot_cap must be even and <= this) */
 int sp_wplan_slot_cap(int rec_stride);
 /* out[c*rows+r] = in[r*cols+c] */
 int sp_transpose_f64(const double *in, double *out, int rows, int cols, sp_stream stream);

@@ -969,7 +969,9 @@ extern "C" int sp_wtrace_read(long long *out_host /*[SP_WINDOW_MAX*8]*/) {
 
 extern "C" int sp_wplan_slot_cap(int rec_stride) {
     if (rec_stride < 2) rec_stride = 2;
-    return W_REC_BYTES / (rec_stride * 8 + 40);    // + room for 2 hot nonzeros (12 B each) and a 128-bit mover mask per slot
+    // + room for 2 hot nonzeros (12 B each) and a 128-bit mover mask per slot; even, so that the masks
+    // (which follow 24*slot_cap bytes of hot nonzeros) stay 16-byte aligned
+    return (W_REC_BYTES / (rec_stride * 8 + 40)) & ~1;
 }
 
 // degree: 1 = linear (cd_linear), -1 = all-subsets, 2..SP_MAXDEG = ANOVA
@@ -982,7 +984,7 @@ int sp_wsweep(const sp_dataset *ds, const sp_wplan *wp, const int32_t *idx_feat,
         return SP_ERR_INVALID;
     }
     if (wp->window < 1 || wp->window > SP_WINDOW_MAX || wp->horizon < 0 || wp->horizon > 1 ||
-        wp->slot_cap > sp_wplan_slot_cap(rec_stride) || wp->slot_cap > 32768) {
+        wp->slot_cap > sp_wplan_slot_cap(rec_stride) || wp->slot_cap > 32768 || (wp->slot_cap & 1)) {
         sp_set_error("window plan: window %d / horizon %d / slot_cap %d invalid for record stride %d",
                      wp->window, wp->horizon, wp->slot_cap, rec_stride);
         return SP_ERR_INVALID;
