@@ -103,3 +103,33 @@ def test_local_batches_cover_reference_minibatches():
     order = interleave_shards(shards, B)
     assert order[:8].tolist() == [0, 1, 2, 3, 100, 101, 102, 103]
     assert sorted(order.tolist()) == sorted(np.concatenate(shards).tolist())
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/sparsepoly_b200.h (compiled with gcc) against the
+    ctypes mirrors in sparsepoly_b200/_lib.py: a renamed or reordered field must not go unnoticed."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from sparsepoly_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    mirrors = {"sp_dataset": _lib.SpDataset, "sp_plan": _lib.SpPlan, "sp_wplan": _lib.SpWPlan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sparsepoly_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof(struct {cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof(struct {cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, val = ln.split()
+        got[(cname, field)] = int(val)
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
