@@ -166,3 +166,113 @@ def test_protocol_commits_the_sequential_sweep(seed, p_mover, p_surprise):
     assert out["state"] == want_state
     assert sh.rec == want_rec
     assert all(sh.wbflag)
+
+
+# ------------------------------------------------------------------------------------------
+# Window hand-over with the EARLY BASE of the bulk CTAs (pcd_window.cu, bulk_role / engine_role,
+# horizon 0): bulk CTA b reduces the (cold) records of its positions of window w+1 while the engine
+# is still in window w; the engine publishes nzwin[w] with eng_done and, when it is 0, starts window
+# w+1 on the early sums without waiting for WB(w) / an exact BASE(w+1).
+def _hand_over_problem(rng, n_win, nb, n_rec, p_move):
+    wins = []
+    for _ in range(n_win):
+        recs = rng.sample(range(n_rec), nb * 2)          # every record is touched by one position per window
+        wins.append([dict(recs=recs[2 * i:2 * i + 2], moves=rng.random() < p_move) for i in range(nb)])
+    return wins
+
+
+def _decide(w, i, p, s, state):
+    upd = ((s + state + w + i) % 4 + 1) if p["moves"] else 0
+    return upd, state + (upd != 0)
+
+
+def _hand_over_sequential(wins, n_rec):
+    rec, state, upds = list(range(n_rec)), 0, []
+    for w, win in enumerate(wins):
+        for i, p in enumerate(win):
+            upd, state = _decide(w, i, p, sum(rec[r] for r in p["recs"]), state)
+            upds.append(upd)
+            for r in p["recs"]:
+                rec[r] += upd
+    return rec, upds
+
+
+def _bulk(b, nbulk, wins, sh):
+    n_win, early_valid = len(wins), False
+
+    def base(w):
+        for i in range(b, len(wins[w]), nbulk):
+            s = 0
+            for r in wins[w][i]["recs"]:
+                s += sh["rec"][r]
+                yield
+            sh["base"][w][i] = s
+            yield
+
+    for w in range(n_win):
+        if not early_valid:
+            while (w >= 1 and sh["wb_cnt"][w - 1] < nbulk) or sh["eng_done"] < w:
+                yield
+            yield from base(w)
+            sh["base_cnt"][w] += 1
+        if w + 1 < n_win:
+            yield from base(w + 1)                           # early: assumes window w changes no record
+            sh["early_cnt"][w + 1] += 1
+        while sh["eng_done"] < w + 1:
+            yield
+        early_valid = sh["nzwin"][w] == 0
+        if not early_valid:
+            for i in range(b, len(wins[w]), nbulk):
+                upd = sh["res"][w][i]
+                if upd != 0:
+                    for r in wins[w][i]["recs"]:
+                        sh["rec"][r] += upd
+                        yield
+        sh["wb_cnt"][w] += 1
+        yield
+
+
+def _engine(nbulk, wins, sh, out):
+    state, prev_nz = 0, 1
+    for w, win in enumerate(wins):
+        if w > 0 and prev_nz == 0:
+            while sh["early_cnt"][w] < nbulk:
+                yield
+        else:
+            while sh["base_cnt"][w] < nbulk or (w >= 1 and sh["wb_cnt"][w - 1] < nbulk):
+                yield
+        nz = 0
+        for i, p in enumerate(win):
+            upd, state = _decide(w, i, p, sh["base"][w][i], state)
+            sh["res"][w][i] = upd
+            out.append(upd)
+            nz += upd != 0
+            yield
+        sh["nzwin"][w] = nz
+        prev_nz = nz
+        yield
+        sh["eng_done"] = w + 1
+
+
+@pytest.mark.parametrize("p_move", [0.0, 0.02, 0.2, 1.0])
+@pytest.mark.parametrize("seed", range(10))
+def test_early_base_hand_over_matches_the_sequential_sweep(seed, p_move):
+    rng = random.Random(77 * seed + int(1000 * p_move))
+    n_win, nb, n_rec, nbulk = 9, 6, 40, 3
+    wins = _hand_over_problem(rng, n_win, nb, n_rec, p_move)
+    want_rec, want_upds = _hand_over_sequential(wins, n_rec)
+    sh = dict(rec=list(range(n_rec)), base=[[None] * nb for _ in range(n_win)], res=[[None] * nb for _ in range(n_win)],
+              base_cnt=[0] * n_win, early_cnt=[0] * (n_win + 1), wb_cnt=[0] * n_win, nzwin=[None] * n_win, eng_done=0)
+    out = []
+    actors = [_engine(nbulk, wins, sh, out)] + [_bulk(b, nbulk, wins, sh) for b in range(nbulk)]
+    live, steps = list(range(len(actors))), 0
+    while live:
+        i = rng.choice(live)
+        try:
+            next(actors[i])
+        except StopIteration:
+            live.remove(i)
+        steps += 1
+        assert steps < 2_000_000, "hand-over dead-locked"
+    assert out == want_upds
+    assert sh["rec"] == want_rec
