@@ -32,13 +32,18 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 2
+#define SP_ABI_VERSION 3
 #define SP_MAX_HOT_FEATURES 16
 #define SP_PBCD_ENT_PER_SLOT 3  /* pbcd window plan: hot nonzeros per window <= 3*slot_cap (pcd: 2*slot_cap) */
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
 #define SP_WPLAN_NO_SPECULATION 1   /* sp_wplan.flags: workers always wait for the write-backs they depend on;
                                        bits 8..15 (debug): a window speculates when <= 1/value of its
                                        coordinates start nonzero (0 = built-in default: <= 55 %) */
+
+#define SP_PSGD_CHUNK 64      /* nonzeros per work item of the planned psgd column pass */
+#define SP_PSGD_BAND_CAP 2048 /* band values per column and rank of the squared-l1,2 selection */
+#define SP_MAX_RANKS 8        /* most ranks (GPUs of one NVSwitch domain) a psgd fit is sharded over */
+#define SP_PSGD_CHANNELS 2    /* flag channels per rank: 0 step barriers, 1 exchanges inside the selection */
 
 typedef void *sp_stream;
 
@@ -244,6 +249,91 @@ int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_or
                   int loss, double *grad_P, double *grad_w, const int32_t *idx_samples,
                   int fit_linear, double eta0, int learning_rate, double power_t, int batch_size,
                   int64_t *it_io_host, double *loss_sum, double *work, sp_stream stream);
+
+
+/* ------------------------------------------------------------------- planned psgd (l1 / squaredl12) */
+/* "Batch CSC" plan of one sample order (built by the host layer with device sorts; psgd_plan.py): the
+ * nonzeros of every minibatch regrouped by feature, samples ascending inside a feature -- the order in
+ * which psgd._update_grads (psgd.py:60-91) adds them.  Minibatch m covers local positions
+ * [m*batch_local, min((m+1)*batch_local, n_local)) of idx_samples.  Arrays named *_host live in host
+ * memory, all others on the device.  Sharded plans (world > 1) order a minibatch's columns by
+ * (owner = feature % world, feature) and carry the owner-side tables. */
+typedef struct sp_psgd_plan {
+    int32_t n_minibatches, batch_local, n_local, chunk;     /* chunk must equal SP_PSGD_CHUNK */
+    const int64_t *mb_eptr_host;   /* [M+1] first nonzero of every minibatch */
+    const int64_t *mb_uptr_host;   /* [M+1] first column (distinct feature) of every minibatch */
+    const int64_t *mb_cptr_host;   /* [M+1] first chunk: minibatch m has ceil(n_entries/chunk) chunks */
+    const int64_t *mb_sptr_host;   /* [M+1] first entry of split_u */
+    const int32_t *e_pos;          /* [E] position of the sample inside its minibatch | 0x80000000 on the
+                                      first nonzero of a column */
+    const double *e_x;             /* [E] value */
+    const int32_t *u_feat;         /* [U] feature id of every column */
+    const int64_t *u_ptr;          /* [U+1] first nonzero of every column */
+    const int32_t *chunk_u0;       /* [n_chunks] column that holds the chunk's first nonzero */
+    const int32_t *split_u;        /* [S] columns whose nonzeros span more than one chunk */
+    int64_t max_chunks;            /* most chunks in one minibatch (sizes part_g / part_w) */
+    int64_t max_cols;              /* most columns in one minibatch (sizes the staging buffers) */
+    /* sharded only */
+    const int32_t *csr_slot;       /* [nnz] per CSR nonzero: index of its feature in its minibatch's columns */
+    const int32_t *mb_owner_start_host; /* [M][world+1] first column of every owner inside the minibatch */
+    const int64_t *mb_optr_host;   /* [M+1] first entry of own_q / own_src */
+    const int32_t *own_q;          /* [O] rows (feature / world) of this rank touched by the GLOBAL minibatch */
+    const int32_t *own_src;        /* [O][world] index of that row in the inbox region of every rank, or -1 */
+} sp_psgd_plan;
+
+/* State of a planned psgd fit: model, scratch and (sharded) peer pointers.  P / w hold RAW values in the
+ * lazy frame  value = soft_threshold(raw, thr[column]) / C  (w: raw / Cw) between sp_psgd_plan_begin and
+ * the materialising sp_psgd_plan_end; C, Cw, seq* are maintained by the library.  When sharded, P / w
+ * are this rank's rows j % world == rank (d_rows = ceil(d / world)) and the peer_* pointers come from
+ * sp_ipc_open (CUDA IPC, peer memory over NVLink). */
+typedef struct sp_psgd_ctx {
+    double *P, *w;                 /* [n_orders, d_rows, k], [d_rows] */
+    const double *lams;            /* [k] */
+    double *thr;                   /* [n_orders*k] raw-space thresholds */
+    int32_t n_orders, k, d_rows, degree, reg, loss, fit_linear;
+    int32_t world, rank;
+    double *bufA, *bufdL;          /* [batch_local, arows*k], [batch_local]: per-sample tables of one minibatch */
+    double *sample_loss;           /* [n_local] */
+    double *part_g, *part_w;       /* [max_chunks, 2, n_orders*k], [max_chunks, 2] */
+    double *work;                  /* sp_psgd_plan_work_doubles() */
+    double *xwork;                 /* sp_psgd_plan_xwork_doubles(): statistics boxes (peer-visible when sharded) */
+    double C, Cw;
+    uint64_t seq, seq_generic;
+    /* sharded only */
+    double *stage, *stage_w;       /* [max_cols, n_orders, k], [max_cols] */
+    double *inbox_g, *inbox_w;     /* [world, inbox_cap, n_orders*k], [world, inbox_cap] (peer-visible) */
+    int64_t inbox_cap;
+    int32_t *err;                  /* device flag: a cross-rank wait timed out */
+    double *peer_P[SP_MAX_RANKS], *peer_w[SP_MAX_RANKS];
+    double *peer_inbox_g[SP_MAX_RANKS], *peer_inbox_w[SP_MAX_RANKS];   /* region of THIS rank in rank r's inbox */
+    double *peer_xwork[SP_MAX_RANKS];
+    uint64_t *peer_flags[SP_MAX_RANKS];    /* [SP_PSGD_CHANNELS][SP_MAX_RANKS] per rank; [rank] is local */
+} sp_psgd_ctx;
+
+size_t sp_psgd_plan_work_doubles(int n_orders, int k);
+size_t sp_psgd_plan_xwork_doubles(int n_orders, int k, int world);
+/* start of a fit: thresholds, scales and the selection state are reset (P / w hold the model) */
+int sp_psgd_plan_begin(sp_psgd_ctx *ctx, sp_stream stream);
+/* minibatches [m_begin, m_end) of psgd.psgd_epoch (psgd.py:150-198): per minibatch the rows pass
+ * (_pred, psgd.py:47-57), the column pass (_update_grads + the SGD step of _update_params,
+ * psgd.py:60-117, on the touched rows only) and the prox (psgd.py:119-122) as a lazily applied column
+ * threshold; *it_io_host advances once per minibatch. */
+int sp_psgd_plan_run(sp_psgd_ctx *ctx, const sp_dataset *ds, const sp_psgd_plan *plan, const double *y,
+                     const int32_t *idx_samples, double alpha, double beta, double gamma, double eta0,
+                     int learning_rate, double power_t, int m_begin, int m_end, int64_t *it_io_host,
+                     sp_stream stream);
+/* end of an epoch: *loss_sum (device, may be NULL) += sum of the per-sample losses of positions
+ * [0, n_local) in fixed order; materialize != 0 rewrites P / w as the model (thr = 0, C = Cw = 1). */
+int sp_psgd_plan_end(sp_psgd_ctx *ctx, int n_local, double *loss_sum, int materialize, sp_stream stream);
+
+/* peer-visible device memory for the sharded path (cudaMalloc + CUDA IPC); handle64: 64 bytes */
+int sp_shm_alloc(size_t bytes, void **out_host);
+int sp_shm_free(void *p);
+int sp_ipc_export(void *p, unsigned char *handle64_host);
+int sp_ipc_open(const unsigned char *handle64_host, void **out_host);
+int sp_ipc_close(void *p);
+/* kind: 0 host->device, 1 device->host (synchronises the stream), 2 device->device */
+int sp_memcpy(void *dst, const void *src, size_t bytes, int kind, sp_stream stream);
 
 /* ------------------------------------------------------------------------------ objective */
 /* The quantity the reference's update rules minimise but never evaluate

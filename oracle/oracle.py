@@ -88,10 +88,22 @@ def lib():
                                         C.c_int64, _dp, _dp]
         L.sp_oracle_loss_sum.restype = C.c_double
         L.sp_oracle_loss_sum.argtypes = [C.c_int, C.c_int, _dp, _dp]
+        L.sp_oracle_branch_count.restype = C.c_longlong
+        L.sp_oracle_branch_count.argtypes = [C.c_int]
         L.sp_oracle_reg_eval.restype = C.c_double
         L.sp_oracle_reg_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp]
         _LIB = L
     return _LIB
+
+
+def branch_counts(reset=False):
+    """How often the rounding-triggered recovery branches ran since the last reset: (omegacs negative
+    dcache, omegacs.py:90-96; omegacs negative cache recompute, :75-76/:80-81; squaredl21 drift guard,
+    squaredl21.py:49-50).  Used to make sure a fixture really enters them."""
+    out = tuple(int(lib().sp_oracle_branch_count(t)) for t in range(3))
+    if reset:
+        lib().sp_oracle_branch_reset()
+    return out
 
 
 # --------------------------------------------------------------------------- data layouts

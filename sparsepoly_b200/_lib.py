@@ -42,7 +42,37 @@ class SpPlan(C.Structure):
                 ("idx_feat", _vp), ("pos_conf", _vp), ("win", C.POINTER(SpWPlan))]
 
 
+MAX_RANKS = 8
+
+
+class SpPsgdPlan(C.Structure):
+    """struct sp_psgd_plan (include/sparsepoly_b200.h)."""
+    _fields_ = [("n_minibatches", C.c_int32), ("batch_local", C.c_int32), ("n_local", C.c_int32), ("chunk", C.c_int32),
+                ("mb_eptr_host", _vp), ("mb_uptr_host", _vp), ("mb_cptr_host", _vp), ("mb_sptr_host", _vp),
+                ("e_pos", _vp), ("e_x", _vp), ("u_feat", _vp), ("u_ptr", _vp), ("chunk_u0", _vp), ("split_u", _vp),
+                ("max_chunks", C.c_int64), ("max_cols", C.c_int64),
+                ("csr_slot", _vp), ("mb_owner_start_host", _vp), ("mb_optr_host", _vp), ("own_q", _vp), ("own_src", _vp)]
+
+
+class SpPsgdCtx(C.Structure):
+    """struct sp_psgd_ctx (include/sparsepoly_b200.h)."""
+    _fields_ = [("P", _vp), ("w", _vp), ("lams", _vp), ("thr", _vp),
+                ("n_orders", C.c_int32), ("k", C.c_int32), ("d_rows", C.c_int32), ("degree", C.c_int32),
+                ("reg", C.c_int32), ("loss", C.c_int32), ("fit_linear", C.c_int32),
+                ("world", C.c_int32), ("rank", C.c_int32),
+                ("bufA", _vp), ("bufdL", _vp), ("sample_loss", _vp), ("part_g", _vp), ("part_w", _vp),
+                ("work", _vp), ("xwork", _vp), ("C", C.c_double), ("Cw", C.c_double),
+                ("seq", C.c_uint64), ("seq_generic", C.c_uint64),
+                ("stage", _vp), ("stage_w", _vp), ("inbox_g", _vp), ("inbox_w", _vp), ("inbox_cap", C.c_int64),
+                ("err", _vp),
+                ("peer_P", _vp * MAX_RANKS), ("peer_w", _vp * MAX_RANKS),
+                ("peer_inbox_g", _vp * MAX_RANKS), ("peer_inbox_w", _vp * MAX_RANKS),
+                ("peer_xwork", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS)]
+
+
 _DSP = C.POINTER(SpDataset)
+_PPP = C.POINTER(SpPsgdPlan)
+_PCP = C.POINTER(SpPsgdCtx)
 _PLP = C.POINTER(SpPlan)
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -84,6 +114,17 @@ SIGNATURES = {
     "sp_prox": (_i, [_vp, _i, _i, _i, _d, _vp, _vp]),
     "sp_psgd_epoch": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp,
                            _i, _d, _i, _d, _i, C.POINTER(C.c_int64), _vp, _vp, _vp]),
+    "sp_psgd_plan_work_doubles": (C.c_size_t, [_i, _i]),
+    "sp_psgd_plan_xwork_doubles": (C.c_size_t, [_i, _i, _i]),
+    "sp_psgd_plan_begin": (_i, [_PCP, _vp]),
+    "sp_psgd_plan_run": (_i, [_PCP, _DSP, _PPP, _vp, _vp, _d, _d, _d, _d, _i, _d, _i, _i, C.POINTER(C.c_int64), _vp]),
+    "sp_psgd_plan_end": (_i, [_PCP, _i, _vp, _i, _vp]),
+    "sp_shm_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "sp_shm_free": (_i, [_vp]),
+    "sp_ipc_export": (_i, [_vp, C.POINTER(C.c_ubyte)]),
+    "sp_ipc_open": (_i, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    "sp_ipc_close": (_i, [_vp]),
+    "sp_memcpy": (_i, [_vp, _vp, C.c_size_t, _i, _vp]),
     "sp_loss_sum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sp_sqnorm": (_i, [_vp, C.c_int64, _vp, _vp, _vp]),
     "sp_sum_work_doubles": (C.c_size_t, []),
@@ -99,9 +140,13 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    if LIB_PATH == os.path.join(_HERE, "libsparsepoly_b200.so"):
         from . import build as _build
-        _build.build()
+        try:
+            _build.build()                       # no-op when the library is newer than every source
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):     # (a box without nvcc can still use a prebuilt library)
+                raise
     try:
         import torch  # noqa: F401  (makes torch's libcudart.so.12 the shared runtime instance)
     except Exception:
@@ -111,7 +156,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sp_abi_version() != 2:
+    if lib.sp_abi_version() != 3:
         raise ImportError("libsparsepoly_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -1,0 +1,1387 @@
+// Planned proximal minibatch SGD (reference optimizer/psgd.py:9-199) for the regularizers whose prox is
+// a column-wise soft threshold: l1 (l1.py:50-51) and squaredl12 (squaredl12.py:66-78, utils.py:26-70).
+//
+// The reference scatters every sample's gradient into a dense grad_P [n_orders,d,k] and then sweeps
+// P, grad_P and the prox over all d*k entries once per minibatch.  Here a minibatch is two GATHER
+// passes over a precomputed plan and nothing is ever scattered:
+//
+//   rows  (psgd_rows_kernel)  one group of lanes per sample (lane = component): psgd._pred
+//                             (psgd.py:47-57) -> the sample's ANOVA table rows A^1..A^(m-1) and
+//                             dloss go to a small per-minibatch buffer (L2 resident);
+//   cols  (psgd_cols_kernel)  the minibatch's nonzeros regrouped by feature (the "batch CSC" plan,
+//                             built once per sample order): for every touched feature j the terms of
+//                             psgd._update_grads (psgd.py:60-91) are summed in ascending sample order
+//                             -- the reference's own order, no atomics, deterministic -- and the SGD
+//                             step of psgd._update_params (psgd.py:94-117) is applied to row P[j,:]
+//                             right there.  Work is cut into chunks of SP_PSGD_CHUNK nonzeros; a
+//                             feature that spans several chunks (dense columns) leaves partial sums
+//                             that psgd_split_kernel adds in chunk order.
+//   untouched rows are never read or written by the step: the divisions by (1 + eta*beta) and the
+//   prox thresholds are kept LAZY in a per-column frame  value = soft_threshold(raw, T_c) / C
+//   (shrink-then-scale maps compose), so a minibatch rewrites only the rows it touches.
+//   stats (psgd_stats_kernel) squaredl12 only: one read-only streaming pass over the raw matrix collects,
+//                             per column, (count, sum) of |value| above a band around the predicted
+//                             threshold and the band's values;
+//   solve (psgd_solve_kernel) sorts each band and runs the fixed-point iteration
+//                             tau <- 2 s S(tau) / (1 + 2 s C(tau)) to the (theta, S) that the reference's
+//                             randomized-pivot search finds (utils.py:26-70); generic read-only passes
+//                             when a band misses.
+//
+// Sharded over G ranks (one process per GPU, samples sharded, P sharded by rows j % G): the ranks PULL
+// the rows their minibatch touches from the owners' HBM over NVLink peer memory (psgd_pull_kernel),
+// PUSH their partial gradient rows into the owners' inboxes (cols kernel epilogue), the owner adds
+// them in rank order and updates its rows (psgd_owner_kernel), and the column statistics are
+// exchanged through peer memory as well -- no NCCL on the data path.
+#include <cooperative_groups.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sparsepoly_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int PL_THREADS = 256;
+constexpr int CH = SP_PSGD_CHUNK;
+constexpr int BAND_CAP = SP_PSGD_BAND_CAP;          // band values per column and rank
+constexpr int BAND_TOTAL = 2048;                    // band values per column over all ranks (shared memory)
+constexpr int STAT_PART_MAX = 148 * 8;              // most blocks of the statistics pass
+constexpr double BAND_DELTA = 0.02;
+constexpr unsigned long long SPIN_TIMEOUT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ double st_true(double r, double T, double invC) {
+    double m = fabs(r) - T;                                  // value = soft_threshold(raw, T) / C
+    if (!(m > 0.0)) return 0.0;
+    m = m * invC;
+    return r > 0.0 ? m : -m;
+}
+// raw representation of `v` in the frame (Cn, T)
+__device__ __forceinline__ double to_raw(double v, double T, double Cn) {
+    if (v == 0.0) return 0.0;
+    const double a = fabs(v) * Cn + T;
+    return v > 0.0 ? a : -a;
+}
+
+template <int DEG, int NORD> struct ARows {          // rows A^1..A^(deg_o-1) kept per sample, all orders
+    static constexpr int value = (DEG - 1) + ARows<DEG - 1, NORD - 1>::value;
+};
+template <int DEG> struct ARows<DEG, 0> { static constexpr int value = 0; };
+template <int DEG, int NORD> __device__ __forceinline__ constexpr int arow_off(int o) {
+    int off = 0;
+    for (int q = 0; q < o; q++) off += DEG - q - 1;
+    return off;
+}
+
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+    return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+}
+
+// ------------------------------------------------------------------------------------ rows
+struct RowsArgs {
+    int k, d;
+    const int32_t *indptr, *colidx;      // colidx: feature ids, or (STAGED) slots in the minibatch's column list
+    const double *data, *y;
+    const double *Psrc, *wsrc;           // raw P [n_orders,d,k] / raw w [d]; STAGED: staged true values [U][n_orders][k] / [U]
+    const double *lams, *thr;
+    double invC, invCw;
+    int loss, fit_linear;
+    const int32_t *idx;
+    int b0, b1;
+    double *bufA, *bufdL, *sloss;        // [b1-b0][AROWS*k], [b1-b0], [n_local]
+};
+
+template <int DEG, int NORD, int G, int KCH, bool STAGED>
+__global__ void __launch_bounds__(PL_THREADS) psgd_rows_kernel(const RowsArgs a) {
+    constexpr int AR = ARows<DEG, NORD>::value;
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int gpb = PL_THREADS / G;
+    const int n_groups = gridDim.x * gpb;
+    const int k = a.k;
+    const size_t dk = (size_t)a.d * k;
+    double lam[KCH], thr[KCH][NORD];
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int s = lane + G * c;
+        lam[c] = s < k ? a.lams[s] : 0.0;
+#pragma unroll
+        for (int o = 0; o < NORD; o++) thr[c][o] = (!STAGED && s < k) ? a.thr[o * k + s] : 0.0;
+    }
+    for (int b = a.b0 + blockIdx.x * gpb + threadIdx.x / G; b < a.b1; b += n_groups) {
+        const int i = a.idx[b];
+        const int st = a.indptr[i], en = a.indptr[i + 1];
+        double A[KCH][NORD][DEG + 1];
+#pragma unroll
+        for (int c = 0; c < KCH; c++)
+#pragma unroll
+            for (int o = 0; o < NORD; o++) {
+                A[c][o][0] = 1.0;
+#pragma unroll
+                for (int t = 1; t <= DEG; t++) A[c][o][t] = 0.0;
+            }
+        double ypred = 0.0;                                   // _pred, psgd.py:47-57
+        for (int base = st; base < en; base += G) {
+            const int e = base + lane;
+            int jl = 0;
+            double xl = 0.0;
+            if (e < en) {
+                jl = a.colidx[e]; xl = a.data[e];
+                if (a.fit_linear) ypred += xl * (STAGED ? a.wsrc[jl] : a.wsrc[jl] * a.invCw);
+            }
+            const int cnt = min(G, en - base);
+            constexpr int UB = (KCH * NORD <= 2) ? 8 : 2;
+            for (int q0 = 0; q0 < cnt; q0 += UB) {
+                double pv[UB][KCH][NORD], xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {                // UB independent row gathers in flight
+                    const int q = q0 + u;
+                    const int j = __shfl_sync(gmask, jl, q & (G - 1), G);
+                    xv[u] = __shfl_sync(gmask, xl, q & (G - 1), G);
+#pragma unroll
+                    for (int c = 0; c < KCH; c++)
+#pragma unroll
+                        for (int o = 0; o < NORD; o++) {
+                            const int s = lane + G * c;
+                            const size_t at = STAGED ? ((size_t)j * NORD + o) * k + s : o * dk + (size_t)j * k + s;
+                            pv[u][c][o] = (q < cnt && s < k) ? a.Psrc[at] : 0.0;
+                        }
+                }
+                if (!STAGED) {
+#pragma unroll
+                    for (int u = 0; u < UB; u++)
+#pragma unroll
+                        for (int c = 0; c < KCH; c++)
+#pragma unroll
+                            for (int o = 0; o < NORD; o++) pv[u][c][o] = st_true(pv[u][c][o], thr[c][o], a.invC);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    if (q0 + u < cnt) {
+#pragma unroll
+                        for (int c = 0; c < KCH; c++)
+#pragma unroll
+                            for (int o = 0; o < NORD; o++)
+#pragma unroll
+                                for (int t = 0; t < DEG - o; t++)       // _anova, psgd.py:34-44
+                                    A[c][o][DEG - o - t] += (A[c][o][DEG - o - t - 1] * xv[u]) * pv[u][c][o];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = G / 2; m > 0; m >>= 1) ypred += __shfl_xor_sync(gmask, ypred, m, G);
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {                      // y_pred += dot(lams, A[order, deg])
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < KCH; c++) v += lam[c] * A[c][o][DEG - o];
+#pragma unroll
+            for (int m = G / 2; m > 0; m >>= 1) v += __shfl_xor_sync(gmask, v, m, G);
+            ypred += v;
+        }
+        const double yi = a.y[i];
+        double *row = a.bufA + (size_t)(b - a.b0) * AR * k;
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int s = lane + G * c;
+            if (s < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++)
+#pragma unroll
+                    for (int t = 1; t < DEG - o; t++) row[(size_t)(arow_off<DEG, NORD>(o) + t - 1) * k + s] = A[c][o][t];
+            }
+        }
+        if (lane == 0) {
+            a.bufdL[b - a.b0] = sp_dloss_rt(a.loss, ypred, yi);
+            a.sloss[b] = sp_loss_rt(a.loss, ypred, yi);        // psgd.py:155 (summed in fixed order at epoch end)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ cols
+enum { MODE_APPLY = 0, MODE_PUSH = 1 };
+
+struct StepArgs {                        // psgd._update_params for one row (psgd.py:94-117) in the lazy frame
+    double cP, denP, CnP;                // eta_P / batch, 1 + eta_P*beta, C * denP
+    double cw, denw, Cnw;
+    double invC, invCw;                  // frame the rows are read in
+    int fit_linear;
+};
+
+struct ColsArgs {
+    int k, d;                            // d: rows of P (this rank's rows when sharded)
+    const int32_t *e_pos;                // minibatch-relative entry arrays
+    const double *e_x;
+    long long n_entries;
+    int n_chunks;
+    const int32_t *u_feat;               // ABSOLUTE column arrays
+    const int64_t *u_ptr;
+    long long e_base;                    // absolute entry offset of the minibatch
+    long long u_base;                    // absolute column offset of the minibatch
+    const int32_t *chunk_u0;             // minibatch-relative: absolute column of every chunk's first entry
+    const int32_t *split_u;              // minibatch-relative list of columns spanning > 1 chunk
+    int n_split;
+    const double *bufA, *bufdL;
+    const double *lams, *thr;
+    double *P, *w;                       // APPLY: raw model (read + written)
+    const double *stage, *stage_w;       // PUSH: staged true values [U][n_orders][k], [U]
+    double *part_g, *part_w;             // partial sums of split columns [n_chunks][2][n_orders*k], [n_chunks][2]
+    StepArgs s;
+    // PUSH: owner inboxes (peer memory)
+    int world, rank;
+    int owner_start[SP_MAX_RANKS + 1];   // first minibatch-relative column of every owner
+    double *inbox_g[SP_MAX_RANKS];       // owner's inbox region of THIS rank: [cap][n_orders*k]
+    double *inbox_w[SP_MAX_RANKS];       // [cap]
+};
+
+// psgd._update_params on one row: P = (P - (eta/b) g) / (1 + eta beta), written back in the frame (CnP, T)
+template <int NORD, int G, int KCH>
+__device__ __forceinline__ void apply_row(const StepArgs &s, double *P, double *w, int d, int k, int j, int lane,
+                                          const double (&g)[KCH][NORD], double gw, const double (&pold)[KCH][NORD],
+                                          const double (&thr)[KCH][NORD]) {
+    const size_t dk = (size_t)d * k;
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int sidx = lane + G * c;
+        if (sidx < k) {
+#pragma unroll
+            for (int o = 0; o < NORD; o++) {
+                double gg = g[c][o] * s.cP;                 // grad *= eta / batch          psgd.py:113
+                double v = pold[c][o] - gg;                 // P -= grad                    psgd.py:114
+                v = v / s.denP;                             // P /= 1 + eta*beta            psgd.py:115
+                P[o * dk + (size_t)j * k + sidx] = to_raw(v, thr[c][o], s.CnP);
+            }
+        }
+    }
+    if (s.fit_linear && lane == 0) {                        // psgd.py:109-112
+        const double wold = w[j] * s.invCw;
+        double gg = gw * s.cw;
+        double v = wold - gg;
+        v = v / s.denw;
+        w[j] = v * s.Cnw;
+    }
+}
+
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int ucol, int feat, bool complete, int chunk,
+                                              bool first_col, const double (&g)[KCH][NORD], double gw,
+                                              const double (&pold)[KCH][NORD], const double (&thr)[KCH][NORD]) {
+    const int k = a.k;
+    if (!complete) {                                        // piece of a split column: summed by psgd_split_kernel
+        const size_t slot = (size_t)chunk * 2 + (first_col ? 0 : 1);
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int sidx = lane + G * c;
+            if (sidx < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++) a.part_g[(slot * NORD + o) * k + sidx] = g[c][o];
+            }
+        }
+        if (lane == 0) a.part_w[slot] = gw;
+        return;
+    }
+    if (MODE == MODE_APPLY) {
+        apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d, k, feat, lane, g, gw, pold, thr);
+    } else {
+        const int su = (int)(ucol - a.u_base);
+        const int owner = feat % a.world;
+        const size_t at = (size_t)(su - a.owner_start[owner]);
+        double *dst = a.inbox_g[owner] + at * NORD * k;
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int sidx = lane + G * c;
+            if (sidx < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++) dst[o * k + sidx] = g[c][o];
+            }
+        }
+        if (lane == 0) a.inbox_w[owner][at] = gw;
+    }
+}
+
+// true (pre-update) values of row `feat` / staged slot `su`
+template <int NORD, int G, int KCH, int MODE>
+__device__ __forceinline__ void load_row(const ColsArgs &a, int lane, int feat, long long su, double (&p)[KCH][NORD],
+                                         const double (&thr)[KCH][NORD]) {
+    const int k = a.k;
+    const size_t dk = (size_t)a.d * k;
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int sidx = lane + G * c;
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {
+            if (sidx < k) {
+                if (MODE == MODE_APPLY) p[c][o] = st_true(a.P[o * dk + (size_t)feat * k + sidx], thr[c][o], a.s.invC);
+                else p[c][o] = a.stage[((size_t)su * NORD + o) * k + sidx];
+            } else p[c][o] = 0.0;
+        }
+    }
+}
+
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__global__ void __launch_bounds__(PL_THREADS) psgd_cols_kernel(const ColsArgs a) {
+    constexpr int AR = ARows<DEG, NORD>::value;
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int gshift = (threadIdx.x & 31) & ~(G - 1);
+    const int gpb = PL_THREADS / G;
+    const int chunk = blockIdx.x * gpb + threadIdx.x / G;
+    if (chunk >= a.n_chunks) return;
+    const int k = a.k;
+    double lam[KCH], thr[KCH][NORD];
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int s = lane + G * c;
+        lam[c] = s < k ? a.lams[s] : 0.0;
+#pragma unroll
+        for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
+    }
+    const long long ce0 = (long long)chunk * CH;
+    const long long ce1 = (ce0 + CH < a.n_entries) ? ce0 + CH : a.n_entries;
+    const bool ends_here = (ce1 == a.n_entries) || (a.e_pos[ce1] < 0);
+    int ubase = a.chunk_u0[chunk] - 1;            // (the chunk's first entry counts as a column start below)
+    double g[KCH][NORD], pold[KCH][NORD];
+    double gw = 0.0;
+    int cur_feat = -1, cur_u = -1;
+    bool cur_started = false, cur_first = true, have = false;
+    for (long long base = ce0; base < ce1; base += G) {
+        const long long e = base + lane;
+        int ep = 0;
+        double ex = 0.0;
+        if (e < ce1) { ep = a.e_pos[e]; ex = a.e_x[e]; }
+        const bool nf_l = e < ce1 && (ep < 0 || e == ce0);
+        const unsigned bal = (__ballot_sync(gmask, nf_l) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+        const int ucol_l = ubase + __popc(bal & ((2u << lane) - 1u));
+        int fj_l = 0;
+        if (nf_l) fj_l = a.u_feat[ucol_l];
+        ubase += __popc(bal);
+        const int cnt = (int)((ce1 - base < G) ? ce1 - base : G);
+        constexpr int UB = (KCH * NORD <= 2) ? 8 : 2;
+        for (int q0 = 0; q0 < cnt; q0 += UB) {
+            double av[UB][KCH][AR], dl[UB], xv[UB], pn[UB][KCH][NORD];
+            int nf[UB], fj[UB], uc[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {                      // all loads of the batch first
+                const int q = (q0 + u) & (G - 1);
+                const int pos = __shfl_sync(gmask, ep, q, G) & 0x7fffffff;
+                xv[u] = __shfl_sync(gmask, ex, q, G);
+                nf[u] = (q0 + u < cnt) ? (int)((bal >> q) & 1u) : 0;
+                fj[u] = __shfl_sync(gmask, fj_l, q, G);
+                uc[u] = __shfl_sync(gmask, ucol_l, q, G);
+                const bool live = q0 + u < cnt;
+                dl[u] = live ? a.bufdL[pos] : 0.0;
+#pragma unroll
+                for (int c = 0; c < KCH; c++) {
+                    const int s = lane + G * c;
+#pragma unroll
+                    for (int r = 0; r < AR; r++) av[u][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                }
+                if (nf[u]) load_row<NORD, G, KCH, MODE>(a, lane, fj[u], uc[u] - a.u_base, pn[u], thr);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                if (q0 + u >= cnt) break;
+                if (nf[u]) {
+                    if (have)                                     // the previous column ends before this entry
+                        finish_column<DEG, NORD, G, KCH, MODE>(a, lane, cur_u, cur_feat, cur_started, chunk, cur_first,
+                                                               g, gw, pold, thr);
+                    cur_first = !have;
+                    have = true;
+                    cur_feat = fj[u]; cur_u = uc[u];
+                    cur_started = cur_first ? (__shfl_sync(gmask, ep, (q0 + u) & (G - 1), G) < 0) : true;
+                    gw = 0.0;
+#pragma unroll
+                    for (int c = 0; c < KCH; c++)
+#pragma unroll
+                        for (int o = 0; o < NORD; o++) { g[c][o] = 0.0; pold[c][o] = pn[u][c][o]; }
+                }
+                const double x = xv[u];
+                gw += dl[u] * x;                                  // psgd.py:86
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int o = 0; o < NORD; o++) {
+                        double dprev = x;                         // _grad_anova, psgd.py:25-31
+#pragma unroll
+                        for (int t = 1; t < DEG - o; t++)
+                            dprev = x * (av[u][c][arow_off<DEG, NORD>(o) + t - 1] - pold[c][o] * dprev);
+                        g[c][o] += (dl[u] * lam[c]) * dprev;      // psgd.py:91
+                    }
+            }
+        }
+    }
+    if (have)
+        finish_column<DEG, NORD, G, KCH, MODE>(a, lane, cur_u, cur_feat, cur_started && ends_here, chunk, cur_first, g, gw,
+                                               pold, thr);
+}
+
+// columns that span several chunks: add their pieces in chunk order, then finish them
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__global__ void __launch_bounds__(PL_THREADS) psgd_split_kernel(const ColsArgs a) {
+    const int lane = threadIdx.x & (G - 1);
+    const int gpb = PL_THREADS / G;
+    const int q = blockIdx.x * gpb + threadIdx.x / G;
+    if (q >= a.n_split) return;
+    const int k = a.k;
+    const int u = a.split_u[q];
+    const long long s_rel = a.u_ptr[u] - a.e_base, e_rel = a.u_ptr[u + 1] - a.e_base;
+    const int c0 = (int)(s_rel / CH), c1 = (int)((e_rel - 1) / CH);
+    double thr[KCH][NORD], g[KCH][NORD], pold[KCH][NORD];
+    double gw = 0.0;
+#pragma unroll
+    for (int c = 0; c < KCH; c++)
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {
+            const int s = lane + G * c;
+            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
+            g[c][o] = 0.0;
+        }
+    const int feat = a.u_feat[u];
+    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
+    for (int ch = c0; ch <= c1; ch++) {
+        const size_t slot = (size_t)ch * 2 + ((ch == c0 && s_rel > (long long)c0 * CH) ? 1 : 0);
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int s = lane + G * c;
+            if (s < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++) g[c][o] += a.part_g[(slot * NORD + o) * k + s];
+            }
+        }
+        gw += a.part_w[slot];
+    }
+    finish_column<DEG, NORD, G, KCH, MODE>(a, lane, u, feat, true, 0, true, g, gw, pold, thr);
+}
+
+// ------------------------------------------------------------------------------------ sharded: pull / owner
+struct PullArgs {
+    int k, d_own, world, n_cols;
+    const int32_t *u_feat;               // the minibatch's columns (minibatch-relative pointer)
+    const double *peer_P[SP_MAX_RANKS];  // owners' raw rows [n_orders][d_own][k]
+    const double *peer_w[SP_MAX_RANKS];  // owners' raw w [d_own]
+    const double *thr;
+    double invC, invCw;
+    int n_orders, fit_linear;
+    double *stage, *stage_w;             // [n_cols][n_orders][k], [n_cols]
+};
+
+// true values of the rows this rank's minibatch touches, read from the owners' HBM (NVLink peer loads;
+// .cv: peer lines must not be served from a stale L1)
+__global__ void __launch_bounds__(PL_THREADS) psgd_pull_kernel(const PullArgs a) {
+    const int k = a.k, rowlen = a.n_orders * k;
+    const long long total = (long long)a.n_cols * rowlen;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(t / rowlen), r = (int)(t % rowlen);
+        const int o = r / k, s = r % k;
+        const int j = a.u_feat[u];
+        const int owner = j % a.world, q = j / a.world;
+        const double raw = __ldcv(a.peer_P[owner] + ((size_t)o * a.d_own + q) * k + s);
+        a.stage[t] = st_true(raw, a.thr[o * k + s], a.invC);
+        if (r == 0 && a.fit_linear) a.stage_w[u] = __ldcv(a.peer_w[owner] + q) * a.invCw;
+    }
+}
+
+struct OwnerArgs {
+    int k, d_own, world, n_rows;         // rows of this owner touched by the global minibatch
+    const int32_t *own_q;                // [n_rows] local row index (feature / world)
+    const int32_t *own_src;              // [n_rows][world] index in the inbox region of every rank, or -1
+    const double *inbox_g[SP_MAX_RANKS]; // local inbox regions [cap][n_orders*k]
+    const double *inbox_w[SP_MAX_RANKS];
+    const double *thr;
+    double *P, *w;
+    StepArgs s;
+};
+
+template <int NORD, int G, int KCH>
+__global__ void __launch_bounds__(PL_THREADS) psgd_owner_kernel(const OwnerArgs a) {
+    const int lane = threadIdx.x & (G - 1);
+    const int gpb = PL_THREADS / G;
+    const int r = blockIdx.x * gpb + threadIdx.x / G;
+    if (r >= a.n_rows) return;
+    const int k = a.k;
+    const size_t dk = (size_t)a.d_own * k;
+    const int q = a.own_q[r];
+    double thr[KCH][NORD], g[KCH][NORD], pold[KCH][NORD];
+    double gw = 0.0;
+#pragma unroll
+    for (int c = 0; c < KCH; c++)
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {
+            const int s = lane + G * c;
+            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
+            g[c][o] = 0.0;
+            pold[c][o] = s < k ? st_true(a.P[o * dk + (size_t)q * k + s], thr[c][o], a.s.invC) : 0.0;
+        }
+    for (int src = 0; src < a.world; src++) {               // fixed rank order: deterministic
+        const int at = a.own_src[(size_t)r * a.world + src];
+        if (at < 0) continue;
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int s = lane + G * c;
+            if (s < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++) g[c][o] += a.inbox_g[src][((size_t)at * NORD + o) * k + s];
+            }
+        }
+        gw += a.inbox_w[src][at];
+    }
+    apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d_own, k, q, lane, g, gw, pold, thr);
+}
+
+// ------------------------------------------------------------------------------------ cross-rank flags
+struct XArgs {
+    int world, rank, chan;
+    unsigned long long seq;
+    uint64_t *peer_flags[SP_MAX_RANKS];   // every rank's flag array [SP_PSGD_CHANNELS][SP_MAX_RANKS]
+    uint64_t *my_flags;
+    int *err;                                        // set to 1 on a timeout
+};
+
+__device__ __forceinline__ void flag_store(uint64_t *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_load(const uint64_t *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// thread r < world: tell rank r that this rank reached `seq` on channel `chan`
+__device__ __forceinline__ void x_signal(const XArgs &x, int r) {
+    __threadfence_system();
+    flag_store(x.peer_flags[r] + (size_t)x.chan * SP_MAX_RANKS + x.rank, x.seq);
+}
+// thread r < world: wait until rank r reached `seq`
+__device__ __forceinline__ void x_wait(const XArgs &x, int r) {
+    const uint64_t *f = x.my_flags + (size_t)x.chan * SP_MAX_RANKS + r;
+    const unsigned long long t0 = now_ns();
+    while (flag_load(f) < x.seq) {
+        __nanosleep(64);
+        if (now_ns() - t0 > SPIN_TIMEOUT_NS) { *x.err = 1; break; }
+    }
+    __threadfence_system();
+}
+__global__ void psgd_xbarrier_kernel(const XArgs x) {       // signal + wait: everything the ranks wrote into
+    const int r = threadIdx.x;                              // each other's memory before is visible after
+    if (r < x.world) { x_signal(x, r); x_wait(x, r); }
+}
+
+// ------------------------------------------------------------------------------------ statistics + solve
+// statbox of one source rank (doubles): sum[ncol] | cnt[ncol] | band_n[ncol] | band[ncol][BAND_CAP]
+__host__ __device__ inline size_t statbox_doubles(size_t ncol) { return ncol * (3 + (size_t)BAND_CAP); }
+
+struct StatArgs {
+    const double *P;                     // raw rows [n_orders][d][k] (this rank's rows)
+    int n_orders, d, k;
+    double invC;                         // frame AFTER the update
+    double strength;
+    const double *thr;
+    int reg;
+    double *psum, *pcnt;                 // [STAT_PART_MAX][ncol] per-block partials
+    double *band;                        // [ncol][BAND_CAP] (this rank)
+    int *band_n;                         // [ncol] counters (zeroed before the launch) | [ncol] ticket
+    double *state;                       // persistent: [0] previous strength, [1] calls, [2]/[3] band hits / generic
+                                         // passes, [4] band half-width, [8+c] tau of the last call, [8+ncol+c] the one before
+    double *tau;                         // [ncol] thresholds of the generic passes (value units); NULL: band pass
+    int world, rank;
+    double *statbox[SP_MAX_RANKS];       // every rank's statbox region of THIS rank (peer memory; [rank] is local)
+    int *err;
+};
+
+__device__ __forceinline__ double predict_tau(const double *state, int ncol, int c, double strength) {
+    const double last = state[8 + c], older = state[8 + ncol + c];
+    double ratio = strength / state[0];
+    if (state[1] >= 2.0 && older > 0.0) ratio = last / older;
+    if (ratio < 0.5) ratio = 0.5;
+    if (ratio > 2.0) ratio = 2.0;
+    return last * ratio;
+}
+
+// One read-only pass over this rank's rows: per-block (sum, count) of the values above the statistics
+// threshold of every column -- the band's upper edge (band pass) or a.tau[c] (generic pass) -- and, in a
+// band pass, the values inside the band.  Partials are combined in fixed order.
+__device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, double *scnt, bool band_pass) {
+    const int tid = threadIdx.x, T = blockDim.x, nblk = gridDim.x, k = a.k, d = a.d;
+    const int ncol = a.n_orders * k;
+    const int tpr = k < T ? k : T;
+    const int rpp = T / tpr;
+    const int col = tid % tpr, row0 = tid / tpr;
+    const bool worker = tid < tpr * rpp;
+    const double bdelta = a.state[4] > 0.0 ? a.state[4] : BAND_DELTA;
+    for (int o = 0; o < a.n_orders; o++) {
+        for (int c0 = 0; c0 < k; c0 += tpr) {
+            const int cc = c0 + col;
+            const bool act = worker && cc < k;
+            const int cidx = o * k + (act ? cc : 0);
+            const double *P = a.P + (size_t)o * d * k;
+            const double Tc = a.thr[cidx];
+            double hi, lo;
+            bool band_on = false;
+            if (band_pass) {
+                const double last = a.state[8 + cidx];
+                band_on = a.state[0] > 0.0 && a.strength > 0.0 && last > 0.0;
+                const double tp = band_on ? predict_tau(a.state, ncol, cidx, a.strength) : 0.0;
+                hi = band_on ? tp * (1.0 + bdelta) : 0.0;
+                lo = band_on ? tp * (1.0 - bdelta) : 0.0;
+            } else {
+                hi = lo = a.tau[cidx];
+            }
+            double lsum = 0.0, lcnt = 0.0;
+            if (act) {
+                const long long step = (long long)nblk * rpp;
+                long long r = (long long)blockIdx.x * rpp + row0;
+                for (; r + 7 * step < d; r += 8 * step) {       // 8 independent loads in flight
+                    double rv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) rv[u] = P[(size_t)(r + u * step) * k + cc];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const double m = fabs(rv[u]) - Tc;
+                        if (m > 0.0) {
+                            const double v = m * a.invC;
+                            if (v > hi) { lsum += v; lcnt += 1.0; }
+                            else if (band_on && v > lo) {
+                                const int bi = atomicAdd(a.band_n + cidx, 1);
+                                if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = v;
+                            }
+                        }
+                    }
+                }
+                for (; r < d; r += step) {
+                    const double m = fabs(P[(size_t)r * k + cc]) - Tc;
+                    if (m > 0.0) {
+                        const double v = m * a.invC;
+                        if (v > hi) { lsum += v; lcnt += 1.0; }
+                        else if (band_on && v > lo) {
+                            const int bi = atomicAdd(a.band_n + cidx, 1);
+                            if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = v;
+                        }
+                    }
+                }
+            }
+            ssum[tid] = lsum; scnt[tid] = lcnt;
+            __syncthreads();
+            if (tid < tpr && c0 + tid < k) {                     // fixed-order combine over the block's rows
+                double s = 0.0, n = 0.0;
+                for (int r = 0; r < rpp; r++) { s += ssum[r * tpr + tid]; n += scnt[r * tpr + tid]; }
+                a.psum[(size_t)blockIdx.x * ncol + o * k + c0 + tid] = s;
+                a.pcnt[(size_t)blockIdx.x * ncol + o * k + c0 + tid] = n;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// reduce the per-block partials of column cidx in fixed order (whole block cooperates)
+__device__ __forceinline__ void reduce_partials(const StatArgs &a, int cidx, int npart, double *ssum, double *scnt,
+                                                double *osum, double *ocnt) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int ncol = a.n_orders * a.k;
+    double s = 0.0, n = 0.0;
+    for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
+    ssum[tid] = s; scnt[tid] = n;
+    __syncthreads();
+    for (int off = T / 2; off > 0; off >>= 1) {
+        if (tid < off) { ssum[tid] += ssum[tid + off]; scnt[tid] += scnt[tid + off]; }
+        __syncthreads();
+    }
+    *osum = ssum[0]; *ocnt = scnt[0];
+    __syncthreads();
+}
+
+// band pass as its own streaming launch; the LAST block to finish reduces the partials and publishes this
+// rank's statbox (to every rank when sharded)
+__global__ void __launch_bounds__(PL_THREADS, 4) psgd_stats_kernel(const StatArgs a) {
+    __shared__ double ssum[PL_THREADS], scnt[PL_THREADS];
+    __shared__ int s_last;
+    stats_pass(a, ssum, scnt, true);
+    const int ncol = a.n_orders * a.k;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.band_n + ncol, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // column totals: thread = (column, slice); slices added in fixed order -> deterministic
+    __shared__ int s_nb[PL_THREADS];
+    const int T = blockDim.x, npart = gridDim.x;
+    for (int c0 = 0; c0 < ncol; c0 += T) {
+        const int tprA = (ncol - c0 < T) ? ncol - c0 : T;
+        const int slices = T / tprA;
+        const int col = c0 + (int)threadIdx.x % tprA, sl = (int)threadIdx.x / tprA;
+        double s = 0.0, n = 0.0;
+        if (sl < slices) {
+            int b = sl;
+            for (; b + 3 * slices < npart; b += 4 * slices) {
+                const double s0 = __ldcg(a.psum + (size_t)b * ncol + col), s1 = __ldcg(a.psum + (size_t)(b + slices) * ncol + col);
+                const double s2 = __ldcg(a.psum + (size_t)(b + 2 * slices) * ncol + col), s3 = __ldcg(a.psum + (size_t)(b + 3 * slices) * ncol + col);
+                const double n0 = __ldcg(a.pcnt + (size_t)b * ncol + col), n1 = __ldcg(a.pcnt + (size_t)(b + slices) * ncol + col);
+                const double n2 = __ldcg(a.pcnt + (size_t)(b + 2 * slices) * ncol + col), n3 = __ldcg(a.pcnt + (size_t)(b + 3 * slices) * ncol + col);
+                s += s0; s += s1; s += s2; s += s3;
+                n += n0; n += n1; n += n2; n += n3;
+            }
+            for (; b < npart; b += slices) { s += __ldcg(a.psum + (size_t)b * ncol + col); n += __ldcg(a.pcnt + (size_t)b * ncol + col); }
+        }
+        ssum[threadIdx.x] = s; scnt[threadIdx.x] = n;
+        __syncthreads();
+        if ((int)threadIdx.x < tprA) {
+            double ts = 0.0, tn = 0.0;
+            for (int q = 0; q < slices; q++) { ts += ssum[q * tprA + threadIdx.x]; tn += scnt[q * tprA + threadIdx.x]; }
+            const int cidx = c0 + threadIdx.x;
+            const int nb = *reinterpret_cast<volatile int *>(a.band_n + cidx);
+            s_nb[threadIdx.x] = nb < BAND_CAP ? nb : BAND_CAP;
+            for (int r = 0; r < a.world; r++) {
+                double *box = a.statbox[r];
+                box[cidx] = ts; box[ncol + cidx] = tn; box[2 * ncol + cidx] = (double)nb;
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < tprA * BAND_CAP; idx += T) {        // the band's values
+            const int cl = idx / BAND_CAP, q = idx % BAND_CAP;
+            if (q < s_nb[cl]) {
+                const double v = __ldcg(a.band + (size_t)(c0 + cl) * BAND_CAP + q);
+                for (int r = 0; r < a.world; r++) a.statbox[r][3 * (size_t)ncol + (size_t)(c0 + cl) * BAND_CAP + q] = v;
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q <= ncol; q += blockDim.x) a.band_n[q] = 0;     // counters + ticket for the next launch
+}
+
+struct SolveArgs {
+    StatArgs st;                         // generic passes reuse the statistics pass (st.tau = tau)
+    double Cn;                           // frame scale after the update: T[c] += Cn * tau[c]
+    double *thr;                         // [ncol] raw-space thresholds (updated)
+    double *tau;                         // [ncol] scratch: new thresholds in value units
+    double *colres;                      // [2*ncol] reduced (sum, cnt) of a generic pass
+    int *fail;                           // [2] (zeroed before the launch): a column could not use its band / overflow
+    const double *statbox_all;           // local statboxes of all ranks [world][statbox_doubles]
+    double *xbuf[SP_MAX_RANKS];          // every rank's exchange buffer region of THIS rank [2][2*ncol] (generic passes)
+    const double *xbuf_local;            // local exchange buffers of all ranks [world][2][2*ncol]
+    XArgs x;                             // channel of the generic-pass exchanges (seq = first free sequence number)
+    unsigned long long *seq_out;         // device counter: sequence numbers consumed (host adds a bound instead)
+    int max_iter;
+};
+
+constexpr int SOLVE_THREADS = 512;
+
+__global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double ssum[SOLVE_THREADS], scnt[SOLVE_THREADS];
+    __shared__ double sband[BAND_TOTAL], spref[BAND_TOTAL];
+    __shared__ int s_flag;
+    const StatArgs &st = a.st;
+    const int tid = threadIdx.x, T = SOLVE_THREADS, nblk = gridDim.x;
+    const int ncol = st.n_orders * st.k, world = st.world;
+    const size_t boxlen = statbox_doubles(ncol);
+    const double bdelta = st.state[4] > 0.0 ? st.state[4] : BAND_DELTA;
+    const bool band_on = st.state[0] > 0.0 && st.strength > 0.0;
+    // ---- band path: every column's fixed point from (statistics above the band) + (the band's values)
+    if (!band_on) {
+        if (blockIdx.x == 0 && tid == 0) a.fail[0] = 1;
+    } else {
+        for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
+            double sumA = 0.0, cntA = 0.0;
+            int nbv = 0;
+            bool ok = st.state[8 + cidx] > 0.0;
+            for (int r = 0; r < world; r++) {                    // rank order: identical on every rank
+                const double *box = a.statbox_all + (size_t)r * boxlen;
+                sumA += box[cidx]; cntA += box[ncol + cidx];
+                const int nb = (int)box[2 * ncol + cidx];
+                if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = 1; }
+                nbv += nb < BAND_CAP ? nb : BAND_CAP;
+            }
+            if (nbv > BAND_TOTAL) { ok = false; if (tid == 0) a.fail[1] = 1; }
+            if (ok) {
+                const double tau_pred = predict_tau(st.state, ncol, cidx, st.strength);
+                const double b_hi = tau_pred * (1.0 + bdelta), b_lo = tau_pred * (1.0 - bdelta);
+                int np2 = 1;
+                while (np2 < nbv) np2 <<= 1;
+                for (int q = tid; q < np2; q += T) sband[q] = -1.0;
+                __syncthreads();
+                int at = 0;
+                for (int r = 0; r < world; r++) {
+                    const double *box = a.statbox_all + (size_t)r * boxlen;
+                    const int nb = (int)box[2 * ncol + cidx];
+                    for (int q = tid; q < nb; q += T) sband[at + q] = box[3 * (size_t)ncol + (size_t)cidx * BAND_CAP + q];
+                    at += nb;
+                }
+                __syncthreads();
+                for (int kk = 2; kk <= np2; kk <<= 1)               // bitonic sort, descending
+                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                        for (int q = tid; q < np2; q += T) {
+                            const int x = q ^ jj;
+                            if (x > q) {
+                                const double va = sband[q], vb = sband[x];
+                                const bool desc = (q & kk) == 0;
+                                if (desc ? (va < vb) : (va > vb)) { sband[q] = vb; sband[x] = va; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                {                                                    // inclusive prefix sums, fixed order
+                    const int per = (np2 + T - 1) / T;
+                    const int q0 = tid * per, q1 = min(np2, q0 + per);
+                    double acc = 0.0;
+                    for (int q = q0; q < q1; q++) acc += (q < nbv) ? sband[q] : 0.0;
+                    ssum[tid] = acc;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double run = 0.0;
+                        for (int b = 0; b < T; b++) { const double v = ssum[b]; ssum[b] = run; run += v; }
+                    }
+                    __syncthreads();
+                    acc = ssum[tid];
+                    for (int q = q0; q < q1; q++) { acc += (q < nbv) ? sband[q] : 0.0; spref[q] = acc; }
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    double tau = b_hi;
+                    int m_prev = -1;
+                    bool good = false;
+                    for (int it = 0; it < 200; it++) {
+                        int lo_i = 0, hi_i = nbv;                      // m = #{band > tau}
+                        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (sband[mid] > tau) lo_i = mid + 1; else hi_i = mid; }
+                        const int m = lo_i;
+                        const double sum = m > 0 ? sumA + spref[m - 1] : sumA;
+                        const double cnt = cntA + (double)m;
+                        const double tnew = 2.0 * st.strength * sum / (1.0 + 2.0 * st.strength * cnt);
+                        if (!(tnew > b_lo) || tnew > b_hi) break;
+                        if (m == m_prev) { a.tau[cidx] = tnew; good = true; break; }
+                        m_prev = m;
+                        tau = tnew;
+                    }
+                    s_flag = good ? 1 : 0;
+                }
+                __syncthreads();
+                ok = s_flag != 0;
+                __syncthreads();
+            }
+            if (!ok && tid == 0) a.fail[0] = 1;
+        }
+    }
+    __threadfence();
+    grid.sync();
+    const bool fb = *reinterpret_cast<volatile int *>(a.fail) != 0;
+    const bool over = *reinterpret_cast<volatile int *>(a.fail + 1) != 0;
+    if (!fb) {
+        if (blockIdx.x == 0) {
+            for (int c = tid; c < ncol; c += T) {
+                st.state[8 + ncol + c] = st.state[8 + c];
+                st.state[8 + c] = a.tau[c];
+                a.thr[c] = a.thr[c] + a.Cn * a.tau[c];
+            }
+            if (tid == 0) { st.state[0] = st.strength; st.state[1] += 1.0; st.state[2] += 1.0; }
+        }
+        return;
+    }
+    // ---- generic path: Michelot iteration from tau = 0 with one read-only pass per step; the active set
+    //      {v > tau} only shrinks and tau rises monotonically to the fixed point the reference finds
+    for (int c = blockIdx.x * T + tid; c < ncol; c += nblk * T) a.tau[c] = 0.0;
+    __threadfence();
+    grid.sync();
+    StatArgs sp = st;
+    sp.tau = a.tau;
+    double prev_total = -1.0;
+    XArgs x = a.x;
+    for (int it = 0; it < a.max_iter; it++) {
+        stats_pass(sp, ssum, scnt, false);
+        __threadfence();
+        grid.sync();
+        for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
+            double s, n;
+            reduce_partials(sp, cidx, nblk, ssum, scnt, &s, &n);
+            if (tid == 0) { a.colres[cidx] = s; a.colres[ncol + cidx] = n; }
+        }
+        __threadfence();
+        grid.sync();
+        if (world > 1) {                                            // sum over the ranks through peer memory
+            const int par = it & 1;
+            if (blockIdx.x == 0) {
+                for (int r = 0; r < world; r++)
+                    for (int q = tid; q < 2 * ncol; q += T) a.xbuf[r][(size_t)par * 2 * ncol + q] = a.colres[q];
+                __threadfence_system();
+                __syncthreads();
+                if (tid < world) { x_signal(x, tid); x_wait(x, tid); }
+                __syncthreads();
+            }
+            x.seq += 1;
+            grid.sync();
+        }
+        // every block derives the same new thresholds and the same convergence decision
+        double total = 0.0;
+        for (int c = tid; c < ncol; c += T) {
+            double s = 0.0, n = 0.0;
+            if (world > 1) {
+                for (int r = 0; r < world; r++) {
+                    const double *xb = a.xbuf_local + ((size_t)r * 2 + (it & 1)) * 2 * ncol;
+                    s += __ldcg(xb + c); n += __ldcg(xb + ncol + c);
+                }
+            } else { s = a.colres[c]; n = a.colres[ncol + c]; }
+            total += n;
+            if (blockIdx.x == 0) a.tau[c] = 2.0 * st.strength * s / (1.0 + 2.0 * st.strength * n);   // = 2*strength*S (utils.py:69-70)
+        }
+        ssum[tid] = total;
+        __syncthreads();
+        for (int off = T / 2; off > 0; off >>= 1) { if (tid < off) ssum[tid] += ssum[tid + off]; __syncthreads(); }
+        total = ssum[0];
+        __syncthreads();
+        __threadfence();
+        grid.sync();
+        if (total == prev_total) break;                           // no column lost an element: fixed point
+        prev_total = total;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = tid; c < ncol; c += T) {
+            st.state[8 + ncol + c] = st.state[8 + c];
+            st.state[8 + c] = a.tau[c];
+            a.thr[c] = a.thr[c] + a.Cn * a.tau[c];
+        }
+        if (tid == 0) {
+            st.state[0] = st.strength; st.state[1] += 1.0; st.state[3] += 1.0;
+            if (band_on) {                                          // adapt the band's half-width
+                double nd = over ? bdelta * 0.5 : bdelta * 2.0;
+                if (nd < 0.002) nd = 0.002;
+                if (nd > 0.1) nd = 0.1;
+                st.state[4] = nd;
+            }
+        }
+    }
+}
+
+// l1: every column's threshold is `strength` (l1.py:50-51)
+__global__ void psgd_thr_advance_kernel(double *thr, int ncol, double add) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncol) thr[c] = thr[c] + add;
+}
+
+// P <- true values (soft_threshold(raw, T) / C), w likewise; thresholds back to 0: the stored matrix is
+// the model again
+__global__ void psgd_materialize_kernel(double *P, int n_orders, size_t d, int k, const double *thr, double invC,
+                                        double *w, double invCw, int fit_linear) {
+    const size_t n = (size_t)n_orders * d * k, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int o = (int)(e / (d * k));
+        P[e] = st_true(P[e], thr[o * k + (int)(e % k)], invC);
+    }
+    if (fit_linear)
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < d; e += stride) w[e] = w[e] * invCw;
+}
+__global__ void psgd_zero_kernel(double *p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
+}
+
+// fixed-order sum of the per-sample losses of positions [b0, b1) (single block; epoch end)
+__global__ void __launch_bounds__(1024) psgd_loss_sum_kernel(const double *sloss, long long b0, long long b1, double *out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (long long b = b0 + threadIdx.x; b < b1; b += 1024) acc += sloss[b];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = out[0] + sh[0];
+}
+
+int grid_for(long long groups, int G) {
+    const int gpb = PL_THREADS / G;
+    long long blocks = (groups + gpb - 1) / gpb;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+// ============================================================================================ host side
+struct PlanMb {                          // one minibatch of the plan, resolved on the host
+    long long e0, e1, u0, u1, c0, c1, s0, s1;
+    int b0, b1;
+};
+
+static inline PlanMb plan_mb(const sp_psgd_plan *pl, int m) {
+    PlanMb q;
+    q.e0 = pl->mb_eptr_host[m]; q.e1 = pl->mb_eptr_host[m + 1];
+    q.u0 = pl->mb_uptr_host[m]; q.u1 = pl->mb_uptr_host[m + 1];
+    q.c0 = pl->mb_cptr_host[m]; q.c1 = pl->mb_cptr_host[m + 1];
+    q.s0 = pl->mb_sptr_host[m]; q.s1 = pl->mb_sptr_host[m + 1];
+    q.b0 = m * pl->batch_local;
+    q.b1 = q.b0 + pl->batch_local < pl->n_local ? q.b0 + pl->batch_local : pl->n_local;
+    return q;
+}
+
+template <int DEG, int NORD, int G, int KCH>
+static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const sp_psgd_plan *pl, const double *y,
+                            const int32_t *idx, const PlanMb &mb, const StepArgs &sa, cudaStream_t st) {
+    const bool sharded = cx->world > 1;
+    RowsArgs ra;
+    ra.k = cx->k; ra.d = cx->d_rows;
+    ra.indptr = ds->csr_indptr;
+    ra.colidx = sharded ? pl->csr_slot : ds->csr_indices;
+    ra.data = ds->csr_data; ra.y = y;
+    ra.Psrc = sharded ? cx->stage : cx->P; ra.wsrc = sharded ? cx->stage_w : cx->w;
+    ra.lams = cx->lams; ra.thr = cx->thr;
+    ra.invC = sa.invC; ra.invCw = sa.invCw;
+    ra.loss = cx->loss; ra.fit_linear = cx->fit_linear;
+    ra.idx = idx; ra.b0 = mb.b0; ra.b1 = mb.b1;
+    ra.bufA = cx->bufA; ra.bufdL = cx->bufdL; ra.sloss = cx->sample_loss;
+    long long groups = mb.b1 - mb.b0;
+    int blocks = grid_for(groups, G);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sp_prof_begin(SP_PROF_PSGD_GRAD, st);
+    if (sharded) psgd_rows_kernel<DEG, NORD, G, KCH, true><<<blocks, PL_THREADS, 0, st>>>(ra);
+    else psgd_rows_kernel<DEG, NORD, G, KCH, false><<<blocks, PL_THREADS, 0, st>>>(ra);
+    sp_prof_end(st);
+    SP_LAUNCH_CHECK("psgd_rows_kernel");
+
+    ColsArgs ca;
+    ca.k = cx->k; ca.d = cx->d_rows;
+    ca.e_pos = pl->e_pos + mb.e0; ca.e_x = pl->e_x + mb.e0;
+    ca.n_entries = mb.e1 - mb.e0;
+    ca.n_chunks = (int)(mb.c1 - mb.c0);
+    ca.u_feat = pl->u_feat; ca.u_ptr = pl->u_ptr;
+    ca.e_base = mb.e0; ca.u_base = mb.u0;
+    ca.chunk_u0 = pl->chunk_u0 + mb.c0;
+    ca.split_u = pl->split_u + mb.s0;
+    ca.n_split = (int)(mb.s1 - mb.s0);
+    ca.bufA = cx->bufA; ca.bufdL = cx->bufdL;
+    ca.lams = cx->lams; ca.thr = cx->thr;
+    ca.P = cx->P; ca.w = cx->w;
+    ca.stage = cx->stage; ca.stage_w = cx->stage_w;
+    ca.part_g = cx->part_g; ca.part_w = cx->part_w;
+    ca.s = sa;
+    ca.world = cx->world; ca.rank = cx->rank;
+    for (int r = 0; r <= SP_MAX_RANKS; r++) ca.owner_start[r] = 0;
+    for (int r = 0; r < SP_MAX_RANKS; r++) { ca.inbox_g[r] = nullptr; ca.inbox_w[r] = nullptr; }
+    if (sharded) {
+        const int m = mb.b0 / pl->batch_local;
+        for (int r = 0; r <= cx->world; r++) ca.owner_start[r] = pl->mb_owner_start_host[(size_t)m * (cx->world + 1) + r];
+        for (int r = 0; r < cx->world; r++) { ca.inbox_g[r] = cx->peer_inbox_g[r]; ca.inbox_w[r] = cx->peer_inbox_w[r]; }
+    }
+    if (ca.n_chunks > 0) {
+        sp_prof_begin(SP_PROF_PSGD_STEP, st);
+        const int cb = grid_for(ca.n_chunks, G);
+        if (sharded) psgd_cols_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<cb, PL_THREADS, 0, st>>>(ca);
+        else psgd_cols_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<cb, PL_THREADS, 0, st>>>(ca);
+        SP_LAUNCH_CHECK("psgd_cols_kernel");
+        if (ca.n_split > 0) {
+            const int sb = grid_for(ca.n_split, G);
+            if (sharded) psgd_split_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
+            else psgd_split_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
+            SP_LAUNCH_CHECK("psgd_split_kernel");
+        }
+        sp_prof_end(st);
+    }
+    return SP_OK;
+}
+
+template <int NORD, int G, int KCH>
+static int launch_owner(const sp_psgd_ctx *cx, const sp_psgd_plan *pl, int m, const StepArgs &sa, cudaStream_t st) {
+    OwnerArgs oa;
+    const long long o0 = pl->mb_optr_host[m], o1 = pl->mb_optr_host[m + 1];
+    oa.k = cx->k; oa.d_own = cx->d_rows; oa.world = cx->world; oa.n_rows = (int)(o1 - o0);
+    oa.own_q = pl->own_q + o0;
+    oa.own_src = pl->own_src + o0 * cx->world;
+    for (int r = 0; r < SP_MAX_RANKS; r++) { oa.inbox_g[r] = nullptr; oa.inbox_w[r] = nullptr; }
+    for (int r = 0; r < cx->world; r++) { oa.inbox_g[r] = cx->inbox_g + (size_t)r * cx->inbox_cap * cx->n_orders * cx->k; oa.inbox_w[r] = cx->inbox_w + (size_t)r * cx->inbox_cap; }
+    oa.thr = cx->thr; oa.P = cx->P; oa.w = cx->w; oa.s = sa;
+    if (oa.n_rows > 0) {
+        psgd_owner_kernel<NORD, G, KCH><<<grid_for(oa.n_rows, G), PL_THREADS, 0, st>>>(oa);
+        SP_LAUNCH_CHECK("psgd_owner_kernel");
+    }
+    return SP_OK;
+}
+
+static int xbarrier(const sp_psgd_ctx *cx, int chan, unsigned long long seq, cudaStream_t st) {
+    XArgs x;
+    x.world = cx->world; x.rank = cx->rank; x.chan = chan; x.seq = seq;
+    for (int r = 0; r < SP_MAX_RANKS; r++) x.peer_flags[r] = r < cx->world ? cx->peer_flags[r] : nullptr;
+    x.my_flags = cx->peer_flags[cx->rank];
+    x.err = cx->err;
+    psgd_xbarrier_kernel<<<1, 32, 0, st>>>(x);
+    SP_LAUNCH_CHECK("psgd_xbarrier_kernel");
+    return SP_OK;
+}
+
+// layout of cx->work (doubles)
+struct WorkLayout {
+    size_t psum, pcnt, colres, tau, state, band, statbox, xbuf, ints, total;
+};
+static WorkLayout work_layout(size_t ncol, int world) {
+    WorkLayout L;
+    size_t at = 0;
+    L.psum = at; at += (size_t)STAT_PART_MAX * ncol;
+    L.pcnt = at; at += (size_t)STAT_PART_MAX * ncol;
+    L.colres = at; at += 2 * ncol;
+    L.tau = at; at += ncol;
+    L.state = at; at += 8 + 2 * ncol;
+    L.band = at; at += ncol * (size_t)BAND_CAP;
+    L.ints = at; at += (ncol + 8) / 2 + 4;            // band counters + ticket | fail[2]
+    L.total = at;
+    (void)world;
+    return L;
+}
+
+extern "C" size_t sp_psgd_plan_work_doubles(int n_orders, int k) {
+    return work_layout((size_t)n_orders * k, 1).total + 64;
+}
+// peer-visible buffer of one rank (doubles): statboxes of all ranks | exchange buffers of all ranks
+extern "C" size_t sp_psgd_plan_xwork_doubles(int n_orders, int k, int world) {
+    const size_t ncol = (size_t)n_orders * k;
+    return (size_t)world * statbox_doubles(ncol) + (size_t)world * 2 * 2 * ncol + 64;
+}
+
+static int solve_grid(int *nblk_out) {
+    int dev = 0, sms = 0, occ = 0;
+    SP_CUDA(cudaGetDevice(&dev));
+    SP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psgd_solve_kernel, SOLVE_THREADS, 0));
+    if (occ < 1) { sp_set_error("psgd_solve_kernel does not fit on an SM"); return SP_ERR_CUDA; }
+    *nblk_out = sms;                       // one block per SM: leaves room when two ranks share a device (tests)
+    return SP_OK;
+}
+
+static int ctx_check(const sp_psgd_ctx *cx) {
+    if (!cx || !cx->P || !cx->w || !cx->lams || !cx->thr || !cx->bufA || !cx->bufdL || !cx->sample_loss || !cx->work ||
+        !cx->part_g || !cx->part_w || cx->k <= 0 || cx->n_orders <= 0 || cx->world < 1 || cx->world > SP_MAX_RANKS ||
+        cx->rank < 0 || cx->rank >= cx->world) {
+        sp_set_error("sp_psgd_plan_*: invalid context");
+        return SP_ERR_INVALID;
+    }
+    if (cx->reg != SP_REG_L1 && cx->reg != SP_REG_SQL12) {
+        sp_set_error("the planned psgd path handles l1 and squaredl12 (use sp_psgd_epoch for l21 / squaredl21)");
+        return SP_ERR_UNSUPPORTED;
+    }
+    if (cx->degree < 2 || cx->degree > SP_MAXDEG) {
+        sp_set_error("psgd degree %d is not supported by the CUDA backend (2..%d)", cx->degree, SP_MAXDEG);
+        return SP_ERR_UNSUPPORTED;
+    }
+    if (cx->n_orders != 1 && cx->n_orders != cx->degree - 1) {
+        sp_set_error("psgd: n_orders must be 1 or degree-1 (got %d)", cx->n_orders);
+        return SP_ERR_INVALID;
+    }
+    if (cx->k > 128) { sp_set_error("psgd: n_components=%d > 128 is not supported by the CUDA backend", cx->k); return SP_ERR_UNSUPPORTED; }
+    if (cx->world > 1 && (!cx->stage || !cx->stage_w || !cx->inbox_g || !cx->inbox_w || !cx->err || !cx->xwork)) {
+        sp_set_error("sp_psgd_plan_*: sharded context without peer buffers");
+        return SP_ERR_INVALID;
+    }
+    return SP_OK;
+}
+
+extern "C" int sp_psgd_plan_begin(sp_psgd_ctx *cx, sp_stream stream) {
+    int rc = ctx_check(cx);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncol = (size_t)cx->n_orders * cx->k;
+    const WorkLayout L = work_layout(ncol, cx->world);
+    SP_CUDA(cudaMemsetAsync(cx->thr, 0, ncol * sizeof(double), st));
+    SP_CUDA(cudaMemsetAsync(cx->work + L.state, 0, (L.total - L.state) * sizeof(double), st));
+    cx->C = 1.0; cx->Cw = 1.0;
+    return SP_OK;
+}
+
+// Minibatches [m_begin, m_end) of one epoch = the body of psgd.psgd_epoch (psgd.py:150-198) for them.
+extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_psgd_plan *pl, const double *y,
+                                const int32_t *idx_samples, double alpha, double beta, double gamma, double eta0,
+                                int learning_rate, double power_t, int m_begin, int m_end, int64_t *it_io_host,
+                                sp_stream stream) {
+    int rc = ctx_check(cx);
+    if (rc) return rc;
+    if (!ds || !ds->csr_indptr || !pl || !y || !idx_samples || !it_io_host || m_begin < 0 || m_end > pl->n_minibatches ||
+        m_begin > m_end) {
+        sp_set_error("sp_psgd_plan_run: invalid argument");
+        return SP_ERR_INVALID;
+    }
+    if (pl->chunk != CH) { sp_set_error("sp_psgd_plan_run: plan built for chunk %d, library uses %d", pl->chunk, CH); return SP_ERR_INVALID; }
+    if (cx->world > 1 && (!pl->csr_slot || !pl->own_q || !pl->own_src || !pl->mb_owner_start_host || !pl->mb_optr_host)) {
+        sp_set_error("sp_psgd_plan_run: sharded run with a single-rank plan");
+        return SP_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = cx->k, nord = cx->n_orders;
+    const size_t ncol = (size_t)nord * k;
+    const WorkLayout L = work_layout(ncol, cx->world);
+    const bool sharded = cx->world > 1;
+    int solve_blocks = 0;
+    if (cx->reg == SP_REG_SQL12) { rc = solve_grid(&solve_blocks); if (rc) return rc; }
+    int64_t it = *it_io_host;
+    for (int m = m_begin; m < m_end; m++) {
+        const PlanMb mb = plan_mb(pl, m);
+        const long long b_glob = (long long)(mb.b1 - mb.b0) * cx->world;
+        double eta_P, eta_w;
+        rc = sp_get_eta(learning_rate, eta0, alpha, beta, power_t, it, &eta_P, &eta_w);     // psgd.py:178
+        if (rc) return rc;
+        StepArgs sa;
+        sa.cP = eta_P / (double)b_glob; sa.denP = 1.0 + eta_P * beta; sa.CnP = cx->C * sa.denP;
+        sa.cw = eta_w / (double)b_glob; sa.denw = 1.0 + eta_w * alpha; sa.Cnw = cx->fit_linear ? cx->Cw * sa.denw : cx->Cw;
+        sa.invC = 1.0 / cx->C; sa.invCw = 1.0 / cx->Cw;
+        sa.fit_linear = cx->fit_linear;
+        const double strength = gamma * eta_P / (1.0 + eta_P * beta);                     // psgd.py:122
+        if (sharded) {
+            PullArgs pa;
+            pa.k = k; pa.d_own = cx->d_rows; pa.world = cx->world; pa.n_cols = (int)(mb.u1 - mb.u0);
+            pa.u_feat = pl->u_feat + mb.u0;
+            for (int r = 0; r < SP_MAX_RANKS; r++) { pa.peer_P[r] = r < cx->world ? cx->peer_P[r] : nullptr; pa.peer_w[r] = r < cx->world ? cx->peer_w[r] : nullptr; }
+            pa.thr = cx->thr; pa.invC = sa.invC; pa.invCw = sa.invCw; pa.n_orders = nord; pa.fit_linear = cx->fit_linear;
+            pa.stage = cx->stage; pa.stage_w = cx->stage_w;
+            if (pa.n_cols > 0) {
+                long long blocks = ((long long)pa.n_cols * nord * k + PL_THREADS - 1) / PL_THREADS;
+                if (blocks > 148 * 16) blocks = 148 * 16;
+                psgd_pull_kernel<<<(int)blocks, PL_THREADS, 0, st>>>(pa);
+                SP_LAUNCH_CHECK("psgd_pull_kernel");
+            }
+        }
+#define SP_MB(D, N, GG, KC) rc = launch_minibatch<D, N, GG, KC>(cx, ds, pl, y, idx_samples, mb, sa, st)
+#define SP_MB_K(D, N)                                                                      \
+        if (k <= 16) SP_MB(D, N, 16, 1);                                                   \
+        else if (k <= 32) SP_MB(D, N, 32, 1);                                              \
+        else if (k <= 64) SP_MB(D, N, 32, 2);                                              \
+        else SP_MB(D, N, 32, 4)
+        const bool ex = nord > 1;
+        switch (cx->degree) {
+        case 2: SP_MB_K(2, 1); break;
+        case 3: if (ex) { SP_MB_K(3, 2); } else { SP_MB_K(3, 1); } break;
+        case 4: if (ex) { SP_MB_K(4, 3); } else { SP_MB_K(4, 1); } break;
+        default: if (ex) { SP_MB_K(5, 4); } else { SP_MB_K(5, 1); } break;
+        }
+#undef SP_MB_K
+#undef SP_MB
+        if (rc) return rc;
+        if (sharded) {
+            cx->seq += 1;
+            rc = xbarrier(cx, 0, cx->seq, st);                     // every rank's partial rows are in the inboxes
+            if (rc) return rc;
+#define SP_OW(N, GG, KC) rc = launch_owner<N, GG, KC>(cx, pl, m, sa, st)
+#define SP_OW_K(N)                                                                         \
+            if (k <= 16) SP_OW(N, 16, 1);                                                  \
+            else if (k <= 32) SP_OW(N, 32, 1);                                             \
+            else if (k <= 64) SP_OW(N, 32, 2);                                             \
+            else SP_OW(N, 32, 4)
+            switch (nord) {
+            case 1: SP_OW_K(1); break;
+            case 2: SP_OW_K(2); break;
+            case 3: SP_OW_K(3); break;
+            default: SP_OW_K(4); break;
+            }
+#undef SP_OW_K
+#undef SP_OW
+            if (rc) return rc;
+        }
+        cx->C = sa.CnP; cx->Cw = sa.Cnw;
+        const double invCn = 1.0 / cx->C;
+        if (cx->reg == SP_REG_L1) {
+            psgd_thr_advance_kernel<<<(int)((ncol + 127) / 128), 128, 0, st>>>(cx->thr, (int)ncol, cx->C * strength);
+            SP_LAUNCH_CHECK("psgd_thr_advance_kernel");
+            if (sharded) { cx->seq += 1; rc = xbarrier(cx, 0, cx->seq, st); if (rc) return rc; }   // owners' rows are final
+        } else {
+            StatArgs sg;
+            sg.P = cx->P; sg.n_orders = nord; sg.d = cx->d_rows; sg.k = k;
+            sg.invC = invCn; sg.strength = strength; sg.thr = cx->thr; sg.reg = cx->reg;
+            sg.psum = cx->work + L.psum; sg.pcnt = cx->work + L.pcnt;
+            sg.band = cx->work + L.band;
+            sg.band_n = reinterpret_cast<int *>(cx->work + L.ints);
+            sg.state = cx->work + L.state;
+            sg.tau = nullptr;
+            sg.world = cx->world; sg.rank = cx->rank;
+            const size_t boxlen = statbox_doubles(ncol);
+            for (int r = 0; r < SP_MAX_RANKS; r++) sg.statbox[r] = nullptr;
+            if (sharded) { for (int r = 0; r < cx->world; r++) sg.statbox[r] = cx->peer_xwork[r] + (size_t)cx->rank * boxlen; }
+            else sg.statbox[0] = cx->xwork;
+            sg.err = cx->err;
+            const int tpr = k < PL_THREADS ? k : PL_THREADS, rpp = PL_THREADS / tpr;
+            long long nblk = ((long long)cx->d_rows + rpp - 1) / rpp;
+            if (nblk > STAT_PART_MAX) nblk = STAT_PART_MAX;
+            if (nblk < 1) nblk = 1;
+            sp_prof_begin(SP_PROF_PROX, st);
+            psgd_stats_kernel<<<(int)nblk, PL_THREADS, 0, st>>>(sg);
+            SP_LAUNCH_CHECK("psgd_stats_kernel");
+            if (sharded) { cx->seq += 1; rc = xbarrier(cx, 0, cx->seq, st); if (rc) { sp_prof_end(st); return rc; } }
+            SolveArgs so;
+            so.st = sg;
+            so.Cn = cx->C; so.thr = cx->thr; so.tau = cx->work + L.tau; so.colres = cx->work + L.colres;
+            so.fail = reinterpret_cast<int *>(cx->work + L.ints) + ((ncol + 8) & ~1) ;
+            so.statbox_all = cx->xwork;
+            const size_t xoff = (size_t)cx->world * boxlen;
+            for (int r = 0; r < SP_MAX_RANKS; r++) so.xbuf[r] = nullptr;
+            if (sharded) for (int r = 0; r < cx->world; r++) so.xbuf[r] = cx->peer_xwork[r] + xoff + (size_t)cx->rank * 4 * ncol;
+            so.xbuf_local = cx->xwork + xoff;
+            so.x.world = cx->world; so.x.rank = cx->rank; so.x.chan = 1; so.x.seq = cx->seq_generic + 1;
+            for (int r = 0; r < SP_MAX_RANKS; r++) so.x.peer_flags[r] = (sharded && r < cx->world) ? cx->peer_flags[r] : nullptr;
+            so.x.my_flags = sharded ? cx->peer_flags[cx->rank] : nullptr;
+            so.x.err = cx->err;
+            so.seq_out = nullptr;
+            so.max_iter = 500;
+            cx->seq_generic += (unsigned long long)so.max_iter;     // sequence numbers reserved for this call's exchanges
+            SP_CUDA(cudaMemsetAsync(so.fail, 0, 2 * sizeof(int), st));
+            void *args[] = {(void *)&so};
+            cudaError_t e = cudaLaunchCooperativeKernel((void *)psgd_solve_kernel, dim3(solve_blocks), dim3(SOLVE_THREADS), args, 0, st);
+            sp_prof_end(st);
+            if (e != cudaSuccess) return sp_check_cuda(e, "psgd_solve_kernel launch");
+        }
+        it++;
+    }
+    *it_io_host = it;
+    return SP_OK;
+}
+
+// epoch end: *loss_sum += sum of the epoch's per-sample losses (fixed order); the raw matrix becomes the
+// model again (thresholds 0, scales 1) so that P / w can be read by anyone
+extern "C" int sp_psgd_plan_end(sp_psgd_ctx *cx, int n_local, double *loss_sum, int materialize, sp_stream stream) {
+    int rc = ctx_check(cx);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (loss_sum && n_local > 0) {
+        psgd_loss_sum_kernel<<<1, 1024, 0, st>>>(cx->sample_loss, 0, n_local, loss_sum);
+        SP_LAUNCH_CHECK("psgd_loss_sum_kernel");
+    }
+    if (materialize) {
+        const size_t n = (size_t)cx->n_orders * cx->d_rows * cx->k;
+        if (n > 0) {
+            size_t b = (n + 255) / 256;
+            if (b > 148 * 16) b = 148 * 16;
+            psgd_materialize_kernel<<<(int)b, 256, 0, st>>>(cx->P, cx->n_orders, (size_t)cx->d_rows, cx->k, cx->thr, 1.0 / cx->C,
+                                                          cx->w, 1.0 / cx->Cw, cx->fit_linear);
+            SP_LAUNCH_CHECK("psgd_materialize_kernel");
+        }
+        psgd_zero_kernel<<<1, 256, 0, st>>>(cx->thr, cx->n_orders * cx->k);
+        SP_LAUNCH_CHECK("psgd_zero_kernel");
+        cx->C = 1.0; cx->Cw = 1.0;
+        if (cx->world > 1) { cx->seq += 1; rc = xbarrier(cx, 0, cx->seq, st); if (rc) return rc; }
+    }
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------------ peer memory (CUDA IPC)
+extern "C" int sp_shm_alloc(size_t bytes, void **out) {
+    if (!out) { sp_set_error("sp_shm_alloc: null pointer"); return SP_ERR_INVALID; }
+    SP_CUDA(cudaMalloc(out, bytes ? bytes : 8));
+    SP_CUDA(cudaMemset(*out, 0, bytes ? bytes : 8));
+    return SP_OK;
+}
+extern "C" int sp_shm_free(void *p) { return sp_check_cuda(cudaFree(p), "cudaFree"); }
+extern "C" int sp_ipc_export(void *p, unsigned char *handle64) {
+    if (!p || !handle64) { sp_set_error("sp_ipc_export: null pointer"); return SP_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    SP_CUDA(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return SP_OK;
+}
+extern "C" int sp_ipc_open(const unsigned char *handle64, void **out) {
+    if (!handle64 || !out) { sp_set_error("sp_ipc_open: null pointer"); return SP_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SP_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SP_OK;
+}
+extern "C" int sp_ipc_close(void *p) { return sp_check_cuda(cudaIpcCloseMemHandle(p), "cudaIpcCloseMemHandle"); }
+extern "C" int sp_memcpy(void *dst, const void *src, size_t bytes, int kind, sp_stream stream) {
+    const cudaMemcpyKind kd = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    SP_CUDA(cudaMemcpyAsync(dst, src, bytes, kd, (cudaStream_t)stream));
+    if (kind == 1) SP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return SP_OK;
+}

@@ -1,0 +1,460 @@
+"""Host side of the planned psgd path (csrc/psgd_plan.cu): the "batch CSC" plan of a sample order and
+the context (model shard, scratch, peer pointers) a planned fit runs in.
+
+Reference semantics: psgd.psgd_epoch (optimizer/psgd.py:125-199) visits the samples in
+`indices_samples` order, cuts them into minibatches of batch_size and, per minibatch, adds every
+sample's gradient terms to the rows of grad_P its nonzeros touch.  The plan regroups the nonzeros of
+each minibatch by feature (samples ascending inside a feature: the reference's summation order), so
+that the CUDA side can sum a row's terms without atomics and update only the touched rows.  It depends
+on X, the sample order and the batch size only -- built once per fit (once per epoch with shuffle=True)
+by device sorts; PyTorch is the sort / allocator provider here, nothing else.
+
+Sharded over the ranks of a process group (one process per GPU): samples are sharded by rank (every
+rank holds n_local rows and contributes batch_local of them to each minibatch), P is sharded by rows
+(feature j lives on rank j % world, local row j // world) in peer-visible memory (CUDA IPC), and a
+minibatch's columns are ordered by (owner, feature) so that the partial gradient rows for one owner
+are contiguous.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CHUNK = 64            # SP_PSGD_CHUNK
+MAX_RANKS = 8         # SP_MAX_RANKS
+CHANNELS = 2          # SP_PSGD_CHANNELS
+_GROUP_ENTRIES = 48_000_000     # nonzeros sorted at a time while building (bounds the temporaries)
+
+
+def _comm_device(group):
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def all_gather_var(t, group):
+    """all_gather of 1-D tensors of different lengths; returns the list on t's device."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cdev = _comm_device(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=cdev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(v.item()) for v in ns]
+    cap = max(max(ns), 1)
+    buf = torch.zeros(cap, dtype=t.dtype, device=cdev)
+    buf[: t.numel()] = t.to(cdev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return [o[:m].to(t.device) for o, m in zip(outs, ns)]
+
+
+class PsgdPlan:
+    """sp_psgd_plan for samples idx[0:n_local] of a device CSR matrix."""
+
+    def __init__(self, csr, idx, n_features, batch_local, world=1, rank=0, group=None, group_entries=_GROUP_ENTRIES,
+                 defer_owner_tables=False):
+        indptr, indices, data = csr
+        dev = data.device
+        self.device = dev
+        self.world, self.rank = int(world), int(rank)
+        self.n_local = int(idx.numel())
+        self.batch_local = max(1, int(batch_local))
+        self.n_features = int(n_features)
+        bL, G = self.batch_local, self.world
+        M = (self.n_local + bL - 1) // bL
+        self.n_minibatches = M
+        dq = (self.n_features + G - 1) // G
+        self.d_rows = dq
+        Dkey = G * dq
+        nnz_total = int(data.numel())
+        i64 = torch.int64
+        # per-minibatch entry counts decide the build groups
+        rows_all = idx.to(i64)
+        cnt_all = (indptr[rows_all + 1] - indptr[rows_all]).to(i64)
+        csum = torch.zeros(self.n_local + 1, dtype=i64, device=dev)
+        csum[1:] = torch.cumsum(cnt_all, 0)
+        mb_bounds = torch.arange(0, M + 1, dtype=i64, device=dev) * bL
+        mb_bounds[-1] = self.n_local
+        mb_eptr = csum[mb_bounds].cpu().numpy().astype(np.int64)             # [M+1]
+        E = int(mb_eptr[-1])
+        self.e_pos = torch.empty(E, dtype=torch.int32, device=dev)
+        self.e_x = torch.empty(E, dtype=torch.float64, device=dev)
+        self.csr_slot = torch.zeros(nnz_total, dtype=torch.int32, device=dev) if G > 1 else None
+        u_feat, u_ptr, chunk_u0, split_u = [], [], [], []
+        mb_ucnt, mb_ccnt, mb_scnt, owner_cnt = [], [], [], []
+        u_off = 0
+        m0 = 0
+        while m0 < M:
+            m1 = m0 + 1
+            while m1 < M and mb_eptr[m1 + 1] - mb_eptr[m0] <= group_entries:
+                m1 += 1
+            e0, e1 = int(mb_eptr[m0]), int(mb_eptr[m1])
+            b0, b1 = m0 * bL, min(m1 * bL, self.n_local)
+            tot = e1 - e0
+            Mg = m1 - m0
+            if tot == 0:
+                mb_ucnt.append(np.zeros(Mg, np.int64)); mb_ccnt.append(np.zeros(Mg, np.int64)); mb_scnt.append(np.zeros(Mg, np.int64))
+                owner_cnt.append(np.zeros((Mg, G), np.int64))
+                m0 = m1
+                continue
+            cnt = cnt_all[b0:b1]
+            pos = torch.arange(b1 - b0, dtype=i64, device=dev)
+            pos_rep = torch.repeat_interleave(pos, cnt, output_size=tot)
+            first = csum[b0:b1] - e0
+            off = torch.arange(tot, dtype=i64, device=dev) - first[pos_rep]
+            src = indptr[rows_all[b0:b1]].to(i64)[pos_rep] + off                 # CSR entry of every plan entry
+            del off, first
+            feat = indices[src].to(i64)
+            mb = pos_rep // bL
+            lpos = (pos_rep - mb * bL).to(torch.int32)
+            del pos_rep
+            key = mb * Dkey + (feat % G) * dq + feat // G
+            del feat
+            key, order = torch.sort(key, stable=True)                           # samples stay ascending inside a column
+            newcol = torch.ones(tot, dtype=torch.bool, device=dev)
+            newcol[1:] = key[1:] != key[:-1]
+            lp = lpos[order]
+            self.e_pos[e0:e1] = torch.where(newcol, lp | torch.tensor(-2 ** 31, dtype=torch.int32, device=dev), lp)
+            del lp
+            self.e_x[e0:e1] = data[src[order]]
+            del lpos
+            ucol = torch.cumsum(newcol.to(i64), 0) - 1                          # group-relative column of every entry
+            ustart = torch.nonzero(newcol).squeeze(1)                           # group-relative first entry of every column
+            ukey = key[ustart]
+            umb = ukey // Dkey
+            upf = ukey - umb * Dkey
+            uowner = upf // dq
+            u_feat.append(((upf - uowner * dq) * G + uowner).to(torch.int32))
+            u_ptr.append(ustart + e0)
+            nU = int(ustart.numel())
+            ecnt = torch.from_numpy(np.diff(mb_eptr[m0:m1 + 1])).to(dev)
+            eptr_rel = torch.zeros(Mg + 1, dtype=i64, device=dev)
+            eptr_rel[1:] = torch.cumsum(ecnt, 0)
+            ucnt = torch.bincount(umb, minlength=Mg)
+            uptr_rel = torch.zeros(Mg + 1, dtype=i64, device=dev)
+            uptr_rel[1:] = torch.cumsum(ucnt, 0)
+            mb_ucnt.append(ucnt.cpu().numpy())
+            if G > 1:
+                mb_sorted = key // Dkey
+                self.csr_slot[src[order]] = (ucol - uptr_rel[mb_sorted]).to(torch.int32)
+                del mb_sorted
+                owner_cnt.append(torch.bincount(umb * G + uowner, minlength=Mg * G).reshape(Mg, G).cpu().numpy())
+            del src, order, key
+            # chunks
+            nch = (ecnt + CHUNK - 1) // CHUNK
+            mb_ccnt.append(nch.cpu().numpy())
+            ntc = int(nch.sum())
+            cptr_rel = torch.zeros(Mg + 1, dtype=i64, device=dev)
+            cptr_rel[1:] = torch.cumsum(nch, 0)
+            cmb = torch.repeat_interleave(torch.arange(Mg, dtype=i64, device=dev), nch, output_size=ntc)
+            c_in = torch.arange(ntc, dtype=i64, device=dev) - cptr_rel[cmb]
+            chunk_u0.append((ucol[eptr_rel[cmb] + c_in * CHUNK] + u_off).to(torch.int32))
+            del ucol
+            # columns spanning more than one chunk
+            uend = torch.empty(nU, dtype=i64, device=dev)
+            uend[:-1] = ustart[1:]
+            uend[-1] = tot
+            s_rel = ustart - eptr_rel[umb]
+            e_rel = uend - eptr_rel[umb]
+            split = (s_rel // CHUNK) != ((e_rel - 1) // CHUNK)
+            sp_idx = torch.nonzero(split).squeeze(1)
+            split_u.append((sp_idx + u_off).to(torch.int32))
+            mb_scnt.append(torch.bincount(umb[sp_idx], minlength=Mg).cpu().numpy())
+            u_off += nU
+            m0 = m1
+        cat = lambda xs, dt: (torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev))   # noqa: E731
+        self.u_feat = cat(u_feat, torch.int32)
+        self.u_ptr = torch.cat([cat(u_ptr, i64), torch.tensor([E], dtype=i64, device=dev)])
+        self.chunk_u0 = cat(chunk_u0, torch.int32)
+        self.split_u = cat(split_u, torch.int32)
+        acc = lambda parts: np.concatenate([[0], np.cumsum(np.concatenate(parts) if parts else np.zeros(0, np.int64))]).astype(np.int64)  # noqa: E731
+        self.mb_eptr = mb_eptr
+        self.mb_uptr = acc(mb_ucnt)
+        self.mb_cptr = acc(mb_ccnt)
+        self.mb_sptr = acc(mb_scnt)
+        self.max_chunks = int(np.max(np.diff(self.mb_cptr))) if M else 0
+        self.max_cols = int(np.max(np.diff(self.mb_uptr))) if M else 0
+        self.n_entries = E
+        self.n_cols = int(self.mb_uptr[-1])
+        # ---- sharded: owner-side tables
+        self.mb_owner_start = self.mb_optr = None
+        self.own_q = self.own_src = None
+        self.inbox_cap = 0
+        if G > 1:
+            oc = np.concatenate(owner_cnt, 0) if owner_cnt else np.zeros((0, G), np.int64)       # [M, G]
+            ostart = np.zeros((M, G + 1), dtype=np.int64)
+            ostart[:, 1:] = np.cumsum(oc, 1)
+            self.mb_owner_start = np.ascontiguousarray(ostart.astype(np.int32))
+            if defer_owner_tables:                      # (tests: several ranks' plans built in one process)
+                return
+            self.finish_owner_tables(*self.gather_column_lists(group))
+            return
+        self._fill_struct()
+
+    def column_lists(self):
+        """What the owners need from this rank: its columns, per-minibatch column offsets and owner offsets."""
+        dev = self.device
+        return (torch.tensor([self.n_local, self.batch_local], dtype=torch.int64, device=dev), self.u_feat,
+                torch.from_numpy(self.mb_uptr).to(dev),
+                torch.from_numpy(self.mb_owner_start.astype(np.int64).reshape(-1)).to(dev))
+
+    def gather_column_lists(self, group):
+        mine = self.column_lists()
+        return tuple(all_gather_var(t, group) for t in mine)
+
+    def finish_owner_tables(self, n_all, feats, uptrs, ostarts):
+        """Rows of this rank touched by each GLOBAL minibatch and, per source rank, where that rank's partial
+        row sits in its inbox region (the source's columns owned by this rank, in feature order).  Inputs:
+        every rank's column_lists()."""
+        dev, G, me, M = self.device, self.world, self.rank, self.n_minibatches
+        dq = self.d_rows
+        i64 = torch.int64
+        if any(int(t[0]) != self.n_local or int(t[1]) != self.batch_local for t in n_all):
+            raise ValueError("sharded psgd needs equal shards: (n_local, batch_local) per rank = "
+                             + str([(int(t[0]), int(t[1])) for t in n_all]))
+        keys, srcs, ats = [], [], []
+        cap = 0
+        for r in range(G):
+            os_r = ostarts[r].reshape(M, G + 1)
+            lo = uptrs[r][:-1] + os_r[:, me]                   # [M] absolute first column of rank r owned by me
+            n = os_r[:, me + 1] - os_r[:, me]
+            tot = int(n.sum())
+            cap = max(cap, int(n.max()) if M else 0)
+            if tot == 0:
+                continue
+            mbi = torch.repeat_interleave(torch.arange(M, dtype=i64, device=dev), n, output_size=tot)
+            first = torch.cumsum(n, 0) - n
+            at = torch.arange(tot, dtype=i64, device=dev) - first[mbi]
+            f = feats[r][lo[mbi] + at].to(i64)
+            keys.append(mbi * dq + f // G)
+            srcs.append(torch.full((tot,), r, dtype=i64, device=dev))
+            ats.append(at)
+        # most columns any rank sends to any owner in one minibatch (identical on every rank: same layout)
+        capg = 0
+        for r in range(G):
+            os_r = ostarts[r].reshape(M, G + 1)
+            if M:
+                capg = max(capg, int((os_r[:, 1:] - os_r[:, :-1]).max()))
+        self.inbox_cap = max(capg, cap, 1)
+        if keys:
+            key = torch.cat(keys); src = torch.cat(srcs); at = torch.cat(ats)
+            uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+            own_src = torch.full((uniq.numel(), G), -1, dtype=torch.int32, device=dev)
+            own_src[inv, src] = at.to(torch.int32)
+            mbo = uniq // dq
+            self.own_q = (uniq - mbo * dq).to(torch.int32)
+            self.own_src = own_src.contiguous()
+            ocnt = torch.bincount(mbo, minlength=M).cpu().numpy()
+        else:
+            self.own_q = torch.zeros(0, dtype=torch.int32, device=dev)
+            self.own_src = torch.zeros((0, G), dtype=torch.int32, device=dev)
+            ocnt = np.zeros(M, np.int64)
+        self.mb_optr = np.concatenate([[0], np.cumsum(ocnt)]).astype(np.int64)
+        self._fill_struct()
+
+    def _fill_struct(self):
+        s = _lib.SpPsgdPlan()
+        s.n_minibatches, s.batch_local, s.n_local, s.chunk = self.n_minibatches, self.batch_local, self.n_local, CHUNK
+        hp = lambda a: a.ctypes.data                         # noqa: E731  (host arrays are kept alive by self)
+        s.mb_eptr_host, s.mb_uptr_host = hp(self.mb_eptr), hp(self.mb_uptr)
+        s.mb_cptr_host, s.mb_sptr_host = hp(self.mb_cptr), hp(self.mb_sptr)
+        s.e_pos, s.e_x = self.e_pos.data_ptr(), self.e_x.data_ptr()
+        s.u_feat, s.u_ptr = self.u_feat.data_ptr(), self.u_ptr.data_ptr()
+        s.chunk_u0, s.split_u = self.chunk_u0.data_ptr(), self.split_u.data_ptr()
+        s.max_chunks, s.max_cols = self.max_chunks, self.max_cols
+        if self.world > 1:
+            s.csr_slot = self.csr_slot.data_ptr()
+            s.mb_owner_start_host = hp(self.mb_owner_start)
+            s.mb_optr_host = hp(self.mb_optr)
+            s.own_q, s.own_src = self.own_q.data_ptr(), self.own_src.data_ptr()
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)
+
+    def nbytes(self):
+        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.chunk_u0, self.split_u, self.csr_slot, self.own_q,
+              self.own_src]
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+class _Raw:
+    """__cuda_array_interface__ view of library-allocated device memory (no ownership)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr, shape, dtype=torch.float64):
+    typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    if int(np.prod(shape)) == 0:
+        return torch.zeros(tuple(shape), dtype=dtype, device="cuda")
+    return torch.as_tensor(_Raw(ptr, shape, typestr), device=torch.device("cuda", torch.cuda.current_device()))
+
+
+def arows(degree, n_orders):
+    """rows A^1..A^(deg_o-1) kept per sample over all orders (ARows<DEG,NORD> in psgd_plan.cu)."""
+    return sum(degree - o - 1 for o in range(n_orders))
+
+
+class PsgdContext:
+    """sp_psgd_ctx + the device memory behind it.  Single rank: P / w are ordinary tensors.  Sharded: the
+    peer-visible buffers (model shard, inboxes, statistics boxes, flags) live in one cudaMalloc slab per
+    rank whose CUDA IPC handle is exchanged through the process group at construction."""
+
+    def __init__(self, plan, n_orders, k, degree, reg, loss, fit_linear, lams, group=None):
+        L = _lib.load()
+        dev = plan.device
+        self.plan_dims = (plan.max_chunks, plan.max_cols, plan.batch_local)
+        self.world, self.rank, self.group = plan.world, plan.rank, group
+        self.n_orders, self.k, self.d, self.d_rows = int(n_orders), int(k), plan.n_features, plan.d_rows
+        f64 = torch.float64
+        ncolk = self.n_orders * self.k
+        self.lams = lams
+        self.thr = torch.zeros(ncolk, dtype=f64, device=dev)
+        ar = arows(degree, n_orders)
+        self.bufA = torch.empty(max(plan.batch_local * ar * k, 1), dtype=f64, device=dev)
+        self.bufdL = torch.empty(max(plan.batch_local, 1), dtype=f64, device=dev)
+        self.sample_loss = torch.zeros(max(plan.n_local, 1), dtype=f64, device=dev)
+        self.part_g = torch.empty(max(plan.max_chunks * 2 * ncolk, 1), dtype=f64, device=dev)
+        self.part_w = torch.empty(max(plan.max_chunks * 2, 1), dtype=f64, device=dev)
+        self.work = torch.zeros(int(L.sp_psgd_plan_work_doubles(self.n_orders, self.k)), dtype=f64, device=dev)
+        xw = int(L.sp_psgd_plan_xwork_doubles(self.n_orders, self.k, self.world))
+        s = _lib.SpPsgdCtx()
+        self._slab = None
+        self._peer_bases = []
+        if self.world == 1:
+            self.P = torch.zeros((self.n_orders, self.d_rows, self.k), dtype=f64, device=dev)
+            self.w = torch.zeros(self.d_rows, dtype=f64, device=dev)
+            self.xwork = torch.zeros(xw, dtype=f64, device=dev)
+            s.xwork = self.xwork.data_ptr()
+        else:
+            import torch.distributed as dist
+            cap = plan.inbox_cap
+            sizes = [("P", ncolk * self.d_rows), ("w", self.d_rows), ("inbox_g", self.world * cap * ncolk),
+                     ("inbox_w", self.world * cap), ("xwork", xw), ("flags", CHANNELS * MAX_RANKS), ("err", 2)]
+            offs, at = {}, 0
+            for name, n in sizes:
+                offs[name] = at
+                at += (int(n) + 31) // 32 * 32                      # 256-byte aligned sub-buffers
+            base = C.c_void_p()
+            _lib.check(L.sp_shm_alloc(C.c_size_t(at * 8), C.byref(base)))
+            self._slab = base.value
+            handle = (C.c_ubyte * 64)()
+            _lib.check(L.sp_ipc_export(C.c_void_p(self._slab), handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            bases = []
+            for r in range(self.world):
+                if r == self.rank:
+                    bases.append(self._slab)
+                    continue
+                hb = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                p = C.c_void_p()
+                _lib.check(L.sp_ipc_open(hb, C.byref(p)))
+                bases.append(p.value)
+                self._peer_bases.append(p.value)
+            at_ptr = lambda r, name: bases[r] + offs[name] * 8          # noqa: E731
+            self.P = _view(at_ptr(self.rank, "P"), (self.n_orders, self.d_rows, self.k))
+            self.w = _view(at_ptr(self.rank, "w"), (self.d_rows,))
+            self.stage = torch.empty(max(plan.max_cols * ncolk, 1), dtype=f64, device=dev)
+            self.stage_w = torch.empty(max(plan.max_cols, 1), dtype=f64, device=dev)
+            s.stage, s.stage_w = self.stage.data_ptr(), self.stage_w.data_ptr()
+            s.inbox_g, s.inbox_w = at_ptr(self.rank, "inbox_g"), at_ptr(self.rank, "inbox_w")
+            s.inbox_cap = cap
+            s.err = at_ptr(self.rank, "err")
+            s.xwork = at_ptr(self.rank, "xwork")
+            self._err = _view(at_ptr(self.rank, "err"), (2,), torch.int32)
+            for r in range(self.world):
+                s.peer_P[r], s.peer_w[r] = at_ptr(r, "P"), at_ptr(r, "w")
+                s.peer_inbox_g[r] = at_ptr(r, "inbox_g") + self.rank * cap * ncolk * 8
+                s.peer_inbox_w[r] = at_ptr(r, "inbox_w") + self.rank * cap * 8
+                s.peer_xwork[r] = at_ptr(r, "xwork")
+                s.peer_flags[r] = at_ptr(r, "flags")
+            dist.barrier(group=group)
+        s.P, s.w, s.lams, s.thr = self.P.data_ptr(), self.w.data_ptr(), lams.data_ptr(), self.thr.data_ptr()
+        s.n_orders, s.k, s.d_rows, s.degree = self.n_orders, self.k, self.d_rows, int(degree)
+        s.reg, s.loss, s.fit_linear = _lib.REG_IDS[reg], _lib.LOSS_IDS[loss], int(bool(fit_linear))
+        s.world, s.rank = self.world, self.rank
+        s.bufA, s.bufdL, s.sample_loss = self.bufA.data_ptr(), self.bufdL.data_ptr(), self.sample_loss.data_ptr()
+        s.part_g, s.part_w, s.work = self.part_g.data_ptr(), self.part_w.data_ptr(), self.work.data_ptr()
+        s.C, s.Cw, s.seq, s.seq_generic = 1.0, 1.0, 0, 0
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)
+
+    # ---- model in / out (feature-major P [n_orders, d, k], w [d] on the device)
+    def load_model(self, P_odk, w):
+        G, r = self.world, self.rank
+        if G == 1:
+            self.P.copy_(P_odk)
+            self.w.copy_(w)
+            return
+        nrow = (self.d - r + G - 1) // G if self.d > r else 0
+        self.P.zero_()
+        self.w.zero_()
+        self.P[:, :nrow] = P_odk[:, r::G]
+        self.w[:nrow] = w[r::G]
+
+    def store_model(self, P_odk, w):
+        """all ranks end up with the full model (sharded: one all-gather of the row shards)."""
+        if self.world == 1:
+            P_odk.copy_(self.P)
+            w.copy_(self.w)
+            return
+        import torch.distributed as dist
+        G = self.world
+        cdev = _comm_device(self.group)
+        mine = torch.cat([self.P.reshape(-1), self.w]).to(cdev)
+        parts = [torch.empty_like(mine) for _ in range(G)]
+        dist.all_gather(parts, mine, group=self.group)
+        npk = self.n_orders * self.d_rows * self.k
+        for r in range(G):
+            nrow = (self.d - r + G - 1) // G if self.d > r else 0
+            pr = parts[r].to(P_odk.device)
+            P_odk[:, r::G] = pr[:npk].reshape(self.n_orders, self.d_rows, self.k)[:, :nrow]
+            w[r::G] = pr[npk:][:nrow]
+
+    def check_peers(self):
+        if self.world > 1 and int(self._err[0].item()) != 0:
+            raise RuntimeError("sharded psgd: a cross-rank wait timed out (a peer rank failed or stalled)")
+
+    def rebind(self, plan):
+        """The scratch sized by the plan must cover a rebuilt plan (shuffle=True rebuilds every epoch)."""
+        if (plan.max_chunks, plan.max_cols, plan.batch_local) != self.plan_dims:
+            dev, f64 = plan.device, torch.float64
+            ncolk = self.n_orders * self.k
+            if plan.max_chunks > self.plan_dims[0]:
+                self.part_g = torch.empty(max(plan.max_chunks * 2 * ncolk, 1), dtype=f64, device=dev)
+                self.part_w = torch.empty(max(plan.max_chunks * 2, 1), dtype=f64, device=dev)
+                self.struct.part_g, self.struct.part_w = self.part_g.data_ptr(), self.part_w.data_ptr()
+            if self.world > 1 and plan.max_cols > self.plan_dims[1]:
+                self.stage = torch.empty(max(plan.max_cols * ncolk, 1), dtype=f64, device=dev)
+                self.stage_w = torch.empty(max(plan.max_cols, 1), dtype=f64, device=dev)
+                self.struct.stage, self.struct.stage_w = self.stage.data_ptr(), self.stage_w.data_ptr()
+            if self.world > 1 and plan.inbox_cap > self.struct.inbox_cap:
+                raise RuntimeError("sharded psgd with shuffle=True: inbox capacity exceeded after a reshuffle")
+            self.plan_dims = (max(plan.max_chunks, self.plan_dims[0]), max(plan.max_cols, self.plan_dims[1]), plan.batch_local)
+
+    def close(self):
+        L = _lib.load()
+        if self._slab is not None:
+            torch.cuda.synchronize()
+            if self.group is not None:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)
+            for p in self._peer_bases:
+                L.sp_ipc_close(C.c_void_p(p))
+            self._peer_bases = []
+            self.P = self.w = self._err = None
+            L.sp_shm_free(C.c_void_p(self._slab))
+            self._slab = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

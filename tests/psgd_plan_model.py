@@ -1,0 +1,268 @@
+"""numpy model of the planned psgd path (sparsepoly_b200/csrc/psgd_plan.cu), driven by the SAME plan arrays
+the CUDA kernels read (sparsepoly_b200/psgd_plan.py).  Test infrastructure: it lets the CPU suite check the
+plan layout (chunks, split columns, owner tables), the lazy (C, T) frame and the sharded pull / push /
+owner protocol against the oracle without a GPU.  G ranks are simulated in one process; "peer memory" is
+just the other rank's arrays."""
+import numpy as np
+
+CH = 64
+
+
+def st_true(r, T, invC):
+    m = np.abs(r) - T
+    return np.where(m > 0, np.sign(r) * m * invC, 0.0)
+
+
+def to_raw(v, T, Cn):
+    return np.where(v == 0.0, 0.0, np.sign(v) * (np.abs(v) * Cn + T))
+
+
+def dloss(loss, p, y):
+    if loss == "squared":
+        return p - y
+    if loss == "logistic":
+        z = p * y
+        if z > 18.0:
+            return -y * np.exp(-z)
+        if z < -18.0:
+            return -y
+        return -y / (np.exp(z) + 1.0)
+    z = 1.0 - p * y
+    return (-2.0 * y) * z if z > 0 else 0.0
+
+
+def lossv(loss, p, y):
+    if loss == "squared":
+        return 0.5 * (p - y) ** 2
+    if loss == "logistic":
+        z = p * y
+        if z > 18.0:
+            return np.exp(-z)
+        if z < -18.0:
+            return -z
+        return np.log(1.0 + np.exp(-z))
+    z = 1.0 - p * y
+    return z * z if z > 0 else 0.0
+
+
+def get_eta(lr, eta0, alpha, beta, power_t, it):
+    if lr == "constant":
+        return eta0, eta0
+    if lr == "optimal":
+        e = eta0 * it
+        return eta0 / (1.0 + e * beta) ** power_t, eta0 / (1.0 + e * alpha) ** power_t
+    if lr == "pegasos":
+        return 1.0 / (beta * it), 1.0 / (alpha * it)
+    e = eta0 / it ** power_t
+    return e, e
+
+
+def michelot(vals, strength):
+    """fixed point tau = 2 s S(tau) / (1 + 2 s C(tau)) over {v > tau}, from tau = 0 (psgd_solve_kernel's
+    generic path; the band path lands on the same point)."""
+    tau, prev = 0.0, -1
+    for _ in range(1000):
+        act = vals > tau
+        n = int(act.sum())
+        tau = 2.0 * strength * float(vals[act].sum()) / (1.0 + 2.0 * strength * n)
+        if n == prev:
+            return tau
+        prev = n
+    raise RuntimeError("no fixed point")
+
+
+class RankState:
+    def __init__(self, plan, csr, y, idx, n_orders, k, degree):
+        t = lambda a: None if a is None else a.cpu().numpy()      # noqa: E731
+        self.plan = plan
+        self.e_pos, self.e_x = t(plan.e_pos), t(plan.e_x)
+        self.u_feat, self.u_ptr = t(plan.u_feat), t(plan.u_ptr)
+        self.chunk_u0, self.split_u = t(plan.chunk_u0), t(plan.split_u)
+        self.csr_slot = t(plan.csr_slot)
+        self.own_q, self.own_src = t(plan.own_q), t(plan.own_src)
+        self.indptr, self.indices, self.data = (np.asarray(a) for a in csr)
+        self.y, self.idx = y, idx
+        self.d_rows = plan.d_rows
+        self.P = np.zeros((n_orders, plan.d_rows, k))
+        self.w = np.zeros(plan.d_rows)
+        self.sloss = np.zeros(plan.n_local)
+
+
+def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha, beta, gamma, eta0, lr, power_t, it,
+              P_odk, w, epochs=1):
+    """`epochs` epochs over the plans of `ranks` (list of RankState, one per simulated rank).  P_odk [o,d,k] / w [d]
+    are updated in place; returns (it, sum of losses of the last epoch)."""
+    G = len(ranks)
+    ncol = n_orders * k
+    for r, R in enumerate(ranks):                       # load_model
+        nrow = len(range(r, d, G))
+        R.P[:] = 0.0; R.w[:] = 0.0
+        R.P[:, :nrow] = P_odk[:, r::G]
+        R.w[:nrow] = w[r::G]
+    thr = np.zeros((n_orders, k))
+    C = Cw = 1.0
+    M = ranks[0].plan.n_minibatches
+    bL = ranks[0].plan.batch_local
+    degs = [degree - o for o in range(n_orders)]
+    sum_loss = 0.0
+    for _ in range(epochs):
+        for m in range(M):
+            eta_P, eta_w = get_eta(lr, eta0, alpha, beta, power_t, it)
+            b_glob = sum(min((m + 1) * bL, R.plan.n_local) - m * bL for R in ranks)
+            cP, denP = eta_P / b_glob, 1.0 + eta_P * beta
+            cw, denw = eta_w / b_glob, 1.0 + eta_w * alpha
+            CnP = C * denP
+            Cnw = Cw * denw if fit_linear else Cw
+            invC, invCw = 1.0 / C, 1.0 / Cw
+            strength = gamma * eta_P / (1.0 + eta_P * beta)
+            inbox = [[None] * G for _ in range(G)]            # inbox[owner][src] = (gP rows, gw)
+            for r, R in enumerate(ranks):
+                pl = R.plan
+                e0, e1 = pl.mb_eptr[m], pl.mb_eptr[m + 1]
+                u0, u1 = pl.mb_uptr[m], pl.mb_uptr[m + 1]
+                c0 = pl.mb_cptr[m]
+                b0, b1 = m * bL, min((m + 1) * bL, pl.n_local)
+                # ---- pull (sharded) / direct reads: true rows of the minibatch's columns
+                feats = R.u_feat[u0:u1]
+                stage = np.zeros((u1 - u0, n_orders, k))
+                stage_w = np.zeros(u1 - u0)
+                for su, j in enumerate(feats):
+                    own, q = ranks[j % G], j // G
+                    stage[su] = st_true(own.P[:, q, :], thr, invC)
+                    stage_w[su] = own.w[q] * invCw
+                slot_of = {int(j): su for su, j in enumerate(feats)}
+                # ---- rows pass
+                bufA = {}
+                bufdL = np.zeros(b1 - b0)
+                for b in range(b0, b1):
+                    i = R.idx[b]
+                    st, en = R.indptr[i], R.indptr[i + 1]
+                    A = np.zeros((n_orders, degree + 1, k))
+                    A[:, 0, :] = 1.0
+                    ypred = 0.0
+                    for e in range(st, en):
+                        j, x = R.indices[e], R.data[e]
+                        su = R.csr_slot[e] if G > 1 else slot_of[int(j)]
+                        assert feats[su] == j
+                        if fit_linear:
+                            ypred += x * stage_w[su]
+                        for o in range(n_orders):
+                            for t in range(degs[o]):
+                                A[o, degs[o] - t] += (A[o, degs[o] - t - 1] * x) * stage[su, o]
+                    for o in range(n_orders):
+                        ypred += float(np.dot(lams, A[o, degs[o]]))
+                    bufA[b - b0] = A
+                    bufdL[b - b0] = dloss(loss, ypred, R.y[i])
+                    R.sloss[b] = lossv(loss, ypred, R.y[i])
+                # ---- cols pass, chunk by chunk exactly like psgd_cols_kernel
+                nE = e1 - e0
+                nch = (nE + CH - 1) // CH
+                assert nch == pl.mb_cptr[m + 1] - c0
+                part = {}
+                done = {}                                   # column -> (g [o,k], gw)
+
+                def term(pos, x, pold):
+                    g = np.zeros((n_orders, k))
+                    A = bufA[pos]
+                    for o in range(n_orders):
+                        dprev = np.full(k, x)
+                        for t in range(1, degs[o]):
+                            dprev = x * (A[o, t] - pold[o] * dprev)
+                        g[o] = (bufdL[pos] * lams) * dprev
+                    return g, bufdL[pos] * x
+
+                for c in range(nch):
+                    ce0, ce1 = c * CH, min((c + 1) * CH, nE)
+                    ends_here = ce1 == nE or R.e_pos[e0 + ce1] < 0
+                    ucur = int(R.chunk_u0[c0 + c]) - 1
+                    have, first = False, True
+                    for e in range(ce0, ce1):
+                        ep = int(R.e_pos[e0 + e])
+                        nf = ep < 0 or e == ce0
+                        if nf:
+                            if have:
+                                (done if started else part)[(cur_u, ) if started else (c, 0 if first_col else 1)] = (g, gw)
+                            first_col = not have
+                            have = True
+                            ucur += 1
+                            cur_u = ucur
+                            started = ep < 0
+                            pold = stage[cur_u - u0]
+                            g, gw = np.zeros((n_orders, k)), 0.0
+                            assert R.u_ptr[cur_u] <= e0 + e < R.u_ptr[cur_u + 1]
+                        tg, tw = term(ep & 0x7fffffff, R.e_x[e0 + e], pold)
+                        g = g + tg
+                        gw = gw + tw
+                    if have:
+                        complete = started and ends_here
+                        (done if complete else part)[(cur_u, ) if complete else (c, 0 if first_col else 1)] = (g, gw)
+                # ---- split columns
+                s0, s1 = pl.mb_sptr[m], pl.mb_sptr[m + 1]
+                for u in R.split_u[s0:s1]:
+                    s_rel, e_rel = R.u_ptr[u] - e0, R.u_ptr[u + 1] - e0
+                    cc0, cc1 = s_rel // CH, (e_rel - 1) // CH
+                    assert cc1 > cc0
+                    g, gw = np.zeros((n_orders, k)), 0.0
+                    for c in range(cc0, cc1 + 1):
+                        slot = 1 if (c == cc0 and s_rel > cc0 * CH) else 0
+                        pg, pw = part.pop((c, slot))
+                        g = g + pg
+                        gw = gw + pw
+                    done[(int(u), )] = (g, gw)
+                assert not part, "a partial sum was never consumed"
+                assert len(done) == u1 - u0, "every column finished exactly once"
+                # ---- apply (single rank) or push to the owners' inboxes
+                if G == 1:
+                    for (u, ), (g, gw) in done.items():
+                        j = int(R.u_feat[u])
+                        pold = stage[u - u0]
+                        v = (pold - g * cP) / denP
+                        R.P[:, j, :] = to_raw(v, thr, CnP)
+                        if fit_linear:
+                            R.w[j] = ((stage_w[u - u0] - gw * cw) / denw) * Cnw
+                else:
+                    ost = pl.mb_owner_start[m]
+                    for o in range(G):
+                        n_o = ost[o + 1] - ost[o]
+                        inbox[o][r] = (np.zeros((n_o, n_orders, k)), np.zeros(n_o))
+                    for (u, ), (g, gw) in done.items():
+                        su = u - u0
+                        owner = int(R.u_feat[u]) % G
+                        assert ost[owner] <= su < ost[owner + 1]
+                        inbox[owner][r][0][su - ost[owner]] = g
+                        inbox[owner][r][1][su - ost[owner]] = gw
+            # ---- owner pass (after the cross-rank barrier)
+            if G > 1:
+                for o, R in enumerate(ranks):
+                    pl = R.plan
+                    o0, o1 = pl.mb_optr[m], pl.mb_optr[m + 1]
+                    for t in range(o0, o1):
+                        q = int(R.own_q[t])
+                        g, gw = np.zeros((n_orders, k)), 0.0
+                        for src in range(G):
+                            at = int(R.own_src[t, src])
+                            if at >= 0:
+                                g = g + inbox[o][src][0][at]
+                                gw = gw + inbox[o][src][1][at]
+                        pold = st_true(R.P[:, q, :], thr, invC)
+                        v = (pold - g * cP) / denP
+                        R.P[:, q, :] = to_raw(v, thr, CnP)
+                        if fit_linear:
+                            R.w[q] = ((R.w[q] * invCw - gw * cw) / denw) * Cnw
+            C, Cw = CnP, Cnw
+            # ---- prox as a lazily applied column threshold
+            if reg == "l1":
+                thr = thr + C * strength
+            else:
+                invCn = 1.0 / C
+                for o in range(n_orders):
+                    for s in range(k):
+                        vals = np.concatenate([np.maximum(np.abs(R.P[o, :, s]) - thr[o, s], 0.0) * invCn for R in ranks])
+                        thr[o, s] = thr[o, s] + C * michelot(vals[vals > 0], strength)
+            it += 1
+        sum_loss = sum(float(R.sloss.sum()) for R in ranks)
+    for r, R in enumerate(ranks):                       # materialise + store_model
+        nrow = len(range(r, d, G))
+        P_odk[:, r::G] = st_true(R.P, thr[:, None, :], 1.0 / C)[:, :nrow]
+        w[r::G] = (R.w / Cw)[:nrow]
+    return it, sum_loss

@@ -1,0 +1,122 @@
+"""CPU checks of the planned psgd path's host logic (sparsepoly_b200/psgd_plan.py) and of its algorithm:
+the plan arrays the CUDA kernels read are replayed by a numpy model of those kernels
+(tests/psgd_plan_model.py) and the result must equal the oracle's psgd fit (reference
+optimizer/psgd.py:125-199) to 1e-9 -- single rank and sharded over 2 / 3 simulated ranks."""
+import numpy as np
+import pytest
+import torch
+
+from psgd_plan_model import RankState, run_model
+from sparsepoly_b200 import synth
+from sparsepoly_b200.distributed import interleave_shards
+from sparsepoly_b200.psgd_plan import CHUNK, PsgdPlan
+
+
+def _csr_t(X):
+    return (torch.from_numpy(X.indptr.astype(np.int32)), torch.from_numpy(X.indices.astype(np.int32)),
+            torch.from_numpy(X.data.astype(np.float64)))
+
+
+def _plans(Xs, idxs, d, b_loc, group_entries=48_000_000):
+    G = len(Xs)
+    plans = [PsgdPlan(_csr_t(X), torch.from_numpy(idx), d, b_loc, world=G, rank=r, group_entries=group_entries,
+                      defer_owner_tables=G > 1) for r, (X, idx) in enumerate(zip(Xs, idxs))]
+    if G > 1:
+        lists = [p.column_lists() for p in plans]
+        gathered = tuple([l[t] for l in lists] for t in range(4))
+        for p in plans:
+            p.finish_owner_tables(*gathered)
+    return plans
+
+
+@pytest.mark.parametrize("b_loc,group_entries", [(37, 48_000_000), (500, 900), (1, 48_000_000), (4000, 48_000_000)])
+def test_plan_layout_matches_brute_force(b_loc, group_entries):
+    X = synth.criteo_like(1500, 400, 3)                      # 13 dense columns: split over many chunks
+    rng = np.random.RandomState(0)
+    idx = rng.permutation(1500).astype(np.int32)
+    plan = _plans([X], [idx], 400, b_loc, group_entries)[0]
+    M = plan.n_minibatches
+    assert M == -(-1500 // b_loc)
+    e_pos, e_x = plan.e_pos.numpy(), plan.e_x.numpy()
+    u_feat, u_ptr = plan.u_feat.numpy(), plan.u_ptr.numpy()
+    for m in range(M):
+        rows = idx[m * b_loc:(m + 1) * b_loc]
+        want = []                                            # (feature, position, value) sorted by feature then position
+        for pos, i in enumerate(rows):
+            for e in range(X.indptr[i], X.indptr[i + 1]):
+                want.append((int(X.indices[e]), pos, float(X.data[e])))
+        want.sort(key=lambda t: (t[0], t[1]))
+        e0, e1 = plan.mb_eptr[m], plan.mb_eptr[m + 1]
+        assert e1 - e0 == len(want)
+        u0, u1 = plan.mb_uptr[m], plan.mb_uptr[m + 1]
+        got_feat = np.repeat(u_feat[u0:u1], np.diff(u_ptr[u0:u1 + 1]))
+        assert np.array_equal(got_feat, [t[0] for t in want])
+        assert np.array_equal(e_pos[e0:e1] & 0x7fffffff, [t[1] for t in want])
+        assert np.array_equal(e_x[e0:e1], [t[2] for t in want])
+        starts = np.zeros(e1 - e0, bool)
+        starts[u_ptr[u0:u1] - e0] = True
+        assert np.array_equal(e_pos[e0:e1] < 0, starts)
+        nch = -(-(e1 - e0) // CHUNK)
+        assert plan.mb_cptr[m + 1] - plan.mb_cptr[m] == nch
+        cu0 = plan.chunk_u0.numpy()[plan.mb_cptr[m]:plan.mb_cptr[m + 1]]
+        for c in range(nch):
+            e = e0 + c * CHUNK
+            assert u_ptr[cu0[c]] <= e < u_ptr[cu0[c] + 1]
+        split = plan.split_u.numpy()[plan.mb_sptr[m]:plan.mb_sptr[m + 1]]
+        want_split = [u for u in range(u0, u1) if (u_ptr[u] - e0) // CHUNK != (u_ptr[u + 1] - 1 - e0) // CHUNK]
+        assert np.array_equal(split, want_split)
+    assert plan.max_chunks == np.max(np.diff(plan.mb_cptr)) and plan.max_cols == np.max(np.diff(plan.mb_uptr))
+
+
+def _oracle_fit(X, y, kw, epochs):
+    from oracle import oracle as O
+    return O.fit_fm(X, y, max_iter=epochs, tol=-1.0, n_iter_no_change=10 ** 9, random_state=0, **kw)
+
+
+CASES = [
+    dict(degree=2, loss="logistic", n_components=5, solver="psgd", regularizer="squaredl12", alpha=1e-3, beta=1e-3,
+         gamma=2e-3, eta0=0.2, fit_lower=None),
+    dict(degree=3, loss="squared", n_components=3, solver="psgd", regularizer="l1", alpha=1e-2, beta=1e-2,
+         gamma=1e-3, eta0=0.05, fit_lower="explicit", learning_rate="invscaling", power_t=0.5),
+    dict(degree=2, loss="squared_hinge", n_components=4, solver="psgd", regularizer="squaredl12", alpha=1e-3,
+         beta=1e-3, gamma=5e-3, eta0=0.1, fit_lower=None, fit_linear=False, learning_rate="constant"),
+]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_plan_model_matches_oracle(case, world):
+    kw = dict(CASES[case])
+    n_loc, d, b_glob = 240, 90, 48 * world if world > 1 else 50
+    if case == 2:
+        b_glob = 240 * world                                   # one minibatch per epoch: the dense columns split
+    Xs = [synth.criteo_like(n_loc, d, 11 + r) for r in range(world)]
+    rng = np.random.RandomState(5)
+    ys = [np.where(rng.rand(n_loc) < 0.4, 1.0, -1.0) if kw["loss"] != "squared" else rng.randn(n_loc) for _ in range(world)]
+    idxs = [np.arange(n_loc, dtype=np.int32) for _ in range(world)]
+    b_loc = max(1, b_glob // world)
+    plans = _plans(Xs, idxs, d, b_loc)
+    degree, k = kw["degree"], kw["n_components"]
+    n_orders = degree - 1 if kw["fit_lower"] == "explicit" else 1
+    ranks = [RankState(p, (X.indptr, X.indices, X.data), y, idx, n_orders, k, degree) for p, X, y, idx in zip(plans, Xs, ys, idxs)]
+    P_kd = 0.01 * np.random.RandomState(0).randn(n_orders, k, d)              # what fit draws with random_state=0
+    P = np.ascontiguousarray(P_kd.swapaxes(1, 2))
+    w = np.zeros(d)
+    epochs = 2
+    it, sum_loss = run_model(ranks, d, n_orders, k, degree, kw["regularizer"], kw["loss"], kw.get("fit_linear", True),
+                             np.ones(k), kw["alpha"], kw["beta"], kw["gamma"], kw["eta0"], kw.get("learning_rate", "optimal"),
+                             kw.get("power_t", 1.0), 1, P, w, epochs=epochs)
+    # the equivalent single-process run: shards interleaved in blocks of b_loc rows (distributed.interleave_shards)
+    import scipy.sparse as sp
+    order = interleave_shards([np.arange(n_loc) + r * n_loc for r in range(world)], b_loc * world)
+    Xall, yall = sp.vstack(Xs).tocsr()[order], np.concatenate(ys)[order]
+    out = _oracle_fit(Xall, yall, dict(kw, batch_size=b_loc * world), epochs)
+    P_ref = out["P_"].swapaxes(1, 2)
+    scale = np.max(np.abs(P_ref))
+    assert np.max(np.abs(P - P_ref)) <= 1e-9 * scale
+    assert np.max(np.abs(w - out["w_"])) <= 1e-9 * max(np.max(np.abs(out["w_"])), 1e-300)
+    dust = (np.abs(P) < 1e-12 * scale) & (np.abs(P_ref) < 1e-12 * scale)
+    assert np.all(((P != 0) == (P_ref != 0)) | dust)
+    assert it == out["it_"]
+    assert abs(sum_loss / (n_loc * world) - out["trace"][-1]) <= 1e-9 * abs(out["trace"][-1])
+    assert 0.02 < np.mean(P_ref != 0) < 0.999 or kw["regularizer"] == "l1"
