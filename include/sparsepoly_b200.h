@@ -202,17 +202,15 @@ int sp_pbcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P_dk, int k
 int sp_get_eta(int learning_rate, double eta0, double alpha, double beta, double power_t,
                int64_t it, double *eta_P_host, double *eta_w_host);
 
-/* Minibatch gradient: samples idx_samples[b0..b1) (psgd._pred + _update_grads,
- * psgd.py:47-91).  P_odk [n_orders,d,k]; grad_P same shape and grad_w [d] are accumulated
- * into (fp64 atomics); *loss_sum accumulates sum of losses at the pre-update parameters.
- * col_thresh (may be NULL): [n_orders*k] thresholds of a lazily applied prox -- the model is
- * soft_threshold(P_odk[o,:,s], col_thresh[o*k+s]) (see sp_psgd_update_prox).
- * touched (may be NULL): [8*ceil(d/8)] bytes; touched[j] is set to 1 for every feature row whose
- * gradient this call adds to, so that sp_psgd_update_prox can skip reading / zeroing the others. */
+/* The dense-gradient psgd path (every regularizer; the only one for l21 / squaredl21, and the
+ * cross-check of the planned path below for l1 / squaredl12).
+ * Minibatch gradient: samples idx_samples[b0..b1) (psgd._pred + _update_grads, psgd.py:47-91).
+ * P_odk [n_orders,d,k]; grad_P same shape and grad_w [d] are accumulated into (fp64 atomics: the sum
+ * order is not fixed); *loss_sum accumulates sum of losses at the pre-update parameters. */
 int sp_psgd_grad(const sp_dataset *ds, const double *y, const double *P_odk, int n_orders, int k,
                  const double *w, const double *lams, int degree, int loss, int fit_linear,
                  const int32_t *idx_samples, int b0, int b1, double *grad_P, double *grad_w,
-                 double *loss_sum, const double *col_thresh, unsigned char *touched, sp_stream stream);
+                 double *loss_sum, sp_stream stream);
 
 /* SGD step + zeroing of the gradients (psgd._update_params without the prox, psgd.py:94-117,
  * :195-196):  P = (P - (eta_P/batch)*grad_P) / (1 + eta_P*beta), same for w with alpha. */
@@ -224,26 +222,11 @@ int sp_psgd_step(double *P_odk, double *grad_P, double *w, double *grad_w, int n
  * squaredl21.py:63-74, regularizer/utils.py:26-70).  work: >= d + 8*k + 64 doubles. */
 int sp_prox(double *P_dk, int d, int k, int reg, double strength, double *work, sp_stream stream);
 
-/* Fused dense update + prox for l1 / squaredl12, one cooperative launch per minibatch:
- * P_raw = (soft_threshold(P_raw, col_thresh) - (eta_P/batch)*grad_P)/(1+eta_P*beta), grad_P = 0,
- * then col_thresh = the new prox thresholds (l1: strength; squaredl12: 2*strength*S_s of
- * regularizer/utils.py:26-70, found by a warm-started fixed-point selection).  The soft threshold
- * is applied lazily by the readers; sp_psgd_finalize materialises it (P = model, col_thresh = 0).
- * col_thresh: [n_orders*k], zero-initialised before the first call; work: sp_psgd_lazy_work_doubles.
- * touched (may be NULL): the flags sp_psgd_grad set (after a multi-GPU gradient all-reduce: their
- * element-wise maximum over the ranks); rows with flag 0 are treated as gradient 0 without reading
- * grad_P; the flags are cleared. */
-int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
-                        double beta, int batch, int reg, double strength, double *col_thresh,
-                        double *work, unsigned char *touched, sp_stream stream);
-int sp_psgd_finalize(double *P_odk, int n_orders, int d, int k, double *col_thresh, sp_stream stream);
-size_t sp_psgd_lazy_work_doubles(int n_orders, int k);
-
 /* doubles of scratch sp_prox / sp_psgd_epoch need for a [d,k] matrix */
 size_t sp_prox_work_doubles(int d, int k);
 
-/* Whole single-GPU psgd epoch = psgd.psgd_epoch (psgd.py:125-199): loops the three calls
- * above over the minibatches; *it_io_host is advanced once per parameter update. */
+/* Whole single-GPU psgd epoch = psgd.psgd_epoch (psgd.py:125-199) on the dense-gradient path: loops the
+ * three calls above over the minibatches; *it_io_host is advanced once per parameter update. */
 int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_orders, int k, double *w,
                   const double *lams, int degree, double alpha, double beta, double gamma, int reg,
                   int loss, double *grad_P, double *grad_w, const int32_t *idx_samples,

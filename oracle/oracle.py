@@ -88,6 +88,7 @@ def lib():
                                         C.c_int64, _dp, _dp]
         L.sp_oracle_loss_sum.restype = C.c_double
         L.sp_oracle_loss_sum.argtypes = [C.c_int, C.c_int, _dp, _dp]
+        L.sp_oracle_col_norm_sq.argtypes = [C.c_int, _ip, _dp, _dp]
         L.sp_oracle_branch_count.restype = C.c_longlong
         L.sp_oracle_branch_count.argtypes = [C.c_int]
         L.sp_oracle_reg_eval.restype = C.c_double
@@ -225,8 +226,12 @@ def poly_predict(X, P, lams, kernel, degree=2):
 def col_norm_sq(X):
     """row_norms(X.T, squared=True) (sparse_factorization_machines.py:409)."""
     if _is_sparse(X):
-        Xc = sp.csc_matrix(X)
-        return np.asarray(Xc.multiply(Xc).sum(axis=0)).ravel().astype(np.float64)
+        # sklearn's csr_row_norms on X.T: one sequential sum per feature, samples ascending (NOT scipy's
+        # pairwise reduction -- the order matters at the ulp level and pcd amplifies it at n >= 10^4)
+        indptr, _, data = to_csc(X)
+        out = np.zeros(X.shape[1])
+        lib().sp_oracle_col_norm_sq(int(X.shape[1]), _i(indptr), _d(data), _d(out))
+        return out
     X = np.asarray(X, dtype=np.float64)
     return np.einsum("ij,ij->j", X, X)
 

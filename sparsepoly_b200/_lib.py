@@ -104,11 +104,7 @@ SIGNATURES = {
     "sp_pbcd_epoch": (_i, [_DSP, _PLP, _vp, _i, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp,
                            _vp]),
     "sp_get_eta": (_i, [_i, _d, _d, _d, _d, C.c_int64, C.POINTER(_d), C.POINTER(_d)]),
-    "sp_psgd_grad": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp,
-                          _vp, _vp, _vp]),
-    "sp_psgd_update_prox": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _i, _d, _vp, _vp, _vp, _vp]),
-    "sp_psgd_finalize": (_i, [_vp, _i, _i, _i, _vp, _vp]),
-    "sp_psgd_lazy_work_doubles": (C.c_size_t, [_i, _i]),
+    "sp_psgd_grad": (_i, [_DSP, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "sp_psgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _i, _i, _vp]),
     "sp_prox_work_doubles": (C.c_size_t, [_i, _i]),
     "sp_prox": (_i, [_vp, _i, _i, _i, _d, _vp, _vp]),

@@ -6,17 +6,16 @@
 
 namespace {
 
-// out[j] = sum_i x_ij^2  (sparse_factorization_machines.py:409  row_norms(X.T, squared=True))
+// out[j] = sum_i x_ij^2  (sparse_factorization_machines.py:409  row_norms(X.T, squared=True) -> sklearn's
+// csr_row_norms: ONE sequential sum per feature, samples ascending).  Setup-only, so each thread walks one
+// column in exactly that order: the step sizes of cd_linear (cd_linear.py:22) are then bit-identical to
+// the reference's, which matters because pcd amplifies ulp-level differences at n >= 10^4.
 __global__ void col_norm_sq_kernel(int d, const int32_t *__restrict__ indptr,
                                    const double *__restrict__ data, double *out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = warp; j < d; j += n_warps) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d; j += gridDim.x * blockDim.x) {
         double acc = 0.0;
-        for (int e = indptr[j] + lane; e < indptr[j + 1]; e += 32) acc += data[e] * data[e];
-        acc = sp_warp_allsum(acc);
-        if (lane == 0) out[j] = acc;
+        for (int e = indptr[j]; e < indptr[j + 1]; e++) acc += data[e] * data[e];
+        out[j] = acc;
     }
 }
 
@@ -114,7 +113,7 @@ int blocks_for(long long work, int threads) {
 extern "C" int sp_col_norm_sq(const sp_dataset *ds, double *out, sp_stream stream) {
     if (!ds || !ds->csc_indptr || !out) { sp_set_error("sp_col_norm_sq: invalid argument"); return SP_ERR_INVALID; }
     if (ds->n_features == 0) return SP_OK;
-    col_norm_sq_kernel<<<blocks_for((long long)ds->n_features * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    col_norm_sq_kernel<<<blocks_for((long long)ds->n_features, 128), 128, 0, (cudaStream_t)stream>>>(
         ds->n_features, ds->csc_indptr, ds->csc_data, out);
     SP_LAUNCH_CHECK("col_norm_sq_kernel");
     return SP_OK;

@@ -33,9 +33,8 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                  const double *__restrict__ P, const double *__restrict__ w,
                  const double *__restrict__ lams, int loss, int fit_linear,
                  const int32_t *__restrict__ idx_samples, int b0, int b1, double *grad_P,
-                 double *grad_w, double *loss_sum, const double *__restrict__ col_thresh, int dbg,
-                 const int8_t *__restrict__ feat_hot, int n_hot, const int32_t *__restrict__ hot_feat,
-                 unsigned char *touched) {
+                 double *grad_w, double *loss_sum,
+                 const int8_t *__restrict__ feat_hot, int n_hot, const int32_t *__restrict__ hot_feat) {
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu
                                      : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -59,14 +58,6 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
     double lam[KCH];
 #pragma unroll
     for (int c = 0; c < KCH; c++) lam[c] = (lane + G * c < k) ? lams[lane + G * c] : 0.0;
-    // lazily applied prox: the stored matrix is P_raw, the model is soft_threshold(P_raw, thr[o][s])
-    double thr[KCH][NORD];
-#pragma unroll
-    for (int c = 0; c < KCH; c++)
-#pragma unroll
-        for (int o = 0; o < NORD; o++)
-            thr[c][o] = (col_thresh != nullptr && lane + G * c < k) ? col_thresh[o * k + lane + G * c] : 0.0;
-    const bool lazy = col_thresh != nullptr;
     double loss_acc = 0.0;
     for (int b = b0 + group; b < b1; b += n_groups) {
         const int i = idx_samples[b];
@@ -105,15 +96,6 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                         for (int o = 0; o < NORD; o++)
                             pv[u][c][o] = (q < cnt && lane + G * c < k) ? P[o * dk + (size_t)j * k + lane + G * c] : 0.0;
                 }
-                if (lazy) {
-#pragma unroll
-                    for (int u = 0; u < UB; u++)
-#pragma unroll
-                        for (int c = 0; c < KCH; c++)
-#pragma unroll
-                            for (int o = 0; o < NORD; o++) pv[u][c][o] = sp_soft_threshold(pv[u][c][o], thr[c][o]);
-                }
-
 #pragma unroll
                 for (int u = 0; u < UB; u++) {
                     if (q0 + u < cnt) {
@@ -141,8 +123,6 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
         if (lane == 0) loss_acc += sp_loss_rt(loss, ypred, yi);     // psgd.py:155
         const double dL = sp_dloss_rt(loss, ypred, yi);
         // ---- _update_grads, psgd.py:60-91
-        if (touched != nullptr)                                  // rows whose gradient becomes nonzero
-            for (int e = st + lane; e < en; e += G) touched[indices[e]] = 1;
         if (fit_linear)
             for (int e = st + lane; e < en; e += G) {
                 const int j = indices[e];
@@ -150,6 +130,7 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                 if (h >= 0) hw[h] += dL * data[e];               // (a row's features are distinct)
                 else atomicAdd(grad_w + j, dL * data[e]);
             }
+        if (use_hot) __syncwarp(gmask);                          // hw[] is shared by the group's lanes
         for (int base = st; base < en; base += G) {
             const int e = base + lane;
             int jl = 0, hl = -1;
@@ -169,15 +150,13 @@ psgd_grad_kernel(int k, int d, const int32_t *__restrict__ indptr, const int32_t
                         for (int o = 0; o < NORD; o++) {
                             double dprev = x;                           // _grad_anova, psgd.py:25-31
                             if (DEG - o > 1) {
-                                double p = P[o * dk + (size_t)j * k + s];
-                                if (lazy) p = sp_soft_threshold(p, thr[c][o]);
+                                const double p = P[o * dk + (size_t)j * k + s];
 #pragma unroll
                                 for (int t = 1; t < DEG - o; t++) dprev = x * (A[c][o][t] - p * dprev);
                             }
                             const double gv = (dL * lam[c]) * dprev;                    // psgd.py:91
                             if (HOT && hq >= 0) hacc[hq * G + lane] += gv;
-                            else if (!(dbg & 1)) atomicAdd(grad_P + o * dk + (size_t)j * k + s, gv);
-                            else if (dprev == 1.2345e-300) loss_acc += 1.0;
+                            else atomicAdd(grad_P + o * dk + (size_t)j * k + s, gv);
                         }
                     }
                 }
@@ -355,396 +334,6 @@ __global__ void row_rescale_kernel(double *__restrict__ P, int d, int k, const d
 }
 
 
-// ------------------------------------------------------------------------------ fused update + prox
-// One cooperative launch per minibatch for the regularizers whose prox is a (column-wise) soft
-// threshold: l1 (threshold = strength) and squaredl12 (threshold_s = 2*strength*S_s).
-//   phase 0 : P_raw <- (soft_threshold(P_raw, thr_old) - c*G) / den ; G <- 0   (psgd.py:113-115,
-//             :195) and, for squaredl12, the (count, sum) statistics of {|p| > thr_old[s]}: the
-//             selection is WARM-STARTED at the previous minibatch's threshold.  That is safe from
-//             any starting point: g(theta) = 2*s*S_theta/(1+2*s*theta) is unimodal over the sorted
-//             prefixes with maximum tau* (utils.py:26-70 picks exactly that theta), so one
-//             application of the fixed-point map lands at or below tau*, after which the iteration
-//             rises monotonically to tau*.
-//   phase k : one read-only pass over P_raw per further fixed-point step, until no column's count
-//             changes.  The new thresholds are stored in `thr`; the soft threshold itself is
-//             applied lazily by the readers (gradient kernel, next update, sp_psgd_finalize), so
-//             the prox costs no extra write pass.
-struct UpArgs {
-    double *P, *G;
-    int n_orders, d, k;
-    double c, den, strength;
-    int reg;
-    double *thr;      // [n_orders*k] in: thresholds the stored matrix still has to be shrunk by; out: new ones
-    double *psum, *pcnt;   // [nblk][n_orders*k] per-block partials
-    double *colres;   // [2][n_orders*k] reduced (sum, cnt)
-    int max_iter;
-    int nblk_part;     // blocks of the update pass (rows of psum / pcnt it wrote)
-    unsigned char *touched;   // [d] or NULL: rows with a nonzero gradient (others skip the G read / zero)
-    // band buffer of the squared-l1,2 selection: the values |p| within +-UP_BAND_DELTA of the
-    // PREDICTED threshold (previous threshold x strength ratio) are collected during the update pass,
-    // so that the fixed point can be located exactly without further passes over P
-    double *band;      // [ncol][UP_BAND_CAP]
-    int *band_n;       // [ncol] (zeroed before the launch)  + [ncol] fallback flag at band_n[ncol]
-    double *state;     // persistent: [0] previous strength, [1] calls so far, [2]/[3] band hits / generic
-                       // (debug), [4] band half-width, [8 + c] threshold before the previous call (trend)
-};
-
-constexpr int UP_BAND_CAP = 2048;
-constexpr int UP_PART_MAX = 148 * 8;          // most blocks of the update pass (rows of the partial sums)
-// doubles of the fused kernel's work buffer in front of its persistent tail: partial sums / counts
-// [UP_PART_MAX][ncol] each, reduced (sum, cnt) [2][ncol]
-static inline size_t up_tail_offset(size_t ncol) { return 2 * (size_t)UP_PART_MAX * ncol + 2 * ncol + 64; }
-constexpr double UP_BAND_DELTA = 0.02;   // initial half-width; adapted (state[4]): /2 on overflow, x2 when the iterate leaves
-
-constexpr int UP_THREADS = 512;
-
-__device__ __forceinline__ void block_col_reduce(double lsum, double lcnt, double *ssum, double *scnt, int tpr,
-                                                 int rpp, double *osum, double *ocnt, int col0, int k) {
-    const int tid = threadIdx.x;
-    ssum[tid] = lsum; scnt[tid] = lcnt;
-    __syncthreads();
-    if (tid < tpr && col0 + tid < k) {                       // fixed-order combine over the block's rows
-        double s = 0.0, n = 0.0;
-        for (int r = 0; r < rpp; r++) { s += ssum[r * tpr + tid]; n += scnt[r * tpr + tid]; }
-        osum[col0 + tid] = s;
-        ocnt[col0 + tid] = n;
-    }
-    __syncthreads();
-}
-
-// predicted threshold of column c: geometric continuation of the last two thresholds (the
-// thresholds decay smoothly while P sparsifies), or the strength ratio when only one is known
-__device__ __forceinline__ double up_predict(const UpArgs &a, int c, double th_old) {
-    const int ncol = a.n_orders * a.k;
-    const double older = a.state[8 + c];
-    double ratio = a.strength / a.state[0];
-    if (a.state[1] >= 2.0 && older > 0.0) ratio = th_old / older;
-    if (ratio < 0.5) ratio = 0.5;
-    if (ratio > 2.0) ratio = 2.0;
-    (void)ncol;
-    return th_old * ratio;
-}
-
-// phase 0: fused SGD update + statistics above the band / at the warm-start thresholds + band
-// collection.  Runs either inside the cooperative kernel (legacy path) or as its own streaming
-// kernel with many resident blocks (psgd_update_stats_kernel).
-__device__ __forceinline__ void up_phase0(const UpArgs &a, double *ssum, double *scnt) {
-    const int tid = threadIdx.x, T = blockDim.x, nblk = gridDim.x, k = a.k, d = a.d;
-    const int ncol = a.n_orders * k;
-    const int tpr = k < T ? k : T;                   // threads per row (host guarantees k <= T)
-    const int rpp = T / tpr;
-    const int col = tid % tpr, row0 = tid / tpr;
-    const bool worker = tid < tpr * rpp;
-    const bool sel = a.reg == SP_REG_SQL12;
-    // ---- phase 0: fused SGD update (+ statistics at the warm-start thresholds)
-    for (int o = 0; o < a.n_orders; o++) {
-        double *P = a.P + (size_t)o * d * k, *G = a.G + (size_t)o * d * k;
-        const double th_old = worker ? a.thr[o * k + col] : 0.0;
-        double lsum = 0.0, lcnt = 0.0;
-        // statistics threshold: th_old without a band; the band's upper edge with one
-        const double s_prev = a.state[0];
-        const bool band_on = sel && s_prev > 0.0 && a.strength > 0.0 && th_old > 0.0;
-        const double tau_pred = band_on ? up_predict(a, o * k + col, th_old) : 0.0;
-        const double bdelta = a.state[4] > 0.0 ? a.state[4] : UP_BAND_DELTA;
-        const double b_hi = band_on ? tau_pred * (1.0 + bdelta) : th_old;
-        const double b_lo = band_on ? tau_pred * (1.0 - bdelta) : th_old;
-        double *bandc = a.band + (size_t)(o * k + col) * UP_BAND_CAP;
-        int *bandn = a.band_n + (o * k + col);
-        if (worker) {
-            const long long step = (long long)nblk * rpp;
-            long long r = (long long)blockIdx.x * rpp + row0;
-            const unsigned char *tch = a.touched;
-            for (; r + 3 * step < d; r += 4 * step) {     // 8 independent loads in flight per thread
-                double pv[4], gv[4];
-                bool tv[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) tv[u] = tch == nullptr || tch[r + u * step] != 0;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const size_t e = (size_t)(r + u * step) * k + col;
-                    pv[u] = P[e]; gv[u] = tv[u] ? G[e] : 0.0;   // untouched rows: gradient is exactly 0
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const size_t e = (size_t)(r + u * step) * k + col;
-                    double p = sp_soft_threshold(pv[u], th_old);
-                    const double g = gv[u] * a.c;     // grad *= eta / batch
-                    p = p - g;                        // P -= grad
-                    p = p / a.den;                    // P /= 1 + eta*beta
-                    P[e] = p;
-                    if (tv[u]) G[e] = 0.0;
-                    const double v = fabs(p);
-                    if (sel && v > b_hi && v > 0.0) { lsum += v; lcnt += 1.0; }
-                    else if (band_on && v > b_lo) {
-                        const int bi = atomicAdd(bandn, 1);
-                        if (bi < UP_BAND_CAP) bandc[bi] = v;
-                    }
-                }
-            }
-            for (; r < d; r += step) {
-                const size_t e = (size_t)r * k + col;
-                const bool tv = tch == nullptr || tch[r] != 0;
-                double p = sp_soft_threshold(P[e], th_old);
-                const double g = (tv ? G[e] : 0.0) * a.c;
-                p = p - g;
-                p = p / a.den;
-                P[e] = p;
-                if (tv) G[e] = 0.0;
-                const double v = fabs(p);
-                if (sel && v > b_hi && v > 0.0) { lsum += v; lcnt += 1.0; }
-                else if (band_on && v > b_lo) {
-                    const int bi = atomicAdd(bandn, 1);
-                    if (bi < UP_BAND_CAP) bandc[bi] = v;
-                }
-            }
-        }
-        if (sel)
-            block_col_reduce(lsum, lcnt, ssum, scnt, tpr, rpp, a.psum + (size_t)blockIdx.x * ncol + o * k,
-                             a.pcnt + (size_t)blockIdx.x * ncol + o * k, 0, k);
-    }
-}
-
-__global__ void __launch_bounds__(256, 4) psgd_update_stats_kernel(const UpArgs a) {
-    __shared__ double ssum[256], scnt[256];
-    up_phase0(a, ssum, scnt);
-}
-
-__global__ void __launch_bounds__(UP_THREADS) psgd_update_prox_kernel(const UpArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double ssum[UP_THREADS], scnt[UP_THREADS];
-    __shared__ int s_changed;
-    const int tid = threadIdx.x, T = UP_THREADS, nblk = gridDim.x, k = a.k, d = a.d;
-    const int ncol = a.n_orders * k;
-    const int tpr = k < T ? k : T;                   // threads per row (host guarantees k <= T)
-    const int rpp = T / tpr;
-    const int col = tid % tpr, row0 = tid / tpr;
-    const bool worker = tid < tpr * rpp;
-    const bool sel = a.reg == SP_REG_SQL12;
-    int npart = a.nblk_part;                         // rows of psum / pcnt the update pass wrote
-    if (npart == 0) {                                // wide model: update pass here
-        up_phase0(a, ssum, scnt);
-        npart = nblk;
-        grid.sync();
-    }
-    if (a.touched != nullptr) {                       // (the update pass, their only reader, is a finished launch)
-        for (size_t r = (size_t)blockIdx.x * T + tid; r < (size_t)((d + 7) / 8); r += (size_t)nblk * T)
-            reinterpret_cast<unsigned long long *>(a.touched)[r] = 0ull;
-    }
-    if (!sel) {                                       // l1: threshold = strength for every column
-        if (blockIdx.x == 0) for (int cidx = tid; cidx < ncol; cidx += T) a.thr[cidx] = a.strength;
-        return;
-    }
-    // ---- band path: locate every column's fixed point from (statistics above the band) + (the
-    //      band's values), no further pass over P.  Any column that cannot (no prediction yet, band
-    //      overflow, iterate leaves the band) sends the whole launch to the generic passes below,
-    //      which start from the same statistics.
-    {
-        __shared__ double sband[UP_BAND_CAP], spref[UP_BAND_CAP];
-        __shared__ int s_m;
-        int *fallback = a.band_n + ncol;              // [0] any column failed, [1] a band overflowed
-        const double bdelta = a.state[4] > 0.0 ? a.state[4] : UP_BAND_DELTA;
-        const double s_prev = a.state[0];
-        const bool band_on = s_prev > 0.0 && a.strength > 0.0;
-        if (!band_on) {
-            if (blockIdx.x == 0 && tid == 0) *fallback = 1;
-        } else {
-            for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
-                // statistics above the band (fixed-order reduction of the per-block partials)
-                double s = 0.0, n = 0.0;
-                for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
-                ssum[tid] = s; scnt[tid] = n;
-                __syncthreads();
-                for (int off = T / 2; off > 0; off >>= 1) {
-                    if (tid < off) { ssum[tid] += ssum[tid + off]; scnt[tid] += scnt[tid + off]; }
-                    __syncthreads();
-                }
-                const double sumA = ssum[0], cntA = scnt[0];
-                __syncthreads();
-                const int nbv = a.band_n[cidx];
-                const double th_old = a.thr[cidx];
-                const double tau_pred = up_predict(a, cidx, th_old);
-                const double b_hi = tau_pred * (1.0 + bdelta), b_lo = tau_pred * (1.0 - bdelta);
-                bool ok = th_old > 0.0 && nbv <= UP_BAND_CAP;
-                if (nbv > UP_BAND_CAP && tid == 0) fallback[1] = 1;
-                if (ok) {
-                    // sort the band descending (bitonic, padded with -1) so that sums are order-free
-                    int np2 = 1;
-                    while (np2 < nbv) np2 <<= 1;
-                    for (int q = tid; q < np2; q += T) sband[q] = q < nbv ? a.band[(size_t)cidx * UP_BAND_CAP + q] : -1.0;
-                    __syncthreads();
-                    for (int kk = 2; kk <= np2; kk <<= 1)
-                        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                            for (int q = tid; q < np2; q += T) {
-                                const int x = q ^ jj;
-                                if (x > q) {
-                                    const double va = sband[q], vb = sband[x];
-                                    const bool desc = (q & kk) == 0;
-                                    if (desc ? (va < vb) : (va > vb)) { sband[q] = vb; sband[x] = va; }
-                                }
-                            }
-                            __syncthreads();
-                        }
-                    // inclusive prefix sums of the sorted values (fixed order: chunk per thread, then
-                    // the chunk totals scanned by one thread)
-                    {
-                        const int per = (np2 + T - 1) / T;
-                        const int q0 = tid * per, q1 = min(np2, q0 + per);
-                        double acc = 0.0;
-                        for (int q = q0; q < q1; q++) acc += (q < nbv) ? sband[q] : 0.0;
-                        ssum[tid] = acc;
-                        __syncthreads();
-                        if (tid == 0) {
-                            double run = 0.0;
-                            for (int b = 0; b < T; b++) { const double v = ssum[b]; ssum[b] = run; run += v; }
-                        }
-                        __syncthreads();
-                        acc = ssum[tid];
-                        for (int q = q0; q < q1; q++) { acc += (q < nbv) ? sband[q] : 0.0; spref[q] = acc; }
-                        __syncthreads();
-                    }
-                    if (tid == 0) {
-                        // Michelot iteration on (statistics above the band) + (band prefix)
-                        double tau = b_hi;
-                        int m_prev = -1;
-                        bool good = true;
-                        double thr_new = 0.0;
-                        for (int it = 0; it < 200; it++) {
-                            int lo_i = 0, hi_i = nbv;                  // m = #{band > tau} (sorted descending)
-                            while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (sband[mid] > tau) lo_i = mid + 1; else hi_i = mid; }
-                            const int m = lo_i;
-                            const double sum = m > 0 ? sumA + spref[m - 1] : sumA;
-                            const double cnt = cntA + (double)m;
-                            const double tnew = 2.0 * a.strength * sum / (1.0 + 2.0 * a.strength * cnt);
-                            if (!(tnew > b_lo) || tnew > b_hi) { good = false; break; }
-                            if (m == m_prev) { thr_new = tnew; break; }
-                            if (it == 199) good = false;
-                            m_prev = m;
-                            tau = tnew;
-                        }
-                        s_m = good ? 1 : 0;
-                        if (good) a.colres[cidx] = thr_new;          // parked until every column is known to be good
-                    }
-                    __syncthreads();
-                    ok = s_m != 0;
-                    __syncthreads();
-                }
-                if (!ok && tid == 0) *fallback = 1;
-            }
-        }
-        grid.sync();
-        const bool fb = *reinterpret_cast<volatile int *>(fallback) != 0;
-        // (every block is past its reads of the trend state: it can be advanced now)
-        if (blockIdx.x == 0) {
-            for (int cidx = tid; cidx < ncol; cidx += T) a.state[8 + cidx] = a.thr[cidx];
-            if (tid == 0) {
-                a.state[0] = a.strength; a.state[1] = a.state[1] + 1.0;
-                a.state[fb ? 3 : 2] += 1.0;                 // (debug counters: band hits / generic passes)
-                if (fb && band_on) {                        // adapt the half-width
-                    const bool over = reinterpret_cast<volatile int *>(fallback)[1] != 0;
-                    double nd = over ? bdelta * 0.5 : bdelta * 2.0;
-                    if (nd < 0.002) nd = 0.002;
-                    if (nd > 0.1) nd = 0.1;
-                    a.state[4] = nd;
-                }
-            }
-        }
-        if (!fb) {
-            if (blockIdx.x == 0) {
-                __syncthreads();
-                for (int cidx = tid; cidx < ncol; cidx += T) a.thr[cidx] = a.colres[cidx];
-            }
-            return;
-        }
-    }
-    double prev_cnt[4] = {-1.0, -1.0, -1.0, -1.0};   // per owned column (ncol <= 4*T)
-    for (int it = 0; it < a.max_iter; it++) {
-        grid.sync();
-        // ---- reduce the per-block partials: block b owns columns b, b+nblk, ...
-        for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
-            double s = 0.0, n = 0.0;
-            for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
-            ssum[tid] = s; scnt[tid] = n;
-            __syncthreads();
-            for (int off = T / 2; off > 0; off >>= 1) {
-                if (tid < off) { ssum[tid] += ssum[tid + off]; scnt[tid] += scnt[tid + off]; }
-                __syncthreads();
-            }
-            if (tid == 0) { a.colres[cidx] = ssum[0]; a.colres[ncol + cidx] = scnt[0]; }
-            __syncthreads();
-        }
-        grid.sync();
-        npart = nblk;                                  // from now on the partials come from this grid's passes
-        // ---- new thresholds (identical in every block) and the convergence test
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        int slot = 0;
-        for (int cidx = tid; cidx < ncol; cidx += T, slot++) {
-            const double n = a.colres[ncol + cidx];
-            if (n != prev_cnt[slot]) s_changed = 1;
-            prev_cnt[slot] = n;
-        }
-        __syncthreads();
-        const bool changed = s_changed != 0;
-        if (blockIdx.x == 0)
-            for (int cidx = tid; cidx < ncol; cidx += T) {
-                const double s = a.colres[cidx], n = a.colres[ncol + cidx];
-                a.thr[cidx] = 2.0 * a.strength * s / (1.0 + 2.0 * a.strength * n);   // = 2*strength*S (utils.py:69-70)
-            }
-        if (!changed && it > 0) break;
-        // ---- read-only pass at the new thresholds
-        for (int o = 0; o < a.n_orders; o++) {
-            const double *P = a.P + (size_t)o * d * k;
-            double tau = 0.0;
-            if (worker) {
-                const double s = a.colres[o * k + col], n = a.colres[ncol + o * k + col];
-                tau = 2.0 * a.strength * s / (1.0 + 2.0 * a.strength * n);
-            }
-            double lsum = 0.0, lcnt = 0.0;
-            if (worker) {
-                long long r = (long long)blockIdx.x * rpp + row0;
-                const long long step = (long long)nblk * rpp;
-                for (; r + 3 * step < d; r += 4 * step) {          // 4 independent loads in flight
-                    const double v0 = fabs(P[(size_t)r * k + col]), v1 = fabs(P[(size_t)(r + step) * k + col]);
-                    const double v2 = fabs(P[(size_t)(r + 2 * step) * k + col]), v3 = fabs(P[(size_t)(r + 3 * step) * k + col]);
-                    if (v0 > tau && v0 > 0.0) { lsum += v0; lcnt += 1.0; }
-                    if (v1 > tau && v1 > 0.0) { lsum += v1; lcnt += 1.0; }
-                    if (v2 > tau && v2 > 0.0) { lsum += v2; lcnt += 1.0; }
-                    if (v3 > tau && v3 > 0.0) { lsum += v3; lcnt += 1.0; }
-                }
-                for (; r < d; r += step) {
-                    const double v = fabs(P[(size_t)r * k + col]);
-                    if (v > tau && v > 0.0) { lsum += v; lcnt += 1.0; }
-                }
-            }
-            block_col_reduce(lsum, lcnt, ssum, scnt, tpr, rpp, a.psum + (size_t)blockIdx.x * ncol + o * k,
-                             a.pcnt + (size_t)blockIdx.x * ncol + o * k, 0, k);
-        }
-    }
-}
-
-// P <- soft_threshold(P_raw, thr) in place; thr <- 0 (the stored matrix is the model again)
-__global__ void psgd_finalize_kernel(double *__restrict__ P, int n_orders, int d, int k, double *thr) {
-    const size_t n = (size_t)n_orders * d * k, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        const int o = (int)(e / ((size_t)d * k));
-        P[e] = sp_soft_threshold(P[e], thr[o * k + (int)(e % k)]);
-    }
-}
-__global__ void zero_kernel(double *p, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
-}
-
-int up_grid(int *nblk_out) {
-    int dev = 0, sms = 0, occ = 0;
-    SP_CUDA(cudaGetDevice(&dev));
-    SP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psgd_update_prox_kernel, UP_THREADS, 0));
-    if (occ < 1) { sp_set_error("psgd_update_prox_kernel does not fit on an SM"); return SP_ERR_CUDA; }
-    if (occ > 2) occ = 2;
-    *nblk_out = sms * occ;
-    return SP_OK;
-}
-
 int ew_blocks(size_t n) {
     size_t b = (n + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -784,10 +373,7 @@ int run_select(const double *V, int rows, int cols, double strength, double *wor
 extern "C" size_t sp_prox_work_doubles(int d, int k) {
     // norms[d] (squaredl21) + tau/S [2*max(k,1)] + partials 2*nblk*cols (nblk <= 148*4) + flags
     const size_t cols = (size_t)(k > 1 ? k : 1);
-    // the psgd epoch additionally keeps [n_orders*k] thresholds + the fused kernel's partials in
-    // front (n_orders <= SP_MAXDEG-1)
-    return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64 + (size_t)(SP_MAXDEG) * cols * (2 * 148 * 2 + 3) +
-           (size_t)(d + 7) / 8 + 1 + up_tail_offset((size_t)SP_MAXDEG * cols) + (size_t)(SP_MAXDEG) * cols * (UP_BAND_CAP + 4) + 128;
+    return (size_t)d + 2 * cols + 2 * (size_t)148 * 4 * cols + 64;
 }
 
 extern "C" int sp_get_eta(int lr, double eta0, double alpha, double beta, double power_t, int64_t it,
@@ -808,17 +394,10 @@ extern "C" int sp_get_eta(int lr, double eta0, double alpha, double beta, double
     return SP_OK;
 }
 
-static int dbg_flags() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("SPARSEPOLY_B200_DEBUG"); v = e ? atoi(e) : 0; }
-    return v;
-}
-
 template <int DEG, int NORD>
 static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, const double *y,
                        const double *P, const double *w, const double *lams, int loss, int fit_linear,
-                       const int32_t *idx, int b0, int b1, double *gP, double *gw, double *ls,
-                       const double *thr, unsigned char *touched) {
+                       const int32_t *idx, int b0, int b1, double *gP, double *gw, double *ls) {
     const int G = k <= 16 ? 16 : 32;
     const int per_block = PG_THREADS / G;
     long long blocks = ((long long)(b1 - b0) + per_block - 1) / per_block;
@@ -835,8 +414,8 @@ static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, cons
             if (e_ != cudaSuccess) return sp_check_cuda(e_, "cudaFuncSetAttribute(psgd_grad_kernel)"); \
         }                                                                                         \
         psgd_grad_kernel<DEG, NORD, GG, KC><<<(int)blocks, PG_THREADS, sm, st>>>(k, d, ds->csr_indptr, \
-            ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls, thr, dbg_flags(), \
-            ds->feat_hot, ds->n_hot_feat, ds->hot_feat, touched); \
+            ds->csr_indices, ds->csr_data, y, P, w, lams, loss, fit_linear, idx, b0, b1, gP, gw, ls, \
+            ds->feat_hot, ds->n_hot_feat, ds->hot_feat); \
     }
     sp_prof_begin(SP_PROF_PSGD_GRAD, st);
     if (k <= 16) SP_GRAD(16, 1)
@@ -853,8 +432,7 @@ static int launch_grad(cudaStream_t st, int k, int d, const sp_dataset *ds, cons
 extern "C" int sp_psgd_grad(const sp_dataset *ds, const double *y, const double *P_odk, int n_orders,
                             int k, const double *w, const double *lams, int degree, int loss,
                             int fit_linear, const int32_t *idx_samples, int b0, int b1,
-                            double *grad_P, double *grad_w, double *loss_sum,
-                            const double *col_thresh, unsigned char *touched, sp_stream stream) {
+                            double *grad_P, double *grad_w, double *loss_sum, sp_stream stream) {
     if (!ds || !ds->csr_indptr || !y || !P_odk || !w || !lams || !idx_samples || !grad_P || !grad_w ||
         !loss_sum || k <= 0 || b0 < 0 || b1 < b0) {
         sp_set_error("sp_psgd_grad: invalid argument");
@@ -873,7 +451,7 @@ extern "C" int sp_psgd_grad(const sp_dataset *ds, const double *y, const double 
     cudaStream_t st = (cudaStream_t)stream;
     const int d = ds->n_features;
     const bool ex = n_orders > 1;
-#define SP_CALL(D, N) return launch_grad<D, N>(st, k, d, ds, y, P_odk, w, lams, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum, col_thresh, touched)
+#define SP_CALL(D, N) return launch_grad<D, N>(st, k, d, ds, y, P_odk, w, lams, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum)
     switch (degree) {
     case 2: SP_CALL(2, 1);
     case 3: if (ex) SP_CALL(3, 2); else SP_CALL(3, 1);
@@ -955,84 +533,6 @@ extern "C" int sp_prox(double *P_dk, int d, int k, int reg, double strength, dou
 }
 
 
-extern "C" size_t sp_psgd_lazy_work_doubles(int n_orders, int k) {
-    // per-block partials 2*nblk*ncol (nblk <= 148*2) + reduced 2*ncol
-    const size_t ncol = (size_t)n_orders * k;
-    // + persistent tail: state[2] | band counters | band[ncol][UP_BAND_CAP]  (must be zero-initialised
-    // before the first sp_psgd_update_prox call of a fit)
-    return up_tail_offset(ncol) + 8 + ncol + (ncol + 3) / 2 + 1 + ncol * (size_t)UP_BAND_CAP + 8;
-}
-
-extern "C" int sp_psgd_update_prox(double *P_odk, double *grad_P, int n_orders, int d, int k, double eta_P,
-                                   double beta, int batch, int reg, double strength, double *col_thresh,
-                                   double *work, unsigned char *touched, sp_stream stream) {
-    if (!P_odk || !grad_P || !col_thresh || !work || batch <= 0 || n_orders <= 0 || k <= 0) {
-        sp_set_error("sp_psgd_update_prox: invalid argument");
-        return SP_ERR_INVALID;
-    }
-    if (reg != SP_REG_L1 && reg != SP_REG_SQL12) {
-        sp_set_error("sp_psgd_update_prox handles l1 and squaredl12 only (use sp_psgd_step + sp_prox)");
-        return SP_ERR_UNSUPPORTED;
-    }
-    if (k > UP_THREADS || n_orders * k > 4 * UP_THREADS) {
-        sp_set_error("sp_psgd_update_prox: n_components=%d too large", k);
-        return SP_ERR_UNSUPPORTED;
-    }
-    if (d == 0) return SP_OK;
-    int nblk = 0;
-    int rc = up_grid(&nblk);
-    if (rc) return rc;
-    const int rpp = UP_THREADS / k;
-    const long long need = ((long long)d + rpp - 1) / rpp;
-    if (nblk > need) nblk = (int)need;
-    const size_t ncol = (size_t)n_orders * k;
-    // update pass: plain streaming launch, 256 threads, up to UP_PART_MAX blocks
-    const int rppA = 256 / (k < 256 ? k : 256);
-    long long nblkA = ((long long)d + rppA - 1) / rppA;
-    if (nblkA > UP_PART_MAX) nblkA = UP_PART_MAX;
-    if (k > 256) nblkA = 0;                          // (wide models: update pass inside the cooperative kernel)
-    UpArgs a;
-    a.P = P_odk; a.G = grad_P; a.n_orders = n_orders; a.d = d; a.k = k;
-    a.c = eta_P / batch; a.den = 1.0 + eta_P * beta; a.strength = strength; a.reg = reg;
-    a.thr = col_thresh;
-    a.psum = work; a.pcnt = work + (size_t)UP_PART_MAX * ncol; a.colres = a.pcnt + (size_t)UP_PART_MAX * ncol;
-    a.nblk_part = (int)nblkA;
-    // persistent tail of the work buffer: state | band counters | band[ncol][UP_BAND_CAP]
-    {
-        double *tail = work + up_tail_offset(ncol);
-        a.state = tail;                                                  // [8 + ncol]
-        a.band_n = reinterpret_cast<int *>(tail + 8 + ncol);             // [ncol + 2] ints
-        a.band = tail + 8 + ncol + (ncol + 3) / 2 + 1;
-    }
-    a.max_iter = (dbg_flags() & 2) ? ((dbg_flags() >> 4) & 15) : 500;   // (debug: cap the selection passes)
-    a.touched = touched;
-    void *args[] = {(void *)&a};
-    cudaStream_t st = (cudaStream_t)stream;
-    SP_CUDA(cudaMemsetAsync(a.band_n, 0, sizeof(int) * (ncol + 2), st));
-    sp_prof_begin(SP_PROF_PROX, st);
-    if (nblkA > 0) {
-        psgd_update_stats_kernel<<<(int)nblkA, 256, 0, st>>>(a);
-        cudaError_t e0 = cudaGetLastError();
-        if (e0 != cudaSuccess) { sp_prof_end(st); return sp_check_cuda(e0, "psgd_update_stats_kernel launch"); }
-    }
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)psgd_update_prox_kernel, dim3(nblk), dim3(UP_THREADS), args, 0, st);
-    sp_prof_end(st);
-    return sp_check_cuda(e, "psgd_update_prox_kernel launch");
-}
-
-extern "C" int sp_psgd_finalize(double *P_odk, int n_orders, int d, int k, double *col_thresh, sp_stream stream) {
-    if (!P_odk || !col_thresh) { sp_set_error("sp_psgd_finalize: invalid argument"); return SP_ERR_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)n_orders * d * k;
-    if (n > 0) {
-        psgd_finalize_kernel<<<ew_blocks(n), 256, 0, st>>>(P_odk, n_orders, d, k, col_thresh);
-        SP_LAUNCH_CHECK("psgd_finalize_kernel");
-    }
-    zero_kernel<<<1, 256, 0, st>>>(col_thresh, n_orders * k);
-    SP_LAUNCH_CHECK("zero_kernel");
-    return SP_OK;
-}
-
 extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_orders, int k,
                              double *w, const double *lams, int degree, double alpha, double beta,
                              double gamma, int reg, int loss, double *grad_P, double *grad_w,
@@ -1041,50 +541,24 @@ extern "C" int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_od
                              double *loss_sum, double *work, sp_stream stream) {
     if (!ds || !it_io_host || batch_size <= 0 || !work) { sp_set_error("sp_psgd_epoch: invalid argument"); return SP_ERR_INVALID; }
     const int n = ds->n_samples, d = ds->n_features;
-    const bool lazy = (reg == SP_REG_L1 || reg == SP_REG_SQL12) && k <= UP_THREADS && n_orders * k <= 4 * UP_THREADS;
-    // work layout: [n_orders*k] lazy thresholds | [ceil(d/8)] doubles of touched-row flags | scratch
-    double *thr = work;
-    unsigned char *touched = lazy ? reinterpret_cast<unsigned char *>(work + (size_t)n_orders * k) : nullptr;
-    double *scratch = work + (size_t)n_orders * k + (size_t)(d + 7) / 8;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (lazy) {
-        zero_kernel<<<ew_blocks((size_t)n_orders * k + (size_t)(d + 7) / 8), 256, 0, st>>>(
-            thr, (int)((size_t)n_orders * k + (size_t)(d + 7) / 8));
-        SP_LAUNCH_CHECK("zero_kernel");
-        // persistent selection state (previous strength) of sp_psgd_update_prox: none yet
-        const size_t ncol = (size_t)n_orders * k;
-        SP_CUDA(cudaMemsetAsync(scratch + up_tail_offset(ncol), 0, (8 + ncol) * sizeof(double), st));
-    }
     int64_t it = *it_io_host;
     for (int b0 = 0; b0 < n; b0 += batch_size) {           // psgd.py:150-198
         const int b1 = (n - b0 < batch_size) ? n : b0 + batch_size;
         int rc = sp_psgd_grad(ds, y, P_odk, n_orders, k, w, lams, degree, loss, fit_linear, idx_samples,
-                              b0, b1, grad_P, grad_w, loss_sum, lazy ? thr : nullptr, touched, stream);
+                              b0, b1, grad_P, grad_w, loss_sum, stream);
         if (rc) return rc;
         double eta_P, eta_w;
         rc = sp_get_eta(learning_rate, eta0, alpha, beta, power_t, it, &eta_P, &eta_w);
         if (rc) return rc;
         const double strength = gamma * eta_P / (1 + eta_P * beta);   // psgd.py:122
-        if (lazy) {
-            rc = sp_psgd_step(nullptr, nullptr, w, grad_w, 0, d, k, eta_P, eta_w, alpha, beta, b1 - b0, fit_linear, stream);
+        rc = sp_psgd_step(P_odk, grad_P, w, grad_w, n_orders, d, k, eta_P, eta_w, alpha, beta, b1 - b0,
+                          fit_linear, stream);
+        if (rc) return rc;
+        for (int o = 0; o < n_orders; o++) {                // psgd.py:119-122
+            rc = sp_prox(P_odk + (size_t)o * d * k, d, k, reg, strength, work, stream);
             if (rc) return rc;
-            rc = sp_psgd_update_prox(P_odk, grad_P, n_orders, d, k, eta_P, beta, b1 - b0, reg, strength, thr, scratch,
-                                     touched, stream);
-            if (rc) return rc;
-        } else {
-            rc = sp_psgd_step(P_odk, grad_P, w, grad_w, n_orders, d, k, eta_P, eta_w, alpha, beta, b1 - b0,
-                              fit_linear, stream);
-            if (rc) return rc;
-            for (int o = 0; o < n_orders; o++) {            // psgd.py:119-122
-                rc = sp_prox(P_odk + (size_t)o * d * k, d, k, reg, strength, scratch, stream);
-                if (rc) return rc;
-            }
         }
         it++;
-    }
-    if (lazy) {
-        int rc = sp_psgd_finalize(P_odk, n_orders, d, k, thr, stream);
-        if (rc) return rc;
     }
     *it_io_host = it;
     return SP_OK;

@@ -49,7 +49,7 @@ constexpr int BAND_CAP = SP_PSGD_BAND_CAP;          // band values per column an
 constexpr int BAND_TOTAL = 2048;                    // band values per column over all ranks (shared memory)
 constexpr int STAT_PART_MAX = 148 * 8;              // most blocks of the statistics pass
 constexpr double BAND_DELTA = 0.02;
-constexpr unsigned long long SPIN_TIMEOUT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 __device__ __forceinline__ double st_true(double r, double T, double invC) {
     double m = fabs(r) - T;                                  // value = soft_threshold(raw, T) / C
@@ -562,6 +562,7 @@ __device__ __forceinline__ void x_wait(const XArgs &x, int r) {
     const uint64_t *f = x.my_flags + (size_t)x.chan * SP_MAX_RANKS + r;
     const unsigned long long t0 = now_ns();
     while (flag_load(f) < x.seq) {
+        if (*reinterpret_cast<volatile int *>(x.err) != 0) break;      // a wait already timed out: do not stack timeouts
         __nanosleep(64);
         if (now_ns() - t0 > SPIN_TIMEOUT_NS) { *x.err = 1; break; }
     }

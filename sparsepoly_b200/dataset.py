@@ -98,7 +98,7 @@ def csr_to_csc_device(n, d, indptr, indices, data):
 class DeviceDataset:
     """CSR and/or CSC copy of X in device memory + the sp_dataset struct handed to the C ABI."""
 
-    def __init__(self, X, need_csr=True, need_csc=True, device=None, pin=False):
+    def __init__(self, X, need_csr=True, need_csc=True, device=None, pin=False, hot_features=True):
         self.device = _device(device)
         self.n_samples, self.n_features = int(X.shape[0]), int(X.shape[1])
         self.h2d_bytes = 0
@@ -123,8 +123,12 @@ class DeviceDataset:
         if self.csc is not None:
             s.csc_indptr, s.csc_indices, s.csc_data = (t.data_ptr() for t in self.csc)
         self.struct = s
-        if self.csr is not None and not need_csc:
+        if self.csr is not None and not need_csc and hot_features:
             self.mark_hot_features()
+
+    def max_row_nnz(self):
+        ip = self.csr[0]
+        return int((ip[1:] - ip[:-1]).max().item()) if self.n_samples else 0
 
     def mark_hot_features(self, min_density=1.0 / 16, max_hot=16):
         """Dense features (present in >= 1/16 of the rows): sp_psgd_grad pre-reduces their gradient

@@ -5,7 +5,57 @@ and batch prediction.  pcd / pbcd are sequential in the coordinate order and sta
 One process per GPU (torchrun); torch.distributed (NCCL over NVLink on the B200 box, gloo in the
 CPU tests) is the only collective provider.
 """
+import contextlib
+
 import numpy as np
+
+_ACTIVE_GROUP = None
+
+
+def enable_sharding(group=None):
+    """Opt in: psgd fits (and sharded_predict) started after this call treat X, y as THIS rank's shard of
+    the samples and run over all ranks of `group` (default: the world group).  Sharding is never implied
+    by torch.distributed merely being initialised -- without this call every rank fits its own X."""
+    import torch.distributed as dist
+    global _ACTIVE_GROUP
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("enable_sharding needs an initialised torch.distributed process group")
+    _ACTIVE_GROUP = group if group is not None else dist.group.WORLD
+    return _ACTIVE_GROUP
+
+
+def disable_sharding():
+    global _ACTIVE_GROUP
+    _ACTIVE_GROUP = None
+
+
+@contextlib.contextmanager
+def sharded(group=None):
+    enable_sharding(group)
+    try:
+        yield
+    finally:
+        disable_sharding()
+
+
+def active_group():
+    """The process group psgd fits shard over, or None (single process, or sharding not enabled)."""
+    import torch.distributed as dist
+    if _ACTIVE_GROUP is None or not (dist.is_available() and dist.is_initialized()):
+        return None
+    return _ACTIVE_GROUP if dist.get_world_size(_ACTIVE_GROUP) > 1 else None
+
+
+def broadcast_arrays(arrays, group, src=0):
+    """Make rank `src`'s numpy arrays (in place) the arrays of every rank: sharded fits must start from
+    identical parameters whatever each rank's random_state drew."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    for a in arrays:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, src) if hasattr(dist, "get_global_rank") else src, group=group)
+        a[...] = t.cpu().numpy().reshape(a.shape)
 
 
 def local_batches(n_local, batch_size_global, world):
@@ -54,22 +104,26 @@ def global_sum(values, group=None):
     return t.tolist()
 
 
-def sharded_predict(estimator, X, group=None):
-    """Batch prediction with rows of X split over the ranks; every rank returns the full vector.
-    No collective on the compute path -- only the final gather of the outputs."""
+def sharded_predict(estimator, X_local, group=None, gather=True):
+    """Batch prediction (base.py:52-100 -> kernels.poly_predict, kernels.py:140-153) with the samples
+    sharded over the ranks: every rank scores ITS rows X_local with the replicated model -- no collective on
+    the compute path.  gather=True: the per-rank outputs are concatenated in rank order on every rank
+    (shards may differ in length); gather=False: the local scores only."""
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return estimator._predict(X)
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n = X.shape[0]
-    per = -(-n // world)
-    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    group = group if group is not None else active_group()
+    mine = np.ascontiguousarray(estimator._predict(X_local), dtype=np.float64)
+    if group is None or not gather:
+        return mine
+    world = dist.get_world_size(group)
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    mine = torch.zeros(per, dtype=torch.float64, device=dev)
-    if hi > lo:
-        part = estimator._predict(X[lo:hi])
-        mine[: hi - lo] = torch.from_numpy(np.ascontiguousarray(part)).to(dev)
-    out = torch.empty(world * per, dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(out, mine, group=group)
-    return out[:n].cpu().numpy()
+    n = torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(v.item()) for v in ns]
+    cap = max(max(ns), 1)
+    buf = torch.zeros(cap, dtype=torch.float64, device=dev)
+    buf[: mine.shape[0]] = torch.from_numpy(mine).to(dev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return np.concatenate([o[:m].cpu().numpy() for o, m in zip(outs, ns)])

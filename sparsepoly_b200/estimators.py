@@ -28,7 +28,7 @@ from sklearn.utils.validation import check_array, check_X_y
 
 from . import _lib, solvers
 from .dataset import DeviceDataset, SweepPlan, _device
-from .distributed import global_sum
+from .distributed import active_group, broadcast_arrays, global_sum
 
 REGRESSION_LOSSES = ("squared",)
 CLASSIFICATION_LOSSES = ("squared", "squared_hinge", "logistic")
@@ -48,10 +48,9 @@ _f64 = torch.float64
 
 
 def _process_group():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist.group.WORLD
-    return None
+    """Sharded psgd is opt-in (distributed.enable_sharding); an initialised torch.distributed alone
+    changes nothing."""
+    return active_group()
 
 
 class _SparsePolyBase(BaseEstimator, metaclass=ABCMeta):
@@ -91,6 +90,14 @@ class _SparsePolyBase(BaseEstimator, metaclass=ABCMeta):
             else:
                 raise ValueError("Lambdas must be initialized as ones (init_lambdas='ones') or as "
                                  "random +/- 1 (init_lambdas='random_signs').")
+
+    def __getstate__(self):
+        # device handles (ctypes structs with pointers, CUDA tensors) are per-fit scratch, not model state:
+        # a fitted estimator pickles / deep-copies like the reference's (P_, w_, lams_, ... are numpy)
+        state = dict(self.__dict__)
+        for key in ("_dev_state", "_y_pred_train"):
+            state.pop(key, None)
+        return state
 
     def _after_epoch(self, it, value, what, sync):
         """callback / verbose handling shared by the epoch loops; True = stop."""
@@ -362,15 +369,30 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
 
     # ---------------------------------------------------------------- psgd
     def _fit_psgd(self, X, y, rng, dev):
+        """sparse_factorization_machines.py:94-173.  l1 / squaredl12 run the planned path (psgd_plan.cu: gather
+        passes over a batch-CSC plan, touched rows only, sharded over peer memory); l21 / squaredl21 the
+        dense-gradient path (psgd.cu)."""
         n, d = X.shape
         k = self.n_components
         group = _process_group()
-        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev)
-        self._h2d_bytes = ds.h2d_bytes
         if self.learning_rate not in LEARNING_RATE:
             raise ValueError(f"learning_rate {self.learning_rate} is not supported."
                              f" Choose from {LEARNING_RATE}.")
         learning_rate = LEARNING_RATE[self.learning_rate]
+        world, rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            # replicas must start identical whatever each rank's random_state drew, and shards must be equal
+            it_arr = np.array([float(self.it_)])
+            broadcast_arrays([self.P_, self.w_, self.lams_, it_arr], group)
+            self.it_ = int(it_arr[0])
+            sizes = global_sum([float(n), float(n) ** 2], group)
+            if abs(sizes[1] * world - sizes[0] ** 2) > 0.5:
+                raise ValueError("sharded psgd needs the same number of samples on every rank")
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev,
+                           hot_features=self.regularizer not in solvers.PLANNED_REGS)
+        self._h2d_bytes = ds.h2d_bytes
         n_glob, nnz_glob = (global_sum([n, ds.nnz], group) if group is not None else (n, ds.nnz))
         if self.batch_size == "auto":
             batch_size = int(n_glob * d / nnz_glob)                          # :101-102
@@ -382,51 +404,88 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         y_dev = torch.from_numpy(y).to(dev)
         P_kd = torch.from_numpy(np.ascontiguousarray(self.P_)).to(dev)
         P = torch.stack([solvers.transpose(P_kd[o]) for o in range(P_kd.shape[0])])   # [n_orders, d, k]
+        del P_kd
         w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
         lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
-        grad_P = torch.zeros_like(P)
-        grad_w = torch.zeros(d, dtype=_f64, device=dev)
         loss_dev = torch.zeros(1, dtype=_f64, device=dev)
-        work = solvers.prox_work(d, k, dev)
+        planned = self.regularizer in solvers.PLANNED_REGS
+        if planned:
+            from .psgd_plan import PsgdContext, PsgdPlan
+            b_loc = max(1, batch_size // world)
+            plan = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
+            ctx = PsgdContext(plan, P.shape[0], k, self.degree, self.regularizer, self.loss, self.fit_linear, lams,
+                              group=group, inbox_cap=(min(plan.d_rows, b_loc * int(ds.max_row_nnz())) if self.shuffle else None))
+            ctx.load_model(P, w)
+            solvers.psgd_planned_begin(ctx)
+            self._psgd_stats = {"plan_bytes": plan.nbytes(), "minibatches": plan.n_minibatches,
+                                "columns_per_minibatch": plan.n_cols / max(plan.n_minibatches, 1)}
+            state = {"model_current": True}
+        else:
+            grad_P = torch.zeros_like(P)
+            grad_w = torch.zeros(d, dtype=_f64, device=dev)
+            work = solvers.prox_work(d, k, dev)
 
         def sync():
+            if planned and not state["model_current"]:
+                solvers.psgd_planned_end(ctx, 0, None, True)
+                state["model_current"] = True
+            if planned:
+                ctx.store_model(P, w)
             for o in range(P.shape[0]):
                 self.P_[o] = solvers.transpose(P[o]).cpu().numpy()
             self.w_[...] = w.cpu().numpy()
 
         converged, epoch = False, 0
         no_improvement_count, best_loss = 0, np.inf
-        for epoch in range(self.max_iter):
-            if self.shuffle:
-                rng.shuffle(indices_samples)
-                idx_dev.copy_(torch.from_numpy(indices_samples))
-            loss_dev.zero_()
-            self.it_ = solvers.psgd_epoch(ds, y_dev, P, w, lams, self.degree, self.alpha, self.beta,
-                                          self.gamma, self.regularizer, self.loss, grad_P, grad_w,
-                                          idx_dev, self.fit_linear, self.eta0, learning_rate,
-                                          self.power_t, batch_size, self.it_, loss_dev, work, group)
-            sum_loss = loss_dev.item()
-            if group is not None:
-                sum_loss = global_sum([sum_loss], group)[0]
-            sum_loss /= n_glob
-            if (self.callback is not None) and epoch % self.n_calls == 0:
-                sync()
-                if self.callback(self) is not None:
-                    break
-            if self.verbose:
-                print(f"Epoch {epoch+1} loss {sum_loss}")
-            if sum_loss > (best_loss - self.tol):
-                no_improvement_count += 1
-            else:
-                no_improvement_count = 0
-            if sum_loss < best_loss:
-                best_loss = sum_loss
-            if no_improvement_count >= self.n_iter_no_change:
+        try:
+            for epoch in range(self.max_iter):
+                if self.shuffle:
+                    rng.shuffle(indices_samples)
+                    idx_dev.copy_(torch.from_numpy(indices_samples))
+                    if planned:
+                        plan = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
+                        ctx.rebind(plan)
+                loss_dev.zero_()
+                if planned:
+                    self.it_ = solvers.psgd_planned_run(ctx, ds, plan, y_dev, idx_dev, self.alpha, self.beta, self.gamma,
+                                                        self.eta0, learning_rate, self.power_t, self.it_)
+                    state["model_current"] = False
+                    # the lazy scales only grow: fold them back into the storage long before they overflow
+                    big = not (1e-100 < ctx.struct.C < 1e100 and 1e-100 < ctx.struct.Cw < 1e100)
+                    solvers.psgd_planned_end(ctx, n, loss_dev, big)
+                    state["model_current"] = big
+                else:
+                    self.it_ = solvers.psgd_epoch(ds, y_dev, P, w, lams, self.degree, self.alpha, self.beta,
+                                                  self.gamma, self.regularizer, self.loss, grad_P, grad_w,
+                                                  idx_dev, self.fit_linear, self.eta0, learning_rate,
+                                                  self.power_t, batch_size, self.it_, loss_dev, work, group)
+                sum_loss = loss_dev.item()
+                if planned:
+                    ctx.check_peers()
+                if group is not None:
+                    sum_loss = global_sum([sum_loss], group)[0]
+                sum_loss /= n_glob
+                if (self.callback is not None) and epoch % self.n_calls == 0:
+                    sync()
+                    if self.callback(self) is not None:
+                        break
                 if self.verbose:
-                    print(f"Converged at iteration {epoch+1}")
-                converged = True
-                break
-        sync()
+                    print(f"Epoch {epoch+1} loss {sum_loss}")
+                if sum_loss > (best_loss - self.tol):
+                    no_improvement_count += 1
+                else:
+                    no_improvement_count = 0
+                if sum_loss < best_loss:
+                    best_loss = sum_loss
+                if no_improvement_count >= self.n_iter_no_change:
+                    if self.verbose:
+                        print(f"Converged at iteration {epoch+1}")
+                    converged = True
+                    break
+            sync()
+        finally:
+            if planned:
+                ctx.close()
         return converged, epoch
 
     # ---------------------------------------------------------------- public

@@ -304,7 +304,7 @@ class PsgdContext:
     peer-visible buffers (model shard, inboxes, statistics boxes, flags) live in one cudaMalloc slab per
     rank whose CUDA IPC handle is exchanged through the process group at construction."""
 
-    def __init__(self, plan, n_orders, k, degree, reg, loss, fit_linear, lams, group=None):
+    def __init__(self, plan, n_orders, k, degree, reg, loss, fit_linear, lams, group=None, inbox_cap=None):
         L = _lib.load()
         dev = plan.device
         self.plan_dims = (plan.max_chunks, plan.max_cols, plan.batch_local)
@@ -332,7 +332,7 @@ class PsgdContext:
             s.xwork = self.xwork.data_ptr()
         else:
             import torch.distributed as dist
-            cap = plan.inbox_cap
+            cap = max(plan.inbox_cap, int(inbox_cap or 0))        # (shuffle=True: bound for any sample order)
             sizes = [("P", ncolk * self.d_rows), ("w", self.d_rows), ("inbox_g", self.world * cap * ncolk),
                      ("inbox_w", self.world * cap), ("xwork", xw), ("flags", CHANNELS * MAX_RANKS), ("err", 2)]
             offs, at = {}, 0

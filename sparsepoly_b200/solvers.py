@@ -86,15 +86,13 @@ def prox(P_dk, reg, strength, work):
                             _stream()))
 
 
-def psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-              loss_sum, col_thresh=None, touched=None):
-    """psgd._pred + _update_grads for samples idx_samples[b0:b1] (psgd.py:47-91).  col_thresh:
-    thresholds of a lazily applied prox (see psgd_update_prox)."""
+def psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum):
+    """psgd._pred + _update_grads for samples idx_samples[b0:b1] (psgd.py:47-91), dense-gradient path."""
     n_orders, _, k = P_odk.shape
     _lib.check(_L().sp_psgd_grad(ds.ref(), _ptr(y), _ptr(P_odk), int(n_orders), int(k), _ptr(w),
                                  _ptr(lams), int(degree), _lib.LOSS_IDS[loss], int(bool(fit_linear)),
                                  _ptr(idx_samples), int(b0), int(b1), _ptr(grad_P), _ptr(grad_w),
-                                 _ptr(loss_sum), _ptr(col_thresh), _ptr(touched), _stream()))
+                                 _ptr(loss_sum), _stream()))
 
 
 def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_linear):
@@ -105,44 +103,19 @@ def psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, batch, fit_li
                                  int(batch), int(bool(fit_linear)), _stream()))
 
 
-LAZY_REGS = ("l1", "squaredl12")
-SPARSE_EXCHANGE_MAX_FRAC = 0.3      # above this fraction of touched rows the dense all-reduce is faster (measured: N=8, 50 % touched)
-
-
-def lazy_work(n_orders, k, device):
-    # zero-initialised: the tail holds the persistent selection state of sp_psgd_update_prox
-    return torch.zeros(int(_L().sp_psgd_lazy_work_doubles(int(n_orders), int(k))), dtype=_f64, device=device)
-
-
-def psgd_step_w(w, grad_w, eta_w, alpha, batch, fit_linear):
-    """The linear half of psgd._update_params (psgd.py:109-112) + zeroing of grad_w."""
-    _lib.check(_L().sp_psgd_step(None, None, _ptr(w), _ptr(grad_w), 0, int(w.shape[0]), 1, 0.0,
-                                 float(eta_w), float(alpha), 0.0, int(batch), int(bool(fit_linear)), _stream()))
-
-
-def psgd_update_prox(P_odk, grad_P, eta_P, beta, batch, reg, strength, col_thresh, work, touched=None):
-    """Fused P update + prox with a lazily applied soft threshold (l1 / squaredl12 only)."""
-    n_orders, d, k = P_odk.shape
-    _lib.check(_L().sp_psgd_update_prox(_ptr(P_odk), _ptr(grad_P), int(n_orders), int(d), int(k),
-                                        float(eta_P), float(beta), int(batch), _lib.REG_IDS[reg],
-                                        float(strength), _ptr(col_thresh), _ptr(work), _ptr(touched),
-                                        _stream()))
-
-
-def psgd_finalize(P_odk, col_thresh):
-    n_orders, d, k = P_odk.shape
-    _lib.check(_L().sp_psgd_finalize(_ptr(P_odk), int(n_orders), int(d), int(k), _ptr(col_thresh), _stream()))
+PLANNED_REGS = ("l1", "squaredl12")     # prox = column-wise soft threshold: planned path (psgd_plan.cu)
 
 
 def psgd_epoch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
                idx_samples, fit_linear, eta0, learning_rate, power_t, batch_size, it, loss_sum, work,
                group=None):
-    """psgd.psgd_epoch (psgd.py:125-199).  Returns the advanced `it`; the epoch's loss sum is
-    accumulated into the device scalar loss_sum.
+    """psgd.psgd_epoch (psgd.py:125-199) on the dense-gradient path (any regularizer).  Returns the
+    advanced `it`; the epoch's loss sum is accumulated into the device scalar loss_sum.
 
-    With `group` (a torch.distributed process group of G ranks, each holding an equal shard of
-    the samples) every rank contributes batch_size//G samples to each minibatch and the dense
-    gradients are summed with one all-reduce before the (replicated) update -- SURVEY.md 8e."""
+    With `group` (a torch.distributed process group of G ranks, each holding an equal shard of the
+    samples) every rank contributes batch_size//G samples to each minibatch and the dense gradients are
+    summed with one all-reduce before the (replicated) update.  l1 / squaredl12 fits do not come here:
+    they run the planned path (psgd_planned_*), which shards over peer memory instead."""
     n_orders, d, k = P_odk.shape
     if group is None:
         it_c = C.c_int64(int(it))
@@ -157,74 +130,41 @@ def psgd_epoch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, gra
     import torch.distributed as dist
     from .distributed import local_batches
     world = dist.get_world_size(group)
-    state = PsgdLazyState(P_odk, reg)
     for b0, b1, b_global in local_batches(ds.n_samples, batch_size, world):
-        psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
-                       idx_samples, fit_linear, eta0, learning_rate, power_t, b0, b1, b_global, it,
-                       loss_sum, work, state, group)
-        it += 1
-    state.finalize(P_odk)
-    return it
-
-
-class PsgdLazyState:
-    """Thresholds of the lazily applied prox (l1 / squaredl12) + scratch of the fused kernel."""
-
-    def __init__(self, P_odk, reg):
-        n_orders, _, k = P_odk.shape
-        self.lazy = reg in LAZY_REGS
-        if self.lazy:
-            self.thr = torch.zeros(n_orders * k, dtype=_f64, device=P_odk.device)
-            self.work = lazy_work(n_orders, k, P_odk.device)
-            # touched-row flags (padded to a multiple of 8 bytes: cleared as 64-bit words)
-            self.touched = torch.zeros(8 * ((P_odk.shape[1] + 7) // 8), dtype=torch.uint8, device=P_odk.device)
-        else:
-            self.thr = None
-            self.touched = None
-
-    def finalize(self, P_odk):
-        if self.lazy:
-            psgd_finalize(P_odk, self.thr)
-
-
-def psgd_minibatch(ds, y, P_odk, w, lams, degree, alpha, beta, gamma, reg, loss, grad_P, grad_w,
-                   idx_samples, fit_linear, eta0, learning_rate, power_t, b0, b1, b_global, it, loss_sum,
-                   work, state, group=None):
-    """One parameter update of psgd.psgd_epoch (psgd.py:153-198) on samples idx_samples[b0:b1] of this
-    rank; b_global = number of samples in the minibatch over all ranks."""
-    n_orders = P_odk.shape[0]
-    psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w,
-              loss_sum, state.thr, state.touched)
-    if group is not None:
-        import torch.distributed as dist
+        psgd_grad(ds, y, P_odk, w, lams, degree, loss, fit_linear, idx_samples, b0, b1, grad_P, grad_w, loss_sum)
         if fit_linear:
             dist.all_reduce(grad_w, group=group)
-        rows = None
-        if state.touched is not None:
-            # union of the ranks' touched rows; only those rows of the dense gradient are nonzero
-            # on any rank, so only they are exchanged (SURVEY.md 8e: "exchange (row id, k doubles)
-            # lists instead when distinct rows << d")
-            dist.all_reduce(state.touched, op=dist.ReduceOp.MAX, group=group)
-            d = P_odk.shape[1]
-            rows = torch.nonzero(state.touched[:d]).squeeze(1)        # identical on every rank
-            if rows.numel() > SPARSE_EXCHANGE_MAX_FRAC * d:
-                rows = None
-        if rows is None:
-            dist.all_reduce(grad_P, group=group)
-        elif rows.numel() > 0:
-            buf = torch.index_select(grad_P, 1, rows)
-            dist.all_reduce(buf, group=group)
-            grad_P.index_copy_(1, rows, buf)
-    eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
-    strength = gamma * eta_P / (1 + eta_P * beta)
-    if state.lazy:
-        psgd_step_w(w, grad_w, eta_w, alpha, b_global, fit_linear)
-        psgd_update_prox(P_odk, grad_P, eta_P, beta, b_global, reg, strength, state.thr, state.work,
-                         state.touched)
-    else:
+        dist.all_reduce(grad_P, group=group)
+        eta_P, eta_w = get_eta(learning_rate, eta0, alpha, beta, power_t, it)
+        strength = gamma * eta_P / (1 + eta_P * beta)
         psgd_step(P_odk, grad_P, w, grad_w, eta_P, eta_w, alpha, beta, b_global, fit_linear)
         for o in range(n_orders):
             prox(P_odk[o], reg, strength, work)
+        it += 1
+    return it
+
+
+def psgd_planned_begin(ctx):
+    """Start of a planned fit: the context's P / w hold the model, thresholds and scales are reset."""
+    _lib.check(_L().sp_psgd_plan_begin(ctx.ref(), _stream()))
+
+
+def psgd_planned_run(ctx, ds, plan, y, idx_samples, alpha, beta, gamma, eta0, learning_rate, power_t, it,
+                     m_begin=0, m_end=None):
+    """Minibatches [m_begin, m_end) of psgd.psgd_epoch (psgd.py:150-198) on the planned path; returns the
+    advanced `it`."""
+    it_c = C.c_int64(int(it))
+    m_end = plan.n_minibatches if m_end is None else m_end
+    _lib.check(_L().sp_psgd_plan_run(ctx.ref(), ds.ref(), plan.ref(), _ptr(y), _ptr(idx_samples), float(alpha),
+                                     float(beta), float(gamma), float(eta0), int(learning_rate), float(power_t),
+                                     int(m_begin), int(m_end), C.byref(it_c), _stream()))
+    return it_c.value
+
+
+def psgd_planned_end(ctx, n_local, loss_sum, materialize):
+    """End of an epoch: loss_sum[0] += the epoch's loss sum (fixed order); materialize=True turns the lazily
+    scaled / thresholded storage back into the model."""
+    _lib.check(_L().sp_psgd_plan_end(ctx.ref(), int(n_local), _ptr(loss_sum), int(bool(materialize)), _stream()))
 
 
 # ------------------------------------------------------------------------------ objective

@@ -53,3 +53,36 @@ def same_support(a, b, noise=1e-12):
     floor = noise * max(np.max(np.abs(b)), 1e-300)
     dust = (np.abs(a) < floor) & (np.abs(b) < floor)
     return bool(np.all(((a != 0) == (b != 0)) | dust))
+
+
+# ------------------------------------------------------------------ larger reference fits (oracle/gen_golden_large.py)
+with open(os.path.join(GOLD, "reference_large.json")) as _f:
+    LARGE_INDEX = json.load(_f)
+_LARGE = None
+
+
+def large_case_names():
+    return [c["name"] for c in LARGE_INDEX]
+
+
+def large_inputs(prob):
+    """X of a reference_large case, regenerated from the seeded generators (same code as the generating script)."""
+    from sparsepoly_b200 import synth
+    if prob["gen"] == "uniform":
+        return synth.uniform_sparse(prob["n"], prob["d"], prob["r"], prob["seed"])
+    return synth.criteo_like(prob["n"], prob["d"], prob["seed"])
+
+
+def load_large_case(name):
+    global _LARGE
+    if _LARGE is None:
+        _LARGE = np.load(os.path.join(GOLD, "reference_large.npz"))
+    rec = next(c for c in LARGE_INDEX if c["name"] == name)
+    arr = {k.split("/", 1)[1]: _LARGE[k] for k in _LARGE.files if k.startswith(name + "/")}
+    X = large_inputs(rec["prob"])
+    nnz, dsum, isum = rec["x_checksum"]
+    assert X.nnz == nnz and float(X.data.sum()) == dsum and int(X.indices.astype(np.int64).sum()) == isum, \
+        "regenerated inputs differ from the ones the reference was run on"
+    arr["y"] = arr["y"].astype(np.float64)
+    arr["Xte"] = large_inputs(dict(rec["prob"], n=200, seed=rec["prob"]["seed"] + 7))
+    return rec, X, arr

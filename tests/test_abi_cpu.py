@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.sp_abi_version() == 2
+    assert lib.sp_abi_version() == 3
 
 
 def test_get_eta_matches_oracle():
@@ -114,7 +114,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     from sparsepoly_b200 import _lib
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    mirrors = {"sp_dataset": _lib.SpDataset, "sp_plan": _lib.SpPlan, "sp_wplan": _lib.SpWPlan}
+    mirrors = {"sp_dataset": _lib.SpDataset, "sp_plan": _lib.SpPlan, "sp_wplan": _lib.SpWPlan,
+               "sp_psgd_plan": _lib.SpPsgdPlan, "sp_psgd_ctx": _lib.SpPsgdCtx}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sparsepoly_b200.h"', "int main(void) {"]
     for cname, cls in mirrors.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof(struct {cname}));')
@@ -133,3 +134,20 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert got[(cname, "size")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_fitted_estimators_pickle_without_device_state():
+    """_dev_state holds ctypes structs with pointers; a fitted estimator must still pickle."""
+    import ctypes as C
+    import copy
+    import pickle
+    import sparsepoly_b200 as S
+    from sparsepoly_b200 import _lib
+    est = S.SparseFactorizationMachineRegressor(degree=2, n_components=3)
+    est.P_ = np.zeros((1, 3, 5)); est.w_ = np.zeros(5); est.lams_ = np.ones(3); est.n_iter_ = 4
+    est._dev_state = {"ds": _lib.SpDataset(), "plan": C.pointer(_lib.SpPlan())}      # what fit leaves behind
+    est._y_pred_train = object()
+    est2 = pickle.loads(pickle.dumps(est))
+    assert np.array_equal(est2.P_, est.P_) and est2.n_iter_ == 4 and not hasattr(est2, "_dev_state")
+    est3 = copy.deepcopy(est)
+    assert not hasattr(est3, "_dev_state") and est3.get_params() == est.get_params()

@@ -100,3 +100,79 @@ def test_sharded_psgd_equals_single_process_oracle(tmp_path):
     assert np.max(np.abs(z["w"] - ref["w_"])) <= 1e-11
     assert int(z["it"]) == ref["it_"]
     assert np.allclose(z["losses"], ref["trace"], rtol=1e-10)
+
+
+# ------------------------------------------------------------------ planned path: host logic over real collectives
+def _plan_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparsepoly_b200 import distributed, synth
+    from sparsepoly_b200.psgd_plan import PsgdPlan
+    assert distributed.active_group() is None                     # initialised torch.distributed alone shards nothing
+    group = distributed.enable_sharding()
+    assert distributed.active_group() is group
+    n_loc, d, b_loc = 300, 120, 64
+    X = synth.criteo_like(n_loc, d, 50 + rank)
+    csr = (torch.from_numpy(X.indptr.astype(np.int32)), torch.from_numpy(X.indices.astype(np.int32)),
+           torch.from_numpy(X.data.astype(np.float64)))
+    idx = torch.arange(n_loc, dtype=torch.int32)
+    plan = PsgdPlan(csr, idx, d, b_loc, world=world, rank=rank, group=group)      # owner tables via all_gather (gloo)
+    np.savez(os.path.join(out_dir, f"plan{rank}.npz"), own_q=plan.own_q.numpy(), own_src=plan.own_src.numpy(),
+             mb_optr=plan.mb_optr, inbox_cap=plan.inbox_cap, mb_owner_start=plan.mb_owner_start,
+             csr_slot=plan.csr_slot.numpy())
+    # replicas start from rank 0's parameters whatever each rank drew
+    P = np.random.RandomState(rank).randn(2, 3)
+    it = np.array([float(7 + rank)])
+    distributed.broadcast_arrays([P, it], group)
+    assert np.array_equal(P, np.random.RandomState(0).randn(2, 3)) and it[0] == 7.0
+    # unequal shards are refused
+    if rank == 1:
+        idx2 = torch.arange(n_loc - 1, dtype=torch.int32)
+    else:
+        idx2 = idx
+    try:
+        PsgdPlan(csr, idx2, d, b_loc, world=world, rank=rank, group=group)
+        raise AssertionError("unequal shards accepted")
+    except ValueError as e:
+        assert "equal shards" in str(e)
+
+    class _Est:                                                    # sharded_predict: rank-order concatenation, ragged shards
+        def _predict(self, Xl):
+            return np.asarray(Xl).sum(1)
+    Xl = np.full((3 + rank, 2), float(rank + 1))
+    got = distributed.sharded_predict(_Est(), Xl)
+    want = np.concatenate([np.full(3 + r, 2.0 * (r + 1)) for r in range(world)])
+    assert np.array_equal(got, want)
+    assert np.array_equal(distributed.sharded_predict(_Est(), Xl, gather=False), np.full(3 + rank, 2.0 * (rank + 1)))
+    distributed.disable_sharding()
+    dist.destroy_process_group()
+
+
+def test_plan_owner_tables_over_gloo_match_in_process_build(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from sparsepoly_b200 import synth
+    from sparsepoly_b200.psgd_plan import PsgdPlan
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_plan_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n_loc, d, b_loc = 300, 120, 64
+    plans = []
+    for r in range(world):
+        X = synth.criteo_like(n_loc, d, 50 + r)
+        csr = (torch.from_numpy(X.indptr.astype(np.int32)), torch.from_numpy(X.indices.astype(np.int32)),
+               torch.from_numpy(X.data.astype(np.float64)))
+        plans.append(PsgdPlan(csr, torch.arange(n_loc, dtype=torch.int32), d, b_loc, world=world, rank=r,
+                              defer_owner_tables=True))
+    lists = [p.column_lists() for p in plans]
+    gathered = tuple([l[t] for l in lists] for t in range(4))
+    for r, p in enumerate(plans):
+        p.finish_owner_tables(*gathered)
+        z = np.load(tmp_path / f"plan{r}.npz")
+        assert np.array_equal(z["own_q"], p.own_q.numpy()) and np.array_equal(z["own_src"], p.own_src.numpy())
+        assert np.array_equal(z["mb_optr"], p.mb_optr) and int(z["inbox_cap"]) == p.inbox_cap
+        assert np.array_equal(z["mb_owner_start"], p.mb_owner_start) and np.array_equal(z["csr_slot"], p.csr_slot.numpy())
+        # every row an owner lists is touched by at least one rank, and each (rank, index) appears once
+        assert np.all((p.own_src.numpy() >= 0).any(1))
