@@ -2,22 +2,26 @@
 """bench.py -- headline benchmark of the sparsepoly B200 backend (contract in the task prompt).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload auto|pcd|pbcd|allsub|psgd] [--scale S]
+                    [--workload auto|psgd|pcd|pbcd|allsub|c1] [--scale S]
 
 Workloads (BASELINE.json configs / SURVEY.md 8d):
-  pcd    C2  FM-Clf degree=3 pcd omegati logistic, n=1M d=100k 50 nnz/row k=16   [N=1 default]
+  psgd   C5  FM-Clf degree=2 psgd squaredl12 logistic, Criteo-shaped d=1M 39 nnz/row k=32,
+             sample-sharded, 6.25M rows per GPU (= n=50M at 8 GPUs)               [headline at every N]
+  pcd    C2  FM-Clf degree=3 pcd omegati logistic, n=1M d=100k 50 nnz/row k=16
   pbcd   C3  FM-Reg degree=2 pbcd omegacs, n=1M d=100k 50 nnz/row k=32
   allsub C4  AllSubsets-Clf pcd omegati squared_hinge, n=500k d=20k 20 nnz/row k=16
-  psgd   C5  FM-Clf degree=2 psgd squaredl12 logistic, Criteo-shaped d=1M 39 nnz/row k=32,
-             sample-sharded, 6.25M rows per GPU (= n=50M at 8 GPUs)               [N>1 default]
-A "step" is one epoch (pcd / pbcd / allsub) or one minibatch of batch_size="auto" (psgd).
-pcd / pbcd do not shard (sequential coordinate order): with N>1 they run N independent replicas.
-With --workload auto (default) the headline line is the pcd workload (replicas for N>1) and the
-"also" list carries the psgd numbers (sample-sharded over the N ranks, NCCL all-reduce) and, at
-N=1, the pbcd epoch time.
+  c1     C1  FM-Reg degree=2 pcd squaredl12, n=10k d=1k 50 nnz/row k=10 (the reference's CPU-runnable case)
+A "step" is one epoch: for psgd one pass over the rank's 6.25M-row shard (244 minibatches of
+batch_size="auto" samples per rank -- weak scaling: the global minibatch is auto x N), for the others one
+sweep over all coordinates.  psgd is the path that shards (samples over the ranks, P over the ranks' HBM,
+peer-memory exchange); pcd / pbcd are sequential in the coordinate order and stay on one GPU.
+With --workload auto (default) the headline line is psgd; at N=1 the "also" list carries C2, C3, C4 and C1,
+each with its own roofline / e2e / cpu_baseline; at N>1 it carries the strong-scaling psgd run (global
+minibatch = auto, split over the ranks).
 
-`--impl reference` times the reference algorithm on the host CPU (the pinned C oracle port of the
-numba path; the numba package itself cannot travel to the GPU box) on a bounded sample.
+`--impl reference` times the reference algorithm on the host CPU (the pinned C oracle port of the numba
+path, 1 core -- the reference is single threaded; the numba package itself cannot travel to the GPU box) on
+a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -47,11 +51,15 @@ WORKLOADS = {
                            # OmegaTI for all-subsets multiplies gamma by prod_j (1 + |p_sj|) ~ e^160 at
                            # d=20k (reference omegati.py:19-34): only an absurdly small gamma leaves ~10 % of P_
                            beta=1e-6, gamma=1e-100, mean=True, shuffle=False, random_state=0, tol=-1.0)),
+    "c1": dict(tag="C1", n=10_000, d=1_000, r=50, seed=0, k=10, degree=2, clf=False,
+               kw=dict(degree=2, n_components=10, solver="pcd", regularizer="squaredl12", alpha=1e-3, beta=1e-3,
+                       gamma=1e-4, mean=True, fit_linear=True, fit_lower="explicit", shuffle=False,
+                       random_state=0, tol=-1.0)),
     "psgd": dict(tag="C5", n_per_gpu=6_250_000, d=1_000_000, r=39, seed=4, k=32, degree=2, clf=True,
                  kw=dict(degree=2, loss="logistic", n_components=32, solver="psgd",
                          regularizer="squaredl12", alpha=1e-7, beta=1e-7, gamma=1e-6, fit_linear=True,
                          fit_lower="explicit", batch_size="auto", eta0=0.1, learning_rate="optimal",
-                         power_t=1.0, shuffle=False, random_state=0)),
+                         power_t=1.0, shuffle=False, random_state=0, tol=-1.0, n_iter_no_change=10 ** 9)),
 }
 
 
@@ -143,8 +151,9 @@ def make_problem(name, scale=1.0, rank=0):
         n = max(1024, int((ROWS_OVERRIDE or wl["n_per_gpu"]) * scale))
         d = max(64, int(wl["d"] * scale))
         X = synth.criteo_like(n, d, wl["seed"] * 1000 + rank)
-        rng = np.random.RandomState(99 + rank)
-        y = np.where(rng.rand(n) < 0.25, 1.0, -1.0)       # CTR-like class balance
+        # planted sparse degree-2 model on 10 % of the features, CTR-like class balance;
+        # the model is the same on every rank (seed without the rank), the noise is not
+        y = synth.planted_fm_targets(X, wl["seed"], 99 + rank, positive_frac=0.25)
         return X, y
     n, d = max(256, int(wl["n"] * scale)), max(32, int(wl["d"] * scale))
     X = synth.uniform_sparse(n, d, wl["r"], wl["seed"] + 17 * rank)
@@ -163,7 +172,7 @@ def sweep_bytes(name, nnz, n, k, degree, fit_linear):
     """Algorithmic bytes of the SWEEP kernels in one epoch (SURVEY.md 8d byte model: column
     idx+val 12 B, A^1..A^(m-1) read+write 16(m-1) B, y_pred r/w 16 B, y 8 B per nonzero)."""
     lin = nnz * 36.0 if fit_linear else 0.0
-    if name == "pcd":
+    if name in ("pcd", "c1"):
         tot = lin
         for deg in range(2, degree + 1):
             tot += k * nnz * (12 + 16 * (deg - 1) + 24)
@@ -188,7 +197,7 @@ def cpu_reference_epoch_seconds(name, X, y, budget_s):
     n, d = X.shape
     k = wl["k"]
     # ~100 ns per nonzero-component-pass on one core: pick the column fraction for the budget
-    passes = {"pcd": 1 + 2 * 5, "pbcd": 1 + 3 * 32 / 2.0, "allsub": 4}[name]
+    passes = {"pcd": 1 + 2 * 5, "pbcd": 1 + 3 * 32 / 2.0, "allsub": 4, "c1": 1 + 5}[name]
     frac = min(1.0, budget_s / (X.nnz * passes * 60e-9))
     d_s = max(16, int(d * frac))
     Xs = sp.csc_matrix(X[:, :d_s])
@@ -200,11 +209,11 @@ def cpu_reference_epoch_seconds(name, X, y, budget_s):
     loss = kw.get("loss", "squared")
     y_pred = np.zeros(n)
     t_total = 0.0
-    if name in ("pcd", "allsub"):
+    if name in ("pcd", "allsub", "c1"):
         reg = O.Reg(kw["regularizer"], d_s, 1)
         lams = np.ones(1)
         idx_comp = np.zeros(1, dtype=np.int32)
-        if name == "pcd":
+        if name in ("pcd", "c1"):
             w = np.zeros(d_s)
             cns = O.col_norm_sq(Xs)
             t0 = time.perf_counter()
@@ -273,6 +282,16 @@ def cpu_reference_psgd_samples_per_s(X, y, budget_s):
                      f"of {batch} at full d={d}, k={k}")
 
 
+def sweep_config(name, args, X, world):
+    """`config` of a pcd / pbcd line: identical in both arms (ours / reference)."""
+    wl = WORKLOADS[name]
+    n, d = X.shape
+    return {"workload": f"{wl['tag']} {name}: " + json.dumps(wl["kw"]),
+            "n_samples": n, "n_features": d, "nnz": int(X.nnz), "scale": args.scale,
+            "l2": "inputs_exceed_l2 (CSC+CSR+records >> 126 MB)" if X.nnz * 24 > 2e8 else "inputs fit L2",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (pcd/pbcd do not shard)"}
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def run_sweep_workload(name, args, rank, world, local):
     import torch
@@ -308,10 +327,16 @@ def run_sweep_workload(name, args, rank, world, local):
         n_orders = est.degree - 1 if est.fit_lower == "explicit" else 1
         est.P_ = 0.01 * rng.randn(n_orders, est.n_components, Xc.shape[1])
         est.lams_ = np.ones(est.n_components)
-        setup = est._pcd_setup if name == "pcd" else est._pbcd_setup
+        setup = est._pcd_setup if name in ("pcd", "c1") else est._pbcd_setup
     epoch, sync = setup(Xc, np.ascontiguousarray(yc, dtype=np.float64), rng, dev)
+    first_epochs = []                                  # the dense regime: P_ starts fully dense (0.01 * randn)
     for _ in range(args.warmup):
-        epoch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        epoch(read_back=False)
+        e1.record()
+        torch.cuda.synchronize()
+        first_epochs.append(e0.elapsed_time(e1) / 1e3)
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
@@ -353,12 +378,12 @@ def run_sweep_workload(name, args, rank, world, local):
     alg_bytes = sweep_bytes(name, X.nnz, n, wl["k"], wl["degree"], True) * args.steps
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
-    coords = (d * (1 + wl["k"] * (wl["degree"] - 1))) if name == "pcd" else (d * wl["k"] if name == "allsub" else 2 * d)
+    coords = (d * (1 + wl["k"] * (wl["degree"] - 1))) if name in ("pcd", "c1") else (d * wl["k"] if name == "allsub" else 2 * d)
     result = {
         "value": sec_per_epoch, "ms_per_step": sec_per_epoch * 1e3,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "sweep_kernel (pcd.cu)" if name == "pcd" else "pbcd_sweep_kernel (pbcd.cu)",
+                     "kernel": "sweep_kernel (pcd.cu)" if name in ("pcd", "c1", "allsub") else "pbcd_sweep_kernel (pbcd.cu)",
                      "kernel_ms_per_step": sweep_ms / args.steps,
                      "kernel_share_of_step": sweep_ms / ms_total if ms_total else None,
                      "algorithmic_bytes_per_step": alg_bytes / args.steps,
@@ -367,6 +392,9 @@ def run_sweep_workload(name, args, rank, world, local):
         "gpu_launches": int(sum(cnt)),
         "kernel_ms": {"rows": ms[0], "regcache": ms[1], "sweep_pcd": ms[2], "sweep_pbcd": ms[3]},
         "clocks": clocks, "p_nonzero_frac": nz_frac, "p_nonzero_frac_by_order": nz_by_order,
+        "dense_regime_epochs_s": first_epochs,
+        "dense_regime_note": "epochs 1..warmup from the dense random start (every coordinate moves), device-timed one by "
+                             "one; `value` is the steady state after them",
         "zero_update_speculation": {"positions": int(wspec[0]), "rejected": int(wspec[1]),
                                     "note": "window-sweep positions evaluated without per-record waits (pcd_window.cu)"},
         "geometry": ({"sweep": "window", **est._dev_state["plan"].wplan.stats}
@@ -376,7 +404,7 @@ def run_sweep_workload(name, args, rank, world, local):
     }
     if result["geometry"]["sweep"] == "window" and name == "pbcd":
         result["roofline"]["kernel"] = "pbcd_wsweep_kernel (pbcd_window.cu)"
-    if result["geometry"]["sweep"] == "window" and name in ("pcd", "allsub"):
+    if result["geometry"]["sweep"] == "window" and name in ("pcd", "allsub", "c1"):
         result["roofline"]["kernel"] = "wsweep_kernel (pcd_window.cu)"
         if name == "pcd" and args.scale == 1.0:
             result["roofline"]["traffic"] = profiled_traffic("wsweep_kernel")
@@ -408,19 +436,35 @@ def run_sweep_workload(name, args, rank, world, local):
     if rank == 0 and not args.no_cpu:
         t_cpu, desc = cpu_reference_epoch_seconds(name, X, y, args.cpu_budget)
         result["cpu_baseline"] = {"value": t_cpu, "unit": "s/epoch", "cores": 1, "kind": "port", "sample": desc}
-    result["config"] = {"workload": f"{wl['tag']} {name}: " + json.dumps({k: v for k, v in kw.items()}),
-                        "n_samples": n, "n_features": d, "nnz": int(X.nnz), "scale": args.scale,
-                        "l2": "inputs_exceed_l2 (CSC+CSR+records >> 126 MB)" if X.nnz * 24 > 2e8 else "inputs fit L2",
-                        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (pcd/pbcd do not shard)"}
+    result["config"] = sweep_config(name, args, X, world)
     return result
 
 
-def run_psgd_workload(args, rank, world, local):
-    import torch
-    from sparsepoly_b200 import _lib, solvers
-    from sparsepoly_b200.dataset import DeviceDataset
+def psgd_config(args, world, batch_mode):
+    """`config` of the psgd line: identical in both arms (ours / reference)."""
     wl = WORKLOADS["psgd"]
-    kw = wl["kw"]
+    n = max(1024, int((args.rows_per_gpu or wl["n_per_gpu"]) * args.scale))
+    d = max(64, int(wl["d"] * args.scale))
+    return {"workload": "C5 psgd: " + json.dumps(wl["kw"]), "rows_per_gpu": n, "n_features": d,
+            "nnz_per_row": wl["r"], "scale": args.scale, "n_gpus": world,
+            "batch": ("weak: global minibatch = batch_size('auto') x n_gpus, every rank contributes one auto-sized batch"
+                      if batch_mode == "weak" else "strong: global minibatch = batch_size('auto'), split over the ranks"),
+            "l2": "inputs_exceed_l2 (P is 256 MB, X 2.9 GB per GPU)" if d * wl["k"] * 8 > 1.3e8 else "P fits L2",
+            "parallelism": ("single GPU" if world == 1 else
+                            f"{world} ranks: samples sharded, P sharded by rows over the ranks' HBM, peer-memory "
+                            f"pull / push / owner-update per minibatch (no NCCL on the data path)")}
+
+
+def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
+    """C5: step = one epoch over the rank's shard.  Device-timed value through the estimator's own epoch
+    function with X / y / plan resident; e2e = fit(X_host, y_host) wall clock (H2D of X, plan, epochs, D2H)."""
+    import ctypes as C
+    import warnings
+    import torch
+    import sparsepoly_b200 as S
+    from sklearn.utils import check_random_state
+    from sparsepoly_b200 import _lib, distributed
+    wl = WORKLOADS["psgd"]
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
@@ -428,178 +472,129 @@ def run_psgd_workload(args, rank, world, local):
     group = None
     if world > 1:
         import torch.distributed as dist
-        group = dist.group.WORLD
+        group = distributed.enable_sharding()
     global ROWS_OVERRIDE
     ROWS_OVERRIDE = args.rows_per_gpu
+    t_gen = time.perf_counter()
     X, y = make_problem("psgd", args.scale, rank)
+    t_gen = time.perf_counter() - t_gen
     n, d = X.shape
-    k = wl["k"]
-    batch = int(n * d / X.nnz)                        # batch_size="auto" = d / nnz_row (independent of n)
-    if args.psgd_batch == "auto":
-        b_loc = max(1, batch // world)                # the reference's global minibatch, split over ranks
-    elif args.psgd_batch == "weak":
-        b_loc = batch                                 # every rank contributes one auto-sized batch
-    else:
-        b_loc = max(1, int(args.psgd_batch) // world)
-    need = (args.warmup + args.steps) * b_loc
-    if need > n:
-        raise SystemExit(f"psgd bench needs {need} rows per GPU, shard has {n}")
-    ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev)
-    y_dev = torch.from_numpy(y).to(dev)
-    idx = torch.arange(n, dtype=torch.int32, device=dev)
-    rng = np.random.RandomState(0)
-    P = torch.from_numpy(np.ascontiguousarray(0.01 * rng.randn(1, d, k))).to(dev)
-    w = torch.zeros(d, dtype=torch.float64, device=dev)
-    lams = torch.ones(k, dtype=torch.float64, device=dev)
-    gP, gw = torch.zeros_like(P), torch.zeros_like(w)
-    loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
-    work = solvers.prox_work(d, k, dev)
-    it = [1]
-    state = solvers.PsgdLazyState(P, kw["regularizer"])
-
-    def minibatch(m):
-        b0, b1 = m * b_loc, (m + 1) * b_loc
-        solvers.psgd_minibatch(ds, y_dev, P, w, lams, 2, kw["alpha"], kw["beta"], kw["gamma"],
-                               kw["regularizer"], kw["loss"], gP, gw, idx, True, kw["eta0"], 1,
-                               kw["power_t"], b0, b1, b_loc * world, it[0], loss_dev, work, state, group)
-        it[0] += 1
-
-    for m in range(args.warmup):
-        minibatch(m)
+    k, r = wl["k"], wl["r"]
+    batch_auto = int(n * d / X.nnz)                   # batch_size="auto" = d / nnz_row (independent of n)
+    kw = dict(wl["kw"])
+    if args.gamma is not None:
+        kw["gamma"] = args.gamma
+    kw["batch_size"] = batch_auto * world if batch_mode == "weak" else batch_auto
+    b_loc = max(1, kw["batch_size"] // world)
+    est = S.SparseFactorizationMachineClassifier(max_iter=args.steps, **kw)
+    Xc, yc = est._check_X_y(X, y)
+    rng = check_random_state(kw["random_state"])
+    est.w_ = np.zeros(d)
+    est.P_ = 0.01 * rng.randn(1, k, d)
+    est.lams_ = np.ones(k)
+    est.it_ = 1
+    t_setup = time.perf_counter()
+    epoch, sync, close = est._psgd_setup(Xc, np.ascontiguousarray(yc, dtype=np.float64), rng, dev)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    n_mb = est._psgd_stats["minibatches"]
+    for _ in range(args.warmup):
+        epoch(read_back=False)
     torch.cuda.synchronize()
     if group is not None:
         dist.barrier()
     lib.sp_profile_enable(1)
-    import ctypes as C
-    _z = (C.c_ulonglong * 2)()
-    lib.sp_wspec_read(_z)                       # reset the speculation counters
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    for m in range(args.warmup, args.warmup + args.steps):
-        minibatch(m)
+    for _ in range(args.steps):
+        epoch(read_back=False)
     ev1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
-    import ctypes as C
     ms = (C.c_double * 8)()
     cnt = (C.c_longlong * 8)()
     lib.sp_profile_collect(ms, cnt)
     lib.sp_profile_enable(0)
+    last_loss = epoch()                              # one more epoch, read back: the metric a user sees
+    sync()
+    nz_frac = float(np.mean(est.P_ != 0))
+    close()
     if group is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    samples = args.steps * b_loc * world
+    samples = args.steps * n * world
     value = samples / (ms_total / 1e3)
-    r = wl["r"]
-    # SURVEY.md 8d byte model per sample / per minibatch
-    per_sample = r * 12 + r * k * 8 + 2 * r * k * 8 + r * 8 * 3 + 8
-    per_batch_dense = 5 * d * k * 8 + 4 * d * 8
-    grad_bytes = per_sample * args.steps * b_loc
+    # SURVEY.md 8d byte model: per sample (rows pass: CSR + P gather + w; column pass: grad_P / grad_w
+    # read-modify-write) and per minibatch (5 dense sweeps of P / grad_P + 4 of w / grad_w)
+    rows_bytes = r * 12 + r * k * 8 + r * 8 + 8
+    cols_bytes = 2 * r * k * 8 + 2 * r * 8
+    dense_bytes = 5 * d * k * 8 + 4 * d * 8
     peak, peak_src = measured_peak()
-    grad_ms = float(ms[4])
-    step_bytes = (per_sample * b_loc + per_batch_dense) * args.steps
+    n_launch = args.steps * n_mb
+    klass = {"psgd_rows_kernel": (float(ms[4]), rows_bytes * b_loc),
+             "psgd_cols_async_kernel + psgd_split_kernel": (float(ms[5]), cols_bytes * b_loc),
+             "psgd_stats_kernel + psgd_solve_kernel": (float(ms[6]), dense_bytes)}
+    dom = max(klass, key=lambda q: klass[q][0])
+    dom_ms, dom_bytes = klass[dom]
+    achieved = dom_bytes * n_launch / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    step_bytes = (rows_bytes + cols_bytes) * n + dense_bytes * n_mb         # one epoch of one rank
     result = {
         "value": value, "ms_per_step": ms_total / args.steps,
-        "roofline": {"bound": "hbm", "achieved": grad_bytes / (grad_ms / 1e3) / 1e9 if grad_ms else 0.0,
-                     "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
-                     "kernel": "psgd_grad_kernel (psgd.cu)", "kernel_ms_per_step": grad_ms / args.steps,
-                     "kernel_share_of_step": grad_ms / ms_total if ms_total else None,
-                     "whole_step_gbs_per_gpu": step_bytes / (ms_total / 1e3) / 1e9,
-                     "whole_step_frac": step_bytes / (ms_total / 1e3) / 1e9 / peak},
-        "gpu_launches": int(sum(cnt)),
-        "kernel_ms": {"psgd_grad": ms[4], "psgd_step_w": ms[5], "fused_update_prox": ms[6]},
-        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": profiled_traffic(dom.split(" ")[0]), "peak_source": peak_src, "kernel": dom + " (psgd_plan.cu)",
+                     "kernel_ms_per_launch": dom_ms / max(n_launch, 1),
+                     "kernel_share_of_step": dom_ms / ms_total if ms_total else None,
+                     "algorithmic_bytes_per_launch": dom_bytes,
+                     "byte_model": "SURVEY.md 8d per-unit figures x units per launch: rows 10.8 KB/sample, column pass "
+                                   "20.6 KB/sample, dense sweeps 1.31 GB/minibatch; the planned path never makes the dense "
+                                   "sweeps (touched rows only + one read-only statistics pass), so fractions above 1 are "
+                                   "work avoided, not bandwidth",
+                     "per_kernel": {q: {"ms_per_launch": v[0] / max(n_launch, 1), "algorithmic_bytes_per_launch": v[1],
+                                        "gbs": v[1] * n_launch / (v[0] / 1e3) / 1e9 if v[0] > 0 else None} for q, v in klass.items()},
+                     "whole_step_gbs_per_gpu": step_bytes * args.steps / (ms_total / 1e3) / 1e9,
+                     "whole_step_frac": step_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
+        "gpu_launches": int(args.steps * (n_mb * (5 if kw["regularizer"] == "squaredl12" else 4) + 1)
+                            + (args.steps * n_mb * 5 if world > 1 else 0)),
+        "clocks": clocks, "p_nonzero_frac": nz_frac, "mean_loss_after": last_loss,
+        "details": {"minibatches_per_epoch": n_mb, "batch_local": b_loc, "global_batch": b_loc * world,
+                    "batch_size_auto": batch_auto, "columns_per_minibatch": est._psgd_stats["columns_per_minibatch"],
+                    "plan_bytes": est._psgd_stats["plan_bytes"], "data_generation_s": t_gen, "setup_s": t_setup},
     }
-    result["roofline"]["frac"] = result["roofline"]["achieved"] / peak
-    # ---- e2e: pinned host CSR rows of each minibatch are copied inside the timed region
-    Xr = X[: need]
-    indptr_h = torch.from_numpy(Xr.indptr.astype(np.int32)).pin_memory()
-    indices_h = torch.from_numpy(Xr.indices.astype(np.int32)).pin_memory()
-    data_h = torch.from_numpy(Xr.data.astype(np.float64)).pin_memory()
-    y_h = torch.from_numpy(y[:need].copy()).pin_memory()
-    P.copy_(torch.from_numpy(np.ascontiguousarray(0.01 * rng.randn(1, d, k))))
-    w.zero_(); it[0] = 1
-    state = solvers.PsgdLazyState(P, kw["regularizer"])
-    max_nnz = int(np.max(Xr.indptr[b_loc::b_loc] - Xr.indptr[:-b_loc:b_loc])) if need >= b_loc else Xr.nnz
-    # two device buffer sets: minibatch m+1 is copied on a side stream while minibatch m is computed (the copy
-    # of every step's inputs still happens inside the timed region, it just overlaps the previous step)
-    bufs = [dict(ip=torch.empty(b_loc + 1, dtype=torch.int32, device=dev),
-                 ix=torch.empty(max_nnz, dtype=torch.int32, device=dev),
-                 dt=torch.empty(max_nnz, dtype=torch.float64, device=dev),
-                 yb=torch.empty(b_loc, dtype=torch.float64, device=dev),
-                 ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
-    idx_b = torch.arange(b_loc, dtype=torch.int32, device=dev)
-    copy_stream = torch.cuda.Stream(device=dev)
-    n_mb = need // b_loc
-    h2d = [0]
-
-    def upload(m):
-        """H2D of minibatch m's CSR rows and targets (pinned host memory) on the copy stream."""
-        if m >= n_mb:
-            return
-        b = bufs[m & 1]
-        r0, r1 = m * b_loc, (m + 1) * b_loc
-        p0, p1 = int(indptr_h[r0]), int(indptr_h[r1])
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(b["free"])             # the compute that last read this buffer set
-            b["ip"].copy_(indptr_h[r0:r1 + 1], non_blocking=True)
-            b["ip"].sub_(p0)
-            b["ix"][: p1 - p0].copy_(indices_h[p0:p1], non_blocking=True)
-            b["dt"][: p1 - p0].copy_(data_h[p0:p1], non_blocking=True)
-            b["yb"].copy_(y_h[r0:r1], non_blocking=True)
-            b["ready"].record(copy_stream)
-        h2d[0] += (b_loc + 1) * 4 + (p1 - p0) * 12 + b_loc * 8
-
-    def minibatch_e2e(m, prefetch=True):
-        b = bufs[m & 1]
-        torch.cuda.current_stream().wait_event(b["ready"])
-        if prefetch:
-            upload(m + 1)                                 # overlaps this minibatch's kernels
-        dsb = DeviceDataset.from_device_csr(b_loc, d, b["ip"], b["ix"], b["dt"])
-        dsb.adopt_hot_features(ds)                        # dense-feature table of the training set
-        solvers.psgd_minibatch(dsb, b["yb"], P, w, lams, 2, kw["alpha"], kw["beta"], kw["gamma"],
-                               kw["regularizer"], kw["loss"], gP, gw, idx_b, True, kw["eta0"], 1,
-                               kw["power_t"], 0, b_loc, b_loc * world, it[0], loss_dev, work, state, group)
-        b["free"].record(torch.cuda.current_stream())
-        it[0] += 1
-        return loss_dev.item()                           # D2H read of the step's metric
-
-    for b_ in bufs:
-        b_["free"].record(torch.cuda.current_stream())
-    upload(0)
-    for m in range(args.warmup):
-        minibatch_e2e(m, prefetch=m + 1 < args.warmup)    # (every timed step's copy happens inside the timed region)
+    del est, epoch, sync, close
+    torch.cuda.empty_cache()
+    # ---- end to end through the public API: host buffers in, fitted host arrays out
+    e_epochs = max(1, min(args.steps, 5))
+    est2 = S.SparseFactorizationMachineClassifier(max_iter=e_epochs, **kw)
     torch.cuda.synchronize()
     if group is not None:
         dist.barrier()
-    h2d[0] = 0
     t0 = time.perf_counter()
-    upload(args.warmup)
-    for m in range(args.warmup, args.warmup + args.steps):
-        minibatch_e2e(m)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        est2.fit(X, y)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if group is not None:
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    result["e2e"] = {"value": samples / dt, "unit": "samples/s", "h2d_bytes_per_step": int(h2d[0] / args.steps),
-                     "d2h_bytes_per_step": 8,
-                     "note": "per minibatch: pinned host CSR rows + y -> device (double-buffered on a copy stream), gradient, (all-reduce), update, prox, loss read back"}
+    result["e2e"] = {"value": e_epochs * n * world / dt, "unit": "samples/s",
+                     "h2d_bytes_per_step": int(est2._h2d_bytes / e_epochs),
+                     "d2h_bytes_per_step": int((est2.P_.nbytes + est2.w_.nbytes) / e_epochs + 8),
+                     "note": f"fit(X_host, y_host) wall clock over {e_epochs} epochs per rank: H2D of the CSR shard, batch-CSC "
+                             f"plan (device sorts), epochs (loss read back each), D2H of P_ / w_"}
+    if group is not None:
+        distributed.disable_sharding()
     if rank == 0 and not args.no_cpu:
         v, desc = cpu_reference_psgd_samples_per_s(X, y, args.cpu_budget)
         result["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port", "sample": desc}
-    result["config"] = {"workload": "C5 psgd: " + json.dumps(kw), "rows_per_gpu": n, "n_features": d,
-                        "nnz_per_row": r, "global_batch": b_loc * world, "batch_mode": args.psgd_batch,
-                        "batch_size_auto": batch, "scale": args.scale,
-                        "l2": "inputs_exceed_l2 (P and grad_P are 256 MB each)" if d * k * 8 > 1.3e8 else "P fits L2",
-                        "parallelism": "single GPU" if world == 1 else f"dp{world}: samples sharded, dense gradient all-reduced (NCCL) per minibatch"}
+    result["config"] = psgd_config(args, world, batch_mode)
     return result
 
 
@@ -607,6 +602,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return None
     name = args.workload
+    global ROWS_OVERRIDE
+    if name == "psgd":
+        ROWS_OVERRIDE = args.rows_per_gpu or 1_000_000      # (the bounded sample only ever reads the leading rows)
     X, y = make_problem(name, args.scale, 0)
     per_step_budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
     vals = []
@@ -622,13 +620,12 @@ def run_reference(args, rank, world):
     wall = time.perf_counter() - t_run0
     value = float(np.mean(vals))
     unit = "samples/s" if name == "psgd" else "s/epoch"
-    wl = WORKLOADS[name]
     return {"impl": "reference", "metric": metric_name(name), "value": value, "unit": unit,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall * 1e3 / max(1, args.steps + args.warmup),
             "higher_is_better": name == "psgd", "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{wl['tag']} {name}: " + json.dumps(wl["kw"]), "scale": args.scale},
+            "config": psgd_config(args, args.gpus, "weak") if name == "psgd" else sweep_config(name, args, X, 1),
             "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -636,23 +633,22 @@ def run_reference(args, rank, world):
 
 def metric_name(name):
     return {"pcd": "pcd_epoch_seconds", "pbcd": "pbcd_epoch_seconds", "allsub": "pcd_allsubsets_epoch_seconds",
-            "psgd": "psgd_samples_per_second"}[name]
+            "c1": "pcd_epoch_seconds", "psgd": "psgd_samples_per_second"}[name]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "pcd", "pbcd", "allsub", "psgd"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "pcd", "pbcd", "allsub", "c1", "psgd"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink n and d (debug only)")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="psgd: override the shard size (debug)")
-    ap.add_argument("--psgd-batch", default="weak",
-                    help="psgd global minibatch: 'auto' (= d/nnz_row split over the ranks), 'weak' "
-                         "(auto x n_gpus: per-GPU work fixed) or an integer")
+    ap.add_argument("--psgd-batch", default="weak", choices=["weak", "strong"],
+                    help="psgd global minibatch: 'weak' (auto x n_gpus: per-GPU work fixed) or 'strong' (auto, split over the ranks)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--gamma", type=float, default=None, help="override the workload's gamma (debug: other sparsity regimes)")
     args = ap.parse_args()
@@ -661,7 +657,7 @@ def main():
     ROWS_OVERRIDE = args.rows_per_gpu
     auto = args.workload == "auto"
     if auto:
-        args.workload = "pcd"
+        args.workload = "psgd"
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -679,37 +675,37 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload
     if name == "psgd":
-        res = run_psgd_workload(args, rank, world, local)
+        res = run_psgd_workload(args, rank, world, local, args.psgd_batch)
     else:
         res = run_sweep_workload(name, args, rank, world, local)
     also = []
     if auto and not args.no_also:
-        # secondary measurements of the same path (north_star: pbcd epoch time and psgd samples/s,
-        # psgd sharded over the ranks); short runs, no CPU leg
         import copy
-        a2 = copy.copy(args)
-        a2.no_cpu = True
-        a2.steps, a2.warmup = 20, 3
-        if a2.rows_per_gpu == 0:
-            a2.rows_per_gpu = 1_000_000          # >= 23 auto-sized minibatches; batch "auto" is n-independent
-        for mode in (["auto"] if world == 1 else ["weak", "auto"]):
-            a2.psgd_batch = mode
-            r2 = run_psgd_workload(a2, rank, world, local)
-            r2.update(metric=metric_name("psgd"), unit="samples/s", n_gpus=world)
-            also.append(r2)
         if world == 1:
-            a3 = copy.copy(args)
-            a3.no_cpu = True
-            a3.steps, a3.warmup = 2, 3
-            r3 = run_sweep_workload("pbcd", a3, rank, world, local)
-            r3.update(metric=metric_name("pbcd"), unit="s/epoch", n_gpus=1)
-            also.append(r3)
+            # the sequential solvers (north_star: pcd / pbcd epoch time at 1 GPU), each with its CPU baseline
+            for nm in ("pcd", "pbcd", "allsub", "c1"):
+                a3 = copy.copy(args)
+                a3.steps, a3.warmup = (3, 3) if nm != "c1" else (10, 3)
+                a3.cpu_budget = min(args.cpu_budget, 8.0)
+                r3 = run_sweep_workload(nm, a3, rank, world, local)
+                r3.update(metric=metric_name(nm), unit="s/epoch", n_gpus=1, steps=a3.steps, warmup=a3.warmup,
+                          higher_is_better=False, dtype="f64", data="synthetic")
+                also.append(r3)
+        else:
+            a2 = copy.copy(args)
+            a2.no_cpu = True
+            a2.steps, a2.warmup = min(args.steps, 10), 3
+            r2 = run_psgd_workload(a2, rank, world, local, "strong")
+            r2.update(metric=metric_name("psgd"), unit="samples/s", n_gpus=world, steps=a2.steps, warmup=a2.warmup,
+                      higher_is_better=True, scaling="strong", dtype="f64", data="synthetic")
+            also.append(r2)
     if rank == 0:
         line = {"metric": metric_name(name), "value": res.pop("value"),
                 "unit": "samples/s" if name == "psgd" else "s/epoch", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"),
-                "higher_is_better": name == "psgd", "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic"}
+                "higher_is_better": name == "psgd",
+                "scaling": "weak" if not (name == "psgd" and args.psgd_batch == "strong") else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
         line.update(res)
         if also:
             line["also"] = also

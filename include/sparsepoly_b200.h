@@ -40,7 +40,8 @@ extern "C" {
                                        bits 8..15 (debug): a window speculates when <= 1/value of its
                                        coordinates start nonzero (0 = built-in default: <= 55 %) */
 
-#define SP_PSGD_CHUNK 64      /* nonzeros per work item of the planned psgd column pass */
+#define SP_PSGD_CHUNK 64      /* nonzeros per chunk of a long column in the planned psgd column pass */
+#define SP_PSGD_SHORT 8       /* columns of at most this many nonzeros are summed by one group of lanes */
 #define SP_PSGD_BAND_CAP 2048 /* band values per column and rank of the squared-l1,2 selection */
 #define SP_MAX_RANKS 8        /* most ranks (GPUs of one NVSwitch domain) a psgd fit is sharded over */
 #define SP_PSGD_CHANNELS 2    /* flag channels per rank: 0 step barriers, 1 exchanges inside the selection */
@@ -242,18 +243,22 @@ int sp_psgd_epoch(const sp_dataset *ds, const double *y, double *P_odk, int n_or
  * memory, all others on the device.  Sharded plans (world > 1) order a minibatch's columns by
  * (owner = feature % world, feature) and carry the owner-side tables. */
 typedef struct sp_psgd_plan {
-    int32_t n_minibatches, batch_local, n_local, chunk;     /* chunk must equal SP_PSGD_CHUNK */
+    int32_t n_minibatches, batch_local, n_local;
+    int32_t chunk, short_max;      /* must equal SP_PSGD_CHUNK / SP_PSGD_SHORT */
     const int64_t *mb_eptr_host;   /* [M+1] first nonzero of every minibatch */
     const int64_t *mb_uptr_host;   /* [M+1] first column (distinct feature) of every minibatch */
-    const int64_t *mb_cptr_host;   /* [M+1] first chunk: minibatch m has ceil(n_entries/chunk) chunks */
-    const int64_t *mb_sptr_host;   /* [M+1] first entry of split_u */
-    const int32_t *e_pos;          /* [E] position of the sample inside its minibatch | 0x80000000 on the
-                                      first nonzero of a column */
+    const int64_t *mb_shptr_host;  /* [M+1] first entry of short_u */
+    const int64_t *mb_lcptr_host;  /* [M+1] first entry of lc_u / lc_e0 */
+    const int64_t *mb_mlptr_host;  /* [M+1] first entry of ml_u / ml_c0 */
+    const int32_t *e_pos;          /* [E] position of the sample inside its minibatch */
     const double *e_x;             /* [E] value */
     const int32_t *u_feat;         /* [U] feature id of every column */
     const int64_t *u_ptr;          /* [U+1] first nonzero of every column */
-    const int32_t *chunk_u0;       /* [n_chunks] column that holds the chunk's first nonzero */
-    const int32_t *split_u;        /* [S] columns whose nonzeros span more than one chunk */
+    const int32_t *short_u;        /* [Ns] columns of <= short_max nonzeros */
+    const int32_t *lc_u;           /* [Nc] chunks of the longer columns: column ... */
+    const int64_t *lc_e0;          /* [Nc] ... and first nonzero; a chunk ends after `chunk` nonzeros or with its column */
+    const int32_t *ml_u;           /* [Nm] columns of more than one chunk ... */
+    const int32_t *ml_c0;          /* [Nm] ... and the index of their first chunk inside the minibatch's chunk list */
     int64_t max_chunks;            /* most chunks in one minibatch (sizes part_g / part_w) */
     int64_t max_cols;              /* most columns in one minibatch (sizes the staging buffers) */
     /* sharded only */
@@ -277,7 +282,7 @@ typedef struct sp_psgd_ctx {
     int32_t world, rank;
     double *bufA, *bufdL;          /* [batch_local, arows*k], [batch_local]: per-sample tables of one minibatch */
     double *sample_loss;           /* [n_local] */
-    double *part_g, *part_w;       /* [max_chunks, 2, n_orders*k], [max_chunks, 2] */
+    double *part_g, *part_w;       /* [max_chunks, n_orders*k], [max_chunks] */
     double *work;                  /* sp_psgd_plan_work_doubles() */
     double *xwork;                 /* sp_psgd_plan_xwork_doubles(): statistics boxes (peer-visible when sharded) */
     double C, Cw;

@@ -34,7 +34,8 @@ t0 = time.time()
 plan = PsgdPlan(ds.csr, idx, d, batch)
 torch.cuda.synchronize()
 print(f"plan {time.time()-t0:.2f}s M={plan.n_minibatches} cols/mb={plan.n_cols/plan.n_minibatches:.0f} "
-      f"max_chunks={plan.max_chunks} split/mb={len(plan.split_u)/plan.n_minibatches:.1f} bytes={plan.nbytes()/1e9:.2f}GB", flush=True)
+      f"short/mb={len(plan.short_u)/plan.n_minibatches:.0f} chunks/mb={len(plan.lc_u)/plan.n_minibatches:.0f} "
+      f"multi/mb={len(plan.ml_u)/plan.n_minibatches:.0f} bytes={plan.nbytes()/1e9:.2f}GB", flush=True)
 lams = torch.ones(k, dtype=torch.float64, device=dev)
 ctx = PsgdContext(plan, 1, k, 2, reg, "logistic", True, lams)
 P = torch.from_numpy(0.01 * np.random.RandomState(0).randn(1, d, k)).to(dev)

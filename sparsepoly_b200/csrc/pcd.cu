@@ -21,6 +21,8 @@
 //     DSMEM hop behind the scalar chain; otherwise they are recomputed after the write-back;
 //   * records the previous two positions may still be rewriting are tagged by the plan (bits
 //     31/30 of flag_idx) and re-read from global memory after the barrier.
+#include <vector>
+
 #include "common.cuh"
 #include "cluster.cuh"
 #include "pcd_common.cuh"
@@ -552,6 +554,19 @@ extern "C" int sp_cd_linear_epoch(const sp_dataset *ds, const sp_plan *plan, dou
     return dispatch_loss<KIND_LINEAR, 1>(loss, a, plan->threads, pick_nz(ds, plan), (cudaStream_t)stream);
 }
 
+// flags[s] = 1 when row s of P [k,d] has a nonzero entry
+__global__ void row_any_nonzero_kernel(const double *__restrict__ P, int d, int *flags) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const double *row = P + (size_t)blockIdx.x * d;
+    int any = 0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) any |= (row[j] != 0.0);
+    if (any) s_any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[blockIdx.x] = s_any;
+}
+
 extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P_kd, int k,
                             const double *lams, int degree, double beta, double gamma, double eta,
                             int reg, int loss, double *rec, int rec_stride, double *regstate,
@@ -585,9 +600,27 @@ extern "C" int sp_pcd_epoch(const sp_dataset *ds, const sp_plan *plan, double *P
     if (d == 0) return SP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int nz = plan->win ? 1 : pick_nz(ds, plan);
+    // Dead components (ANOVA, degree >= 2, beta > 0): when row P[s,:] is entirely zero, A^t_i = 0 for every
+    // t >= 1, so dA[m-1] = x (A^{m-1} - p dA[m-2]) = 0 on every nonzero, g = h = 0, the step is
+    // (lams*0 + beta*0) / beta = 0 and the prox of 0 is 0 for l1 / squaredl12 / omegati: the reference's sweep
+    // over that component (pcd.py:33-68, :92-135) changes nothing and adds 0 to the violation.  It is skipped
+    // exactly; with beta == 0 the reference divides 0/0, so there the sweep runs as usual.  One small
+    // reduction + ONE stream synchronisation per call (the only one this library makes inside an epoch).
+    std::vector<int> alive(k, 1);
+    if (degree >= 2 && beta > 0.0) {
+        int *flags = nullptr;
+        SP_CUDA(cudaMallocAsync((void **)&flags, sizeof(int) * k, st));
+        row_any_nonzero_kernel<<<k, 256, 0, st>>>(P_kd, d, flags);
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(alive.data(), flags, sizeof(int) * k, cudaMemcpyDeviceToHost, st);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+        cudaFreeAsync(flags, st);
+        if (e1 != cudaSuccess) return sp_check_cuda(e1, "sp_pcd_epoch: dead-component scan");
+    }
     for (int ss = 0; ss < k; ss++) {
         const int s = idx_comp_host[ss];
         if (s < 0 || s >= k) { sp_set_error("sp_pcd_epoch: bad component index %d", s); return SP_ERR_INVALID; }
+        if (!alive[s]) continue;
         double *prow = P_kd + (size_t)s * d;
         rc = sp_rows_precompute_one(ds, prow, degree, rec, rec_stride, st);      // pcd.py:94 / pcd_all.py:65
         if (rc) return rc;

@@ -47,7 +47,7 @@ constexpr int PL_THREADS = 256;
 constexpr int CH = SP_PSGD_CHUNK;
 constexpr int BAND_CAP = SP_PSGD_BAND_CAP;          // band values per column and rank
 constexpr int BAND_TOTAL = 2048;                    // band values per column over all ranks (shared memory)
-constexpr int STAT_PART_MAX = 148 * 8;              // most blocks of the statistics pass
+constexpr int STAT_PART_MAX = 148 * 3;              // most blocks of the statistics pass
 constexpr double BAND_DELTA = 0.02;
 constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -93,7 +93,7 @@ struct RowsArgs {
 };
 
 template <int DEG, int NORD, int G, int KCH, bool STAGED>
-__global__ void __launch_bounds__(PL_THREADS) psgd_rows_kernel(const RowsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 2) psgd_rows_kernel(const RowsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_rows_kernel(const RowsArgs a)
                 if (a.fit_linear) ypred += xl * (STAGED ? a.wsrc[jl] : a.wsrc[jl] * a.invCw);
             }
             const int cnt = min(G, en - base);
-            constexpr int UB = (KCH * NORD <= 2) ? 8 : 2;
+            constexpr int UB = (16 / (KCH * NORD) > 8) ? 8 : ((16 / (KCH * NORD) < 1) ? 1 : 16 / (KCH * NORD));   // row gathers in flight
             for (int q0 = 0; q0 < cnt; q0 += UB) {
                 double pv[UB][KCH][NORD], xv[UB];
 #pragma unroll
@@ -212,22 +212,23 @@ struct StepArgs {                        // psgd._update_params for one row (psg
 
 struct ColsArgs {
     int k, d;                            // d: rows of P (this rank's rows when sharded)
-    const int32_t *e_pos;                // minibatch-relative entry arrays
+    const int32_t *e_pos;                // ABSOLUTE entry arrays: position of the sample inside its minibatch, value
     const double *e_x;
-    long long n_entries;
-    int n_chunks;
     const int32_t *u_feat;               // ABSOLUTE column arrays
     const int64_t *u_ptr;
-    long long e_base;                    // absolute entry offset of the minibatch
     long long u_base;                    // absolute column offset of the minibatch
-    const int32_t *chunk_u0;             // minibatch-relative: absolute column of every chunk's first entry
-    const int32_t *split_u;              // minibatch-relative list of columns spanning > 1 chunk
-    int n_split;
+    const int32_t *short_u;              // minibatch-relative lists: short columns (<= SP_PSGD_SHORT nonzeros) ...
+    int n_short;
+    const int32_t *lc_u;                 // ... chunks of the long columns (column, first nonzero) ...
+    const int64_t *lc_e0;
+    int n_chunks;
+    const int32_t *ml_u, *ml_c0;         // ... and the long columns of several chunks (column, its first chunk)
+    int n_multi;
     const double *bufA, *bufdL;
     const double *lams, *thr;
     double *P, *w;                       // APPLY: raw model (read + written)
     const double *stage, *stage_w;       // PUSH: staged true values [U][n_orders][k], [U]
-    double *part_g, *part_w;             // partial sums of split columns [n_chunks][2][n_orders*k], [n_chunks][2]
+    double *part_g, *part_w;             // partial sums of the chunks [n_chunks][n_orders*k], [n_chunks]
     StepArgs s;
     // PUSH: owner inboxes (peer memory)
     int world, rank;
@@ -264,24 +265,11 @@ __device__ __forceinline__ void apply_row(const StepArgs &s, double *P, double *
     }
 }
 
-template <int DEG, int NORD, int G, int KCH, int MODE>
-__device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int ucol, int feat, bool complete, int chunk,
-                                              bool first_col, const double (&g)[KCH][NORD], double gw,
-                                              const double (&pold)[KCH][NORD], const double (&thr)[KCH][NORD]) {
+// a column's gradient row is complete: apply the step (single rank) or push it to the owner's inbox
+template <int NORD, int G, int KCH, int MODE>
+__device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int ucol, int feat, const double (&g)[KCH][NORD],
+                                              double gw, const double (&pold)[KCH][NORD], const double (&thr)[KCH][NORD]) {
     const int k = a.k;
-    if (!complete) {                                        // piece of a split column: summed by psgd_split_kernel
-        const size_t slot = (size_t)chunk * 2 + (first_col ? 0 : 1);
-#pragma unroll
-        for (int c = 0; c < KCH; c++) {
-            const int sidx = lane + G * c;
-            if (sidx < k) {
-#pragma unroll
-                for (int o = 0; o < NORD; o++) a.part_g[(slot * NORD + o) * k + sidx] = g[c][o];
-            }
-        }
-        if (lane == 0) a.part_w[slot] = gw;
-        return;
-    }
     if (MODE == MODE_APPLY) {
         apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d, k, feat, lane, g, gw, pold, thr);
     } else {
@@ -320,15 +308,32 @@ __device__ __forceinline__ void load_row(const ColsArgs &a, int lane, int feat, 
     }
 }
 
+// one term of psgd._update_grads (psgd.py:60-91) for nonzero x of a sample with table rows av, dloss dl
+template <int DEG, int NORD, int KCH, int AR>
+__device__ __forceinline__ void add_term(double (&g)[KCH][NORD], double &gw, double x, double dl, const double (&av)[KCH][AR],
+                                         const double (&pold)[KCH][NORD], const double (&lam)[KCH]) {
+    gw += dl * x;                                             // psgd.py:86
+#pragma unroll
+    for (int c = 0; c < KCH; c++)
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {
+            double dprev = x;                                 // _grad_anova, psgd.py:25-31
+#pragma unroll
+            for (int t = 1; t < DEG - o; t++) dprev = x * (av[c][arow_off<DEG, NORD>(o) + t - 1] - pold[c][o] * dprev);
+            g[c][o] += (dl * lam[c]) * dprev;                 // psgd.py:91
+        }
+}
+
+// ---- short columns (<= SP_PSGD_SHORT nonzeros; 95 % of a Criteo-shaped minibatch's columns): one group of lanes
+// per column, all of its table-row gathers in flight at once, terms added in sample order (the reference's)
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS) psgd_cols_kernel(const ColsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const ColsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
+    constexpr int SH = SP_PSGD_SHORT;
+    static_assert(SH <= 8 && G >= 8, "a group's lanes hold the column's nonzeros");
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
-    const int gshift = (threadIdx.x & 31) & ~(G - 1);
     const int gpb = PL_THREADS / G;
-    const int chunk = blockIdx.x * gpb + threadIdx.x / G;
-    if (chunk >= a.n_chunks) return;
     const int k = a.k;
     double lam[KCH], thr[KCH][NORD];
 #pragma unroll
@@ -338,110 +343,140 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_cols_kernel(const ColsArgs a)
 #pragma unroll
         for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
     }
-    const long long ce0 = (long long)chunk * CH;
-    const long long ce1 = (ce0 + CH < a.n_entries) ? ce0 + CH : a.n_entries;
-    const bool ends_here = (ce1 == a.n_entries) || (a.e_pos[ce1] < 0);
-    int ubase = a.chunk_u0[chunk] - 1;            // (the chunk's first entry counts as a column start below)
-    double g[KCH][NORD], pold[KCH][NORD];
-    double gw = 0.0;
-    int cur_feat = -1, cur_u = -1;
-    bool cur_started = false, cur_first = true, have = false;
-    for (long long base = ce0; base < ce1; base += G) {
-        const long long e = base + lane;
+    for (int q = blockIdx.x * gpb + threadIdx.x / G; q < a.n_short; q += gridDim.x * gpb) {
+        const int u = a.short_u[q];
+        const long long e0 = a.u_ptr[u];
+        const int len = (int)(a.u_ptr[u + 1] - e0);
+        const int feat = a.u_feat[u];
         int ep = 0;
         double ex = 0.0;
-        if (e < ce1) { ep = a.e_pos[e]; ex = a.e_x[e]; }
-        const bool nf_l = e < ce1 && (ep < 0 || e == ce0);
-        const unsigned bal = (__ballot_sync(gmask, nf_l) >> gshift) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-        const int ucol_l = ubase + __popc(bal & ((2u << lane) - 1u));
-        int fj_l = 0;
-        if (nf_l) fj_l = a.u_feat[ucol_l];
-        ubase += __popc(bal);
-        const int cnt = (int)((ce1 - base < G) ? ce1 - base : G);
-        constexpr int UB = (KCH * NORD <= 2) ? 8 : 2;
-        for (int q0 = 0; q0 < cnt; q0 += UB) {
-            double av[UB][KCH][AR], dl[UB], xv[UB], pn[UB][KCH][NORD];
-            int nf[UB], fj[UB], uc[UB];
+        if (lane < len) { ep = a.e_pos[e0 + lane]; ex = a.e_x[e0 + lane]; }
+        double pold[KCH][NORD];
+        load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
+        double g[KCH][NORD];
+        double gw = 0.0;
 #pragma unroll
-            for (int u = 0; u < UB; u++) {                      // all loads of the batch first
-                const int q = (q0 + u) & (G - 1);
-                const int pos = __shfl_sync(gmask, ep, q, G) & 0x7fffffff;
-                xv[u] = __shfl_sync(gmask, ex, q, G);
-                nf[u] = (q0 + u < cnt) ? (int)((bal >> q) & 1u) : 0;
-                fj[u] = __shfl_sync(gmask, fj_l, q, G);
-                uc[u] = __shfl_sync(gmask, ucol_l, q, G);
-                const bool live = q0 + u < cnt;
-                dl[u] = live ? a.bufdL[pos] : 0.0;
+        for (int c = 0; c < KCH; c++)
+#pragma unroll
+            for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+        constexpr int UBR = 16 / (KCH * AR);
+        constexpr int UB = UBR > SH ? SH : (UBR < 1 ? 1 : UBR);
+        for (int q0 = 0; q0 < len; q0 += UB) {
+            double av[UB][KCH][AR], dl[UB], xv[UB];
+#pragma unroll
+            for (int t = 0; t < UB; t++) {
+                const int pos = __shfl_sync(gmask, ep, (q0 + t) & (G - 1), G);
+                xv[t] = __shfl_sync(gmask, ex, (q0 + t) & (G - 1), G);
+                const bool live = q0 + t < len;
+                dl[t] = live ? a.bufdL[pos] : 0.0;
 #pragma unroll
                 for (int c = 0; c < KCH; c++) {
                     const int s = lane + G * c;
 #pragma unroll
-                    for (int r = 0; r < AR; r++) av[u][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                    for (int r = 0; r < AR; r++) av[t][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
                 }
-                if (nf[u]) load_row<NORD, G, KCH, MODE>(a, lane, fj[u], uc[u] - a.u_base, pn[u], thr);
             }
 #pragma unroll
-            for (int u = 0; u < UB; u++) {
-                if (q0 + u >= cnt) break;
-                if (nf[u]) {
-                    if (have)                                     // the previous column ends before this entry
-                        finish_column<DEG, NORD, G, KCH, MODE>(a, lane, cur_u, cur_feat, cur_started, chunk, cur_first,
-                                                               g, gw, pold, thr);
-                    cur_first = !have;
-                    have = true;
-                    cur_feat = fj[u]; cur_u = uc[u];
-                    cur_started = cur_first ? (__shfl_sync(gmask, ep, (q0 + u) & (G - 1), G) < 0) : true;
-                    gw = 0.0;
-#pragma unroll
-                    for (int c = 0; c < KCH; c++)
-#pragma unroll
-                        for (int o = 0; o < NORD; o++) { g[c][o] = 0.0; pold[c][o] = pn[u][c][o]; }
-                }
-                const double x = xv[u];
-                gw += dl[u] * x;                                  // psgd.py:86
-#pragma unroll
-                for (int c = 0; c < KCH; c++)
-#pragma unroll
-                    for (int o = 0; o < NORD; o++) {
-                        double dprev = x;                         // _grad_anova, psgd.py:25-31
-#pragma unroll
-                        for (int t = 1; t < DEG - o; t++)
-                            dprev = x * (av[u][c][arow_off<DEG, NORD>(o) + t - 1] - pold[c][o] * dprev);
-                        g[c][o] += (dl[u] * lam[c]) * dprev;      // psgd.py:91
-                    }
-            }
+            for (int t = 0; t < UB; t++)
+                if (q0 + t < len) add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold, lam);
         }
+        finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
     }
-    if (have)
-        finish_column<DEG, NORD, G, KCH, MODE>(a, lane, cur_u, cur_feat, cur_started && ends_here, chunk, cur_first, g, gw,
-                                               pold, thr);
 }
 
-// columns that span several chunks: add their pieces in chunk order, then finish them
+// ---- long columns: cut into chunks of SP_PSGD_CHUNK nonzeros of ONE column -- a pure streaming sum, no column
+// bookkeeping inside.  A column of one chunk is finished right here, the others leave one partial per chunk.
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS) psgd_split_kernel(const ColsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_long_kernel(const ColsArgs a) {
+    constexpr int AR = ARows<DEG, NORD>::value;
     const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
-    const int q = blockIdx.x * gpb + threadIdx.x / G;
-    if (q >= a.n_split) return;
+    const int chunk = blockIdx.x * gpb + threadIdx.x / G;
+    if (chunk >= a.n_chunks) return;
     const int k = a.k;
-    const int u = a.split_u[q];
-    const long long s_rel = a.u_ptr[u] - a.e_base, e_rel = a.u_ptr[u + 1] - a.e_base;
-    const int c0 = (int)(s_rel / CH), c1 = (int)((e_rel - 1) / CH);
-    double thr[KCH][NORD], g[KCH][NORD], pold[KCH][NORD];
+    const int u = a.lc_u[chunk];
+    const long long ce0 = a.lc_e0[chunk];
+    const long long cend = a.u_ptr[u + 1];
+    const long long ce1 = ce0 + CH < cend ? ce0 + CH : cend;
+    const bool single = (cend - a.u_ptr[u]) <= CH;
+    const int feat = a.u_feat[u];
+    double lam[KCH], thr[KCH][NORD], pold[KCH][NORD], g[KCH][NORD];
+    double gw = 0.0;
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int s = lane + G * c;
+        lam[c] = s < k ? a.lams[s] : 0.0;
+#pragma unroll
+        for (int o = 0; o < NORD; o++) { thr[c][o] = s < k ? a.thr[o * k + s] : 0.0; g[c][o] = 0.0; }
+    }
+    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
+    constexpr int UBR = 16 / (KCH * AR);
+    constexpr int UB = UBR > 8 ? 8 : (UBR < 1 ? 1 : UBR);
+    int ep = 0;
+    double ex = 0.0;
+    if (ce0 + lane < ce1) { ep = a.e_pos[ce0 + lane]; ex = a.e_x[ce0 + lane]; }
+    for (long long base = ce0; base < ce1; base += G) {
+        const int cnt = (int)((ce1 - base < G) ? ce1 - base : G);
+        int ep_n = 0;                                          // next block of (position, value): in flight during this one
+        double ex_n = 0.0;
+        if (base + G + lane < ce1) { ep_n = a.e_pos[base + G + lane]; ex_n = a.e_x[base + G + lane]; }
+        for (int q0 = 0; q0 < cnt; q0 += UB) {
+            double av[UB][KCH][AR], dl[UB], xv[UB];
+#pragma unroll
+            for (int t = 0; t < UB; t++) {                      // UB independent gathers in flight
+                const int pos = __shfl_sync(gmask, ep, (q0 + t) & (G - 1), G);
+                xv[t] = __shfl_sync(gmask, ex, (q0 + t) & (G - 1), G);
+                const bool live = q0 + t < cnt;
+                dl[t] = live ? a.bufdL[pos] : 0.0;
+#pragma unroll
+                for (int c = 0; c < KCH; c++) {
+                    const int s = lane + G * c;
+#pragma unroll
+                    for (int r = 0; r < AR; r++) av[t][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < UB; t++)
+                if (q0 + t < cnt) add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold, lam);
+        }
+        ep = ep_n; ex = ex_n;
+    }
+    if (single) {
+        finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
+    } else {
+#pragma unroll
+        for (int c = 0; c < KCH; c++) {
+            const int s = lane + G * c;
+            if (s < k) {
+#pragma unroll
+                for (int o = 0; o < NORD; o++) a.part_g[((size_t)chunk * NORD + o) * k + s] = g[c][o];
+            }
+        }
+        if (lane == 0) a.part_w[chunk] = gw;
+    }
+}
+
+// long columns of several chunks: one block per column adds the chunks' partial sums -- group w the chunks w,
+// w+G', ... in order, then the groups' sums in group order (a fixed association: deterministic) -- and finishes it
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__global__ void __launch_bounds__(PL_THREADS) psgd_cols_combine_kernel(const ColsArgs a) {
+    constexpr int GPB = PL_THREADS / G;
+    constexpr int ROW = KCH * G * NORD + 1;
+    __shared__ double sh[GPB * ROW];
+    const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
+    const int k = a.k;
+    const int u = a.ml_u[blockIdx.x];
+    const int c0 = a.ml_c0[blockIdx.x];
+    const int np = (int)((a.u_ptr[u + 1] - a.u_ptr[u] + CH - 1) / CH);
+    double g[KCH][NORD];
     double gw = 0.0;
 #pragma unroll
     for (int c = 0; c < KCH; c++)
 #pragma unroll
-        for (int o = 0; o < NORD; o++) {
-            const int s = lane + G * c;
-            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
-            g[c][o] = 0.0;
-        }
-    const int feat = a.u_feat[u];
-    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
-    for (int ch = c0; ch <= c1; ch++) {
-        const size_t slot = (size_t)ch * 2 + ((ch == c0 && s_rel > (long long)c0 * CH) ? 1 : 0);
+        for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+    for (int pc = grp; pc < np; pc += GPB) {
+        const size_t slot = (size_t)(c0 + pc);
 #pragma unroll
         for (int c = 0; c < KCH; c++) {
             const int s = lane + G * c;
@@ -452,7 +487,32 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_split_kernel(const ColsArgs a
         }
         gw += a.part_w[slot];
     }
-    finish_column<DEG, NORD, G, KCH, MODE>(a, lane, u, feat, true, 0, true, g, gw, pold, thr);
+#pragma unroll
+    for (int c = 0; c < KCH; c++)
+#pragma unroll
+        for (int o = 0; o < NORD; o++) sh[grp * ROW + (c * NORD + o) * G + lane] = g[c][o];
+    if (lane == 0) sh[grp * ROW + ROW - 1] = gw;
+    __syncthreads();
+    if (grp != 0) return;
+    const int ngrp = np < GPB ? np : GPB;
+    for (int w = 1; w < ngrp; w++) {
+#pragma unroll
+        for (int c = 0; c < KCH; c++)
+#pragma unroll
+            for (int o = 0; o < NORD; o++) g[c][o] += sh[w * ROW + (c * NORD + o) * G + lane];
+        gw += sh[w * ROW + ROW - 1];
+    }
+    double thr[KCH][NORD], pold[KCH][NORD];
+#pragma unroll
+    for (int c = 0; c < KCH; c++)
+#pragma unroll
+        for (int o = 0; o < NORD; o++) {
+            const int s = lane + G * c;
+            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
+        }
+    const int feat = a.u_feat[u];
+    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
+    finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
 }
 
 // ------------------------------------------------------------------------------------ sharded: pull / owner
@@ -606,76 +666,88 @@ __device__ __forceinline__ double predict_tau(const double *state, int ncol, int
 
 // One read-only pass over this rank's rows: per-block (sum, count) of the values above the statistics
 // threshold of every column -- the band's upper edge (band pass) or a.tau[c] (generic pass) -- and, in a
-// band pass, the values inside the band.  Partials are combined in fixed order.
+// band pass, the values inside the band.  Partials are combined in fixed order.  VEC = 2: a thread owns two
+// adjacent columns and streams 16-byte loads, 8 in flight (needs an even k); ssum / scnt hold VEC*blockDim.
+template <int VEC>
 __device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, double *scnt, bool band_pass) {
     const int tid = threadIdx.x, T = blockDim.x, nblk = gridDim.x, k = a.k, d = a.d;
     const int ncol = a.n_orders * k;
-    const int tpr = k < T ? k : T;
+    const int tpr = k / VEC;                        // threads per row (host: k <= 128, k % VEC == 0)
     const int rpp = T / tpr;
-    const int col = tid % tpr, row0 = tid / tpr;
-    const bool worker = tid < tpr * rpp;
+    const int cq = tid % tpr, row0 = tid / tpr;
+    const bool act = tid < tpr * rpp;
     const double bdelta = a.state[4] > 0.0 ? a.state[4] : BAND_DELTA;
     for (int o = 0; o < a.n_orders; o++) {
-        for (int c0 = 0; c0 < k; c0 += tpr) {
-            const int cc = c0 + col;
-            const bool act = worker && cc < k;
-            const int cidx = o * k + (act ? cc : 0);
-            const double *P = a.P + (size_t)o * d * k;
-            const double Tc = a.thr[cidx];
-            double hi, lo;
-            bool band_on = false;
+        const double *P = a.P + (size_t)o * d * k;
+        double Tc[VEC], hi[VEC], lo[VEC], lsum[VEC], lcnt[VEC];
+        bool band_on[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const int cidx = o * k + (act ? cq * VEC + v : 0);
+            Tc[v] = a.thr[cidx];
+            band_on[v] = false;
             if (band_pass) {
                 const double last = a.state[8 + cidx];
-                band_on = a.state[0] > 0.0 && a.strength > 0.0 && last > 0.0;
-                const double tp = band_on ? predict_tau(a.state, ncol, cidx, a.strength) : 0.0;
-                hi = band_on ? tp * (1.0 + bdelta) : 0.0;
-                lo = band_on ? tp * (1.0 - bdelta) : 0.0;
+                band_on[v] = a.state[0] > 0.0 && a.strength > 0.0 && last > 0.0;
+                const double tp = band_on[v] ? predict_tau(a.state, ncol, cidx, a.strength) : 0.0;
+                hi[v] = band_on[v] ? tp * (1.0 + bdelta) : 0.0;
+                lo[v] = band_on[v] ? tp * (1.0 - bdelta) : 0.0;
             } else {
-                hi = lo = a.tau[cidx];
+                hi[v] = lo[v] = a.tau[cidx];
             }
-            double lsum = 0.0, lcnt = 0.0;
-            if (act) {
-                const long long step = (long long)nblk * rpp;
-                long long r = (long long)blockIdx.x * rpp + row0;
-                for (; r + 7 * step < d; r += 8 * step) {       // 8 independent loads in flight
-                    double rv[8];
+            lsum[v] = 0.0; lcnt[v] = 0.0;
+        }
+        auto take = [&](double raw, int v) {
+            const double m = fabs(raw) - Tc[v];
+            if (m > 0.0) {
+                const double val = m * a.invC;
+                if (val > hi[v]) { lsum[v] += val; lcnt[v] += 1.0; }
+                else if (band_on[v] && val > lo[v]) {
+                    const int cidx = o * k + cq * VEC + v;
+                    const int bi = atomicAdd(a.band_n + cidx, 1);
+                    if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = val;
+                }
+            }
+        };
+        if (act) {
+            const long long step = (long long)nblk * rpp;
+            long long r = (long long)blockIdx.x * rpp + row0;
+            if (VEC == 2) {
+                const double2 *P2 = reinterpret_cast<const double2 *>(P);
+                const int k2 = k / 2;
+                for (; r + 7 * step < d; r += 8 * step) {       // 8 independent 16-byte loads in flight
+                    double2 rv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) rv[u] = P[(size_t)(r + u * step) * k + cc];
+                    for (int u = 0; u < 8; u++) rv[u] = P2[(size_t)(r + u * step) * k2 + cq];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const double m = fabs(rv[u]) - Tc;
-                        if (m > 0.0) {
-                            const double v = m * a.invC;
-                            if (v > hi) { lsum += v; lcnt += 1.0; }
-                            else if (band_on && v > lo) {
-                                const int bi = atomicAdd(a.band_n + cidx, 1);
-                                if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = v;
-                            }
-                        }
-                    }
+                    for (int u = 0; u < 8; u++) { take(rv[u].x, 0); take(rv[u].y, VEC - 1); }
                 }
                 for (; r < d; r += step) {
-                    const double m = fabs(P[(size_t)r * k + cc]) - Tc;
-                    if (m > 0.0) {
-                        const double v = m * a.invC;
-                        if (v > hi) { lsum += v; lcnt += 1.0; }
-                        else if (band_on && v > lo) {
-                            const int bi = atomicAdd(a.band_n + cidx, 1);
-                            if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = v;
-                        }
-                    }
+                    const double2 rv = P2[(size_t)r * k2 + cq];
+                    take(rv.x, 0); take(rv.y, VEC - 1);
                 }
+            } else {
+                for (; r + 7 * step < d; r += 8 * step) {
+                    double rv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) rv[u] = P[(size_t)(r + u * step) * k + cq];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) take(rv[u], 0);
+                }
+                for (; r < d; r += step) take(P[(size_t)r * k + cq], 0);
             }
-            ssum[tid] = lsum; scnt[tid] = lcnt;
-            __syncthreads();
-            if (tid < tpr && c0 + tid < k) {                     // fixed-order combine over the block's rows
-                double s = 0.0, n = 0.0;
-                for (int r = 0; r < rpp; r++) { s += ssum[r * tpr + tid]; n += scnt[r * tpr + tid]; }
-                a.psum[(size_t)blockIdx.x * ncol + o * k + c0 + tid] = s;
-                a.pcnt[(size_t)blockIdx.x * ncol + o * k + c0 + tid] = n;
-            }
-            __syncthreads();
         }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) { ssum[v * T + tid] = lsum[v]; scnt[v * T + tid] = lcnt[v]; }
+        __syncthreads();
+        if (tid < k) {                                        // fixed-order combine over the block's rows
+            const int q = tid / VEC, v = tid % VEC;
+            double sm = 0.0, n = 0.0;
+            for (int r = 0; r < rpp; r++) { sm += ssum[v * T + r * tpr + q]; n += scnt[v * T + r * tpr + q]; }
+            a.psum[(size_t)blockIdx.x * ncol + o * k + tid] = sm;
+            a.pcnt[(size_t)blockIdx.x * ncol + o * k + tid] = n;
+        }
+        __syncthreads();
     }
 }
 
@@ -696,63 +768,30 @@ __device__ __forceinline__ void reduce_partials(const StatArgs &a, int cidx, int
     __syncthreads();
 }
 
-// band pass as its own streaming launch; the LAST block to finish reduces the partials and publishes this
-// rank's statbox (to every rank when sharded)
-__global__ void __launch_bounds__(PL_THREADS, 4) psgd_stats_kernel(const StatArgs a) {
+// band pass as its own streaming launch
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_stats_kernel(const StatArgs a) {
+    __shared__ double ssum[2 * PL_THREADS], scnt[2 * PL_THREADS];
+    if ((a.k & 1) == 0) stats_pass<2>(a, ssum, scnt, true);
+    else stats_pass<1>(a, ssum, scnt, true);
+}
+
+// sharded: block c reduces column c's partials (fixed order) and publishes this rank's statistics + band to
+// every rank's statbox; the band counter is reset for the next minibatch
+__global__ void __launch_bounds__(PL_THREADS) psgd_stats_publish_kernel(const StatArgs a, int npart) {
     __shared__ double ssum[PL_THREADS], scnt[PL_THREADS];
-    __shared__ int s_last;
-    stats_pass(a, ssum, scnt, true);
-    const int ncol = a.n_orders * a.k;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(a.band_n + ncol, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // column totals: thread = (column, slice); slices added in fixed order -> deterministic
-    __shared__ int s_nb[PL_THREADS];
-    const int T = blockDim.x, npart = gridDim.x;
-    for (int c0 = 0; c0 < ncol; c0 += T) {
-        const int tprA = (ncol - c0 < T) ? ncol - c0 : T;
-        const int slices = T / tprA;
-        const int col = c0 + (int)threadIdx.x % tprA, sl = (int)threadIdx.x / tprA;
-        double s = 0.0, n = 0.0;
-        if (sl < slices) {
-            int b = sl;
-            for (; b + 3 * slices < npart; b += 4 * slices) {
-                const double s0 = __ldcg(a.psum + (size_t)b * ncol + col), s1 = __ldcg(a.psum + (size_t)(b + slices) * ncol + col);
-                const double s2 = __ldcg(a.psum + (size_t)(b + 2 * slices) * ncol + col), s3 = __ldcg(a.psum + (size_t)(b + 3 * slices) * ncol + col);
-                const double n0 = __ldcg(a.pcnt + (size_t)b * ncol + col), n1 = __ldcg(a.pcnt + (size_t)(b + slices) * ncol + col);
-                const double n2 = __ldcg(a.pcnt + (size_t)(b + 2 * slices) * ncol + col), n3 = __ldcg(a.pcnt + (size_t)(b + 3 * slices) * ncol + col);
-                s += s0; s += s1; s += s2; s += s3;
-                n += n0; n += n1; n += n2; n += n3;
-            }
-            for (; b < npart; b += slices) { s += __ldcg(a.psum + (size_t)b * ncol + col); n += __ldcg(a.pcnt + (size_t)b * ncol + col); }
-        }
-        ssum[threadIdx.x] = s; scnt[threadIdx.x] = n;
-        __syncthreads();
-        if ((int)threadIdx.x < tprA) {
-            double ts = 0.0, tn = 0.0;
-            for (int q = 0; q < slices; q++) { ts += ssum[q * tprA + threadIdx.x]; tn += scnt[q * tprA + threadIdx.x]; }
-            const int cidx = c0 + threadIdx.x;
-            const int nb = *reinterpret_cast<volatile int *>(a.band_n + cidx);
-            s_nb[threadIdx.x] = nb < BAND_CAP ? nb : BAND_CAP;
-            for (int r = 0; r < a.world; r++) {
-                double *box = a.statbox[r];
-                box[cidx] = ts; box[ncol + cidx] = tn; box[2 * ncol + cidx] = (double)nb;
-            }
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < tprA * BAND_CAP; idx += T) {        // the band's values
-            const int cl = idx / BAND_CAP, q = idx % BAND_CAP;
-            if (q < s_nb[cl]) {
-                const double v = __ldcg(a.band + (size_t)(c0 + cl) * BAND_CAP + q);
-                for (int r = 0; r < a.world; r++) a.statbox[r][3 * (size_t)ncol + (size_t)(c0 + cl) * BAND_CAP + q] = v;
-            }
-        }
-        __syncthreads();
+    const int ncol = a.n_orders * a.k, cidx = blockIdx.x;
+    double s, n;
+    reduce_partials(a, cidx, npart, ssum, scnt, &s, &n);
+    const int nb = a.band_n[cidx];
+    const int nv = nb < BAND_CAP ? nb : BAND_CAP;
+    for (int r = 0; r < a.world; r++) {
+        double *box = a.statbox[r];
+        if (threadIdx.x == 0) { box[cidx] = s; box[ncol + cidx] = n; box[2 * ncol + cidx] = (double)nb; }
+        for (int q = threadIdx.x; q < nv; q += blockDim.x)
+            box[3 * (size_t)ncol + (size_t)cidx * BAND_CAP + q] = a.band[(size_t)cidx * BAND_CAP + q];
     }
-    for (int q = threadIdx.x; q <= ncol; q += blockDim.x) a.band_n[q] = 0;     // counters + ticket for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) a.band_n[cidx] = 0;
 }
 
 struct SolveArgs {
@@ -762,6 +801,7 @@ struct SolveArgs {
     double *tau;                         // [ncol] scratch: new thresholds in value units
     double *colres;                      // [2*ncol] reduced (sum, cnt) of a generic pass
     int *fail;                           // [2] (zeroed before the launch): a column could not use its band / overflow
+    int npart;                           // single rank: rows of st.psum / st.pcnt the statistics pass wrote
     const double *statbox_all;           // local statboxes of all ranks [world][statbox_doubles]
     double *xbuf[SP_MAX_RANKS];          // every rank's exchange buffer region of THIS rank [2][2*ncol] (generic passes)
     const double *xbuf_local;            // local exchange buffers of all ranks [world][2][2*ncol]
@@ -791,12 +831,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
             double sumA = 0.0, cntA = 0.0;
             int nbv = 0;
             bool ok = st.state[8 + cidx] > 0.0;
-            for (int r = 0; r < world; r++) {                    // rank order: identical on every rank
-                const double *box = a.statbox_all + (size_t)r * boxlen;
-                sumA += box[cidx]; cntA += box[ncol + cidx];
-                const int nb = (int)box[2 * ncol + cidx];
+            if (world == 1) {                                    // partials + band straight from the statistics pass
+                reduce_partials(st, cidx, a.npart, ssum, scnt, &sumA, &cntA);
+                const int nb = st.band_n[cidx];
                 if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = 1; }
-                nbv += nb < BAND_CAP ? nb : BAND_CAP;
+                nbv = nb < BAND_CAP ? nb : BAND_CAP;
+            } else {
+                for (int r = 0; r < world; r++) {                // rank order: identical on every rank
+                    const double *box = a.statbox_all + (size_t)r * boxlen;
+                    sumA += box[cidx]; cntA += box[ncol + cidx];
+                    const int nb = (int)box[2 * ncol + cidx];
+                    if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = 1; }
+                    nbv += nb < BAND_CAP ? nb : BAND_CAP;
+                }
             }
             if (nbv > BAND_TOTAL) { ok = false; if (tid == 0) a.fail[1] = 1; }
             if (ok) {
@@ -806,12 +853,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
                 while (np2 < nbv) np2 <<= 1;
                 for (int q = tid; q < np2; q += T) sband[q] = -1.0;
                 __syncthreads();
-                int at = 0;
-                for (int r = 0; r < world; r++) {
-                    const double *box = a.statbox_all + (size_t)r * boxlen;
-                    const int nb = (int)box[2 * ncol + cidx];
-                    for (int q = tid; q < nb; q += T) sband[at + q] = box[3 * (size_t)ncol + (size_t)cidx * BAND_CAP + q];
-                    at += nb;
+                if (world == 1) {
+                    for (int q = tid; q < nbv; q += T) sband[q] = st.band[(size_t)cidx * BAND_CAP + q];
+                } else {
+                    int at = 0;
+                    for (int r = 0; r < world; r++) {
+                        const double *box = a.statbox_all + (size_t)r * boxlen;
+                        const int nb0 = (int)box[2 * ncol + cidx];
+                        const int nb = nb0 < BAND_CAP ? nb0 : BAND_CAP;
+                        for (int q = tid; q < nb; q += T) sband[at + q] = box[3 * (size_t)ncol + (size_t)cidx * BAND_CAP + q];
+                        at += nb;
+                    }
                 }
                 __syncthreads();
                 for (int kk = 2; kk <= np2; kk <<= 1)               // bitonic sort, descending
@@ -867,6 +919,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
             if (!ok && tid == 0) a.fail[0] = 1;
         }
     }
+    if (world == 1) {                                            // band counters: ready for the next minibatch
+        __syncthreads();
+        for (int c = blockIdx.x * T + tid; c < ncol; c += nblk * T) st.band_n[c] = 0;
+    }
     __threadfence();
     grid.sync();
     const bool fb = *reinterpret_cast<volatile int *>(a.fail) != 0;
@@ -892,7 +948,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
     double prev_total = -1.0;
     XArgs x = a.x;
     for (int it = 0; it < a.max_iter; it++) {
-        stats_pass(sp, ssum, scnt, false);
+        stats_pass<1>(sp, ssum, scnt, false);
         __threadfence();
         grid.sync();
         for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
@@ -1000,7 +1056,7 @@ int grid_for(long long groups, int G) {
 
 // ============================================================================================ host side
 struct PlanMb {                          // one minibatch of the plan, resolved on the host
-    long long e0, e1, u0, u1, c0, c1, s0, s1;
+    long long e0, e1, u0, u1, sh0, sh1, lc0, lc1, ml0, ml1;
     int b0, b1;
 };
 
@@ -1008,8 +1064,9 @@ static inline PlanMb plan_mb(const sp_psgd_plan *pl, int m) {
     PlanMb q;
     q.e0 = pl->mb_eptr_host[m]; q.e1 = pl->mb_eptr_host[m + 1];
     q.u0 = pl->mb_uptr_host[m]; q.u1 = pl->mb_uptr_host[m + 1];
-    q.c0 = pl->mb_cptr_host[m]; q.c1 = pl->mb_cptr_host[m + 1];
-    q.s0 = pl->mb_sptr_host[m]; q.s1 = pl->mb_sptr_host[m + 1];
+    q.sh0 = pl->mb_shptr_host[m]; q.sh1 = pl->mb_shptr_host[m + 1];
+    q.lc0 = pl->mb_lcptr_host[m]; q.lc1 = pl->mb_lcptr_host[m + 1];
+    q.ml0 = pl->mb_mlptr_host[m]; q.ml1 = pl->mb_mlptr_host[m + 1];
     q.b0 = m * pl->batch_local;
     q.b1 = q.b0 + pl->batch_local < pl->n_local ? q.b0 + pl->batch_local : pl->n_local;
     return q;
@@ -1041,14 +1098,12 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
 
     ColsArgs ca;
     ca.k = cx->k; ca.d = cx->d_rows;
-    ca.e_pos = pl->e_pos + mb.e0; ca.e_x = pl->e_x + mb.e0;
-    ca.n_entries = mb.e1 - mb.e0;
-    ca.n_chunks = (int)(mb.c1 - mb.c0);
+    ca.e_pos = pl->e_pos; ca.e_x = pl->e_x;
     ca.u_feat = pl->u_feat; ca.u_ptr = pl->u_ptr;
-    ca.e_base = mb.e0; ca.u_base = mb.u0;
-    ca.chunk_u0 = pl->chunk_u0 + mb.c0;
-    ca.split_u = pl->split_u + mb.s0;
-    ca.n_split = (int)(mb.s1 - mb.s0);
+    ca.u_base = mb.u0;
+    ca.short_u = pl->short_u + mb.sh0; ca.n_short = (int)(mb.sh1 - mb.sh0);
+    ca.lc_u = pl->lc_u + mb.lc0; ca.lc_e0 = pl->lc_e0 + mb.lc0; ca.n_chunks = (int)(mb.lc1 - mb.lc0);
+    ca.ml_u = pl->ml_u + mb.ml0; ca.ml_c0 = pl->ml_c0 + mb.ml0; ca.n_multi = (int)(mb.ml1 - mb.ml0);
     ca.bufA = cx->bufA; ca.bufdL = cx->bufdL;
     ca.lams = cx->lams; ca.thr = cx->thr;
     ca.P = cx->P; ca.w = cx->w;
@@ -1063,20 +1118,26 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
         for (int r = 0; r <= cx->world; r++) ca.owner_start[r] = pl->mb_owner_start_host[(size_t)m * (cx->world + 1) + r];
         for (int r = 0; r < cx->world; r++) { ca.inbox_g[r] = cx->peer_inbox_g[r]; ca.inbox_w[r] = cx->peer_inbox_w[r]; }
     }
-    if (ca.n_chunks > 0) {
-        sp_prof_begin(SP_PROF_PSGD_STEP, st);
+    sp_prof_begin(SP_PROF_PSGD_STEP, st);
+    if (ca.n_chunks > 0) {                                   // long columns first: their tail (combine) overlaps nothing else
         const int cb = grid_for(ca.n_chunks, G);
-        if (sharded) psgd_cols_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<cb, PL_THREADS, 0, st>>>(ca);
-        else psgd_cols_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<cb, PL_THREADS, 0, st>>>(ca);
-        SP_LAUNCH_CHECK("psgd_cols_kernel");
-        if (ca.n_split > 0) {
-            const int sb = grid_for(ca.n_split, G);
-            if (sharded) psgd_split_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
-            else psgd_split_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
-            SP_LAUNCH_CHECK("psgd_split_kernel");
-        }
-        sp_prof_end(st);
+        if (sharded) psgd_cols_long_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<cb, PL_THREADS, 0, st>>>(ca);
+        else psgd_cols_long_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<cb, PL_THREADS, 0, st>>>(ca);
+        SP_LAUNCH_CHECK("psgd_cols_long_kernel");
     }
+    if (ca.n_multi > 0) {
+        if (sharded) psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<ca.n_multi, PL_THREADS, 0, st>>>(ca);
+        else psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<ca.n_multi, PL_THREADS, 0, st>>>(ca);
+        SP_LAUNCH_CHECK("psgd_cols_combine_kernel");
+    }
+    if (ca.n_short > 0) {
+        int sb = grid_for(ca.n_short, G);
+        if (sb > 148 * 12) sb = 148 * 12;
+        if (sharded) psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
+        else psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
+        SP_LAUNCH_CHECK("psgd_cols_short_kernel");
+    }
+    sp_prof_end(st);
     return SP_OK;
 }
 
@@ -1197,7 +1258,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
         sp_set_error("sp_psgd_plan_run: invalid argument");
         return SP_ERR_INVALID;
     }
-    if (pl->chunk != CH) { sp_set_error("sp_psgd_plan_run: plan built for chunk %d, library uses %d", pl->chunk, CH); return SP_ERR_INVALID; }
+    if (pl->chunk != CH || pl->short_max != SP_PSGD_SHORT) { sp_set_error("sp_psgd_plan_run: plan built for chunk %d / short %d, library uses %d / %d", pl->chunk, pl->short_max, CH, SP_PSGD_SHORT); return SP_ERR_INVALID; }
     if (cx->world > 1 && (!pl->csr_slot || !pl->own_q || !pl->own_src || !pl->mb_owner_start_host || !pl->mb_optr_host)) {
         sp_set_error("sp_psgd_plan_run: sharded run with a single-rank plan");
         return SP_ERR_INVALID;
@@ -1238,7 +1299,8 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
         }
 #define SP_MB(D, N, GG, KC) rc = launch_minibatch<D, N, GG, KC>(cx, ds, pl, y, idx_samples, mb, sa, st)
 #define SP_MB_K(D, N)                                                                      \
-        if (k <= 16) SP_MB(D, N, 16, 1);                                                   \
+        if (k <= 8) SP_MB(D, N, 8, 1);                                                     \
+        else if (k <= 16) SP_MB(D, N, 16, 1);                                              \
         else if (k <= 32) SP_MB(D, N, 32, 1);                                              \
         else if (k <= 64) SP_MB(D, N, 32, 2);                                              \
         else SP_MB(D, N, 32, 4)
@@ -1258,7 +1320,8 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             if (rc) return rc;
 #define SP_OW(N, GG, KC) rc = launch_owner<N, GG, KC>(cx, pl, m, sa, st)
 #define SP_OW_K(N)                                                                         \
-            if (k <= 16) SP_OW(N, 16, 1);                                                  \
+            if (k <= 8) SP_OW(N, 8, 1);                                                    \
+            else if (k <= 16) SP_OW(N, 16, 1);                                             \
             else if (k <= 32) SP_OW(N, 32, 1);                                             \
             else if (k <= 64) SP_OW(N, 32, 2);                                             \
             else SP_OW(N, 32, 4)
@@ -1293,18 +1356,25 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             if (sharded) { for (int r = 0; r < cx->world; r++) sg.statbox[r] = cx->peer_xwork[r] + (size_t)cx->rank * boxlen; }
             else sg.statbox[0] = cx->xwork;
             sg.err = cx->err;
-            const int tpr = k < PL_THREADS ? k : PL_THREADS, rpp = PL_THREADS / tpr;
+            const int tpr = (k & 1) ? k : k / 2, rpp = PL_THREADS / tpr;
             long long nblk = ((long long)cx->d_rows + rpp - 1) / rpp;
             if (nblk > STAT_PART_MAX) nblk = STAT_PART_MAX;
             if (nblk < 1) nblk = 1;
             sp_prof_begin(SP_PROF_PROX, st);
             psgd_stats_kernel<<<(int)nblk, PL_THREADS, 0, st>>>(sg);
             SP_LAUNCH_CHECK("psgd_stats_kernel");
-            if (sharded) { cx->seq += 1; rc = xbarrier(cx, 0, cx->seq, st); if (rc) { sp_prof_end(st); return rc; } }
+            if (sharded) {
+                psgd_stats_publish_kernel<<<(int)ncol, PL_THREADS, 0, st>>>(sg, (int)nblk);
+                SP_LAUNCH_CHECK("psgd_stats_publish_kernel");
+                cx->seq += 1;
+                rc = xbarrier(cx, 0, cx->seq, st);
+                if (rc) { sp_prof_end(st); return rc; }
+            }
             SolveArgs so;
             so.st = sg;
             so.Cn = cx->C; so.thr = cx->thr; so.tau = cx->work + L.tau; so.colres = cx->work + L.colres;
             so.fail = reinterpret_cast<int *>(cx->work + L.ints) + ((ncol + 8) & ~1) ;
+            so.npart = (int)nblk;
             so.statbox_all = cx->xwork;
             const size_t xoff = (size_t)cx->world * boxlen;
             for (int r = 0; r < SP_MAX_RANKS; r++) so.xbuf[r] = nullptr;

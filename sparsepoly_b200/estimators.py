@@ -368,10 +368,11 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         return converged, it
 
     # ---------------------------------------------------------------- psgd
-    def _fit_psgd(self, X, y, rng, dev):
-        """sparse_factorization_machines.py:94-173.  l1 / squaredl12 run the planned path (psgd_plan.cu: gather
-        passes over a batch-CSC plan, touched rows only, sharded over peer memory); l21 / squaredl21 the
-        dense-gradient path (psgd.cu)."""
+    def _psgd_setup(self, X, y, rng, dev):
+        """Move everything to the device and return (epoch, sync, close): epoch() runs one psgd.psgd_epoch
+        (sparse_factorization_machines.py:123-150) and returns the epoch's mean loss (None with
+        read_back=False).  l1 / squaredl12 run the planned path (psgd_plan.cu: gather passes over a batch-CSC
+        plan, touched rows only, sharded over peer memory); l21 / squaredl21 the dense-gradient path (psgd.cu)."""
         n, d = X.shape
         k = self.n_components
         group = _process_group()
@@ -390,9 +391,9 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
             sizes = global_sum([float(n), float(n) ** 2], group)
             if abs(sizes[1] * world - sizes[0] ** 2) > 0.5:
                 raise ValueError("sharded psgd needs the same number of samples on every rank")
-        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev,
-                           hot_features=self.regularizer not in solvers.PLANNED_REGS)
-        self._h2d_bytes = ds.h2d_bytes
+        planned = self.regularizer in solvers.PLANNED_REGS
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned, pin=planned)
+        self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         n_glob, nnz_glob = (global_sum([n, ds.nnz], group) if group is not None else (n, ds.nnz))
         if self.batch_size == "auto":
             batch_size = int(n_glob * d / nnz_glob)                          # :101-102
@@ -408,63 +409,78 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         w = torch.from_numpy(np.ascontiguousarray(self.w_)).to(dev)
         lams = torch.from_numpy(np.ascontiguousarray(self.lams_, dtype=np.float64)).to(dev)
         loss_dev = torch.zeros(1, dtype=_f64, device=dev)
-        planned = self.regularizer in solvers.PLANNED_REGS
+        st = {"model_current": True}
         if planned:
             from .psgd_plan import PsgdContext, PsgdPlan
             b_loc = max(1, batch_size // world)
-            plan = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
-            ctx = PsgdContext(plan, P.shape[0], k, self.degree, self.regularizer, self.loss, self.fit_linear, lams,
-                              group=group, inbox_cap=(min(plan.d_rows, b_loc * int(ds.max_row_nnz())) if self.shuffle else None))
+            st["plan"] = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
+            ctx = PsgdContext(st["plan"], P.shape[0], k, self.degree, self.regularizer, self.loss, self.fit_linear, lams,
+                              group=group,
+                              inbox_cap=(min(st["plan"].d_rows, b_loc * int(ds.max_row_nnz())) if self.shuffle else None))
             ctx.load_model(P, w)
             solvers.psgd_planned_begin(ctx)
-            self._psgd_stats = {"plan_bytes": plan.nbytes(), "minibatches": plan.n_minibatches,
-                                "columns_per_minibatch": plan.n_cols / max(plan.n_minibatches, 1)}
-            state = {"model_current": True}
+            self._psgd_stats = {"plan_bytes": st["plan"].nbytes(), "minibatches": st["plan"].n_minibatches,
+                                "columns_per_minibatch": st["plan"].n_cols / max(st["plan"].n_minibatches, 1),
+                                "batch_size": batch_size, "batch_local": b_loc, "world": world}
         else:
             grad_P = torch.zeros_like(P)
             grad_w = torch.zeros(d, dtype=_f64, device=dev)
             work = solvers.prox_work(d, k, dev)
+            self._psgd_stats = {"batch_size": batch_size, "world": world}
 
         def sync():
-            if planned and not state["model_current"]:
-                solvers.psgd_planned_end(ctx, 0, None, True)
-                state["model_current"] = True
             if planned:
+                if not st["model_current"]:
+                    solvers.psgd_planned_end(ctx, 0, None, True)
+                    st["model_current"] = True
                 ctx.store_model(P, w)
             for o in range(P.shape[0]):
                 self.P_[o] = solvers.transpose(P[o]).cpu().numpy()
             self.w_[...] = w.cpu().numpy()
 
+        def epoch(read_back=True):
+            if self.shuffle:
+                rng.shuffle(indices_samples)
+                idx_dev.copy_(torch.from_numpy(indices_samples))
+                if planned:
+                    st["plan"] = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
+                    ctx.rebind(st["plan"])
+            loss_dev.zero_()
+            if planned:
+                self.it_ = solvers.psgd_planned_run(ctx, ds, st["plan"], y_dev, idx_dev, self.alpha, self.beta, self.gamma,
+                                                    self.eta0, learning_rate, self.power_t, self.it_)
+                # the lazy scales only grow: fold them back into the storage long before they overflow
+                big = not (1e-100 < ctx.struct.C < 1e100 and 1e-100 < ctx.struct.Cw < 1e100)
+                solvers.psgd_planned_end(ctx, n, loss_dev, big)
+                st["model_current"] = big
+            else:
+                self.it_ = solvers.psgd_epoch(ds, y_dev, P, w, lams, self.degree, self.alpha, self.beta,
+                                              self.gamma, self.regularizer, self.loss, grad_P, grad_w,
+                                              idx_dev, self.fit_linear, self.eta0, learning_rate,
+                                              self.power_t, batch_size, self.it_, loss_dev, work, group)
+            if not read_back:
+                return None
+            sum_loss = loss_dev.item()
+            if planned:
+                ctx.check_peers()
+            if group is not None:
+                sum_loss = global_sum([sum_loss], group)[0]
+            return sum_loss / n_glob
+
+        def close():
+            if planned:
+                ctx.close()
+
+        return epoch, sync, close
+
+    def _fit_psgd(self, X, y, rng, dev):
+        """sparse_factorization_machines.py:94-173 (epoch loop, plateau stopping rule :157-170)."""
+        epoch_fn, sync, close = self._psgd_setup(X, y, rng, dev)
         converged, epoch = False, 0
         no_improvement_count, best_loss = 0, np.inf
         try:
             for epoch in range(self.max_iter):
-                if self.shuffle:
-                    rng.shuffle(indices_samples)
-                    idx_dev.copy_(torch.from_numpy(indices_samples))
-                    if planned:
-                        plan = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
-                        ctx.rebind(plan)
-                loss_dev.zero_()
-                if planned:
-                    self.it_ = solvers.psgd_planned_run(ctx, ds, plan, y_dev, idx_dev, self.alpha, self.beta, self.gamma,
-                                                        self.eta0, learning_rate, self.power_t, self.it_)
-                    state["model_current"] = False
-                    # the lazy scales only grow: fold them back into the storage long before they overflow
-                    big = not (1e-100 < ctx.struct.C < 1e100 and 1e-100 < ctx.struct.Cw < 1e100)
-                    solvers.psgd_planned_end(ctx, n, loss_dev, big)
-                    state["model_current"] = big
-                else:
-                    self.it_ = solvers.psgd_epoch(ds, y_dev, P, w, lams, self.degree, self.alpha, self.beta,
-                                                  self.gamma, self.regularizer, self.loss, grad_P, grad_w,
-                                                  idx_dev, self.fit_linear, self.eta0, learning_rate,
-                                                  self.power_t, batch_size, self.it_, loss_dev, work, group)
-                sum_loss = loss_dev.item()
-                if planned:
-                    ctx.check_peers()
-                if group is not None:
-                    sum_loss = global_sum([sum_loss], group)[0]
-                sum_loss /= n_glob
+                sum_loss = epoch_fn()
                 if (self.callback is not None) and epoch % self.n_calls == 0:
                     sync()
                     if self.callback(self) is not None:
@@ -484,8 +500,7 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                     break
             sync()
         finally:
-            if planned:
-                ctx.close()
+            close()
         return converged, epoch
 
     # ---------------------------------------------------------------- public

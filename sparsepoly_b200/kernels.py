@@ -31,13 +31,20 @@ def all_subsets_kernel(X, P):
     return _gram(X, P, -1)
 
 
+def homogeneous_kernel(X, P, degree=2):
+    """K_P(x, p) = <x, p> ^ degree  (kernels.py:50-68): the degree-1 ANOVA kernel is the inner product."""
+    return _gram(X, P, 1) ** degree
+
+
 def poly_predict(X, P, lams, kernel, degree=2):
-    """np.dot(K, lams)  (kernels.py:140-153); kernel in {'anova', 'all-subsets'}."""
+    """np.dot(K, lams)  (kernels.py:140-153); kernel in {'anova', 'poly', 'all-subsets'}."""
     if kernel == "anova":
         K = anova_kernel(X, P, degree)
+    elif kernel == "poly":
+        K = homogeneous_kernel(X, P, degree)
     elif kernel == "all-subsets":
         K = all_subsets_kernel(X, P)
     else:
         raise ValueError(("Unsuppported kernel: {}. Use one of "
-                          "{{'anova'|'all-subsets'}}").format(kernel))
+                          "{{'anova'|'poly'|'all-subsets'}}").format(kernel))
     return np.dot(K, lams)

@@ -23,6 +23,7 @@ import torch
 from . import _lib
 
 CHUNK = 64            # SP_PSGD_CHUNK
+SHORT = 8             # SP_PSGD_SHORT
 MAX_RANKS = 8         # SP_MAX_RANKS
 CHANNELS = 2          # SP_PSGD_CHANNELS
 _GROUP_ENTRIES = 48_000_000     # nonzeros sorted at a time while building (bounds the temporaries)
@@ -82,8 +83,8 @@ class PsgdPlan:
         self.e_pos = torch.empty(E, dtype=torch.int32, device=dev)
         self.e_x = torch.empty(E, dtype=torch.float64, device=dev)
         self.csr_slot = torch.zeros(nnz_total, dtype=torch.int32, device=dev) if G > 1 else None
-        u_feat, u_ptr, chunk_u0, split_u = [], [], [], []
-        mb_ucnt, mb_ccnt, mb_scnt, owner_cnt = [], [], [], []
+        u_feat, u_ptr, short_u, lc_u, lc_e0, ml_u, ml_c0 = [], [], [], [], [], [], []
+        mb_ucnt, mb_shcnt, mb_lccnt, mb_mlcnt, owner_cnt = [], [], [], [], []
         u_off = 0
         m0 = 0
         while m0 < M:
@@ -95,7 +96,8 @@ class PsgdPlan:
             tot = e1 - e0
             Mg = m1 - m0
             if tot == 0:
-                mb_ucnt.append(np.zeros(Mg, np.int64)); mb_ccnt.append(np.zeros(Mg, np.int64)); mb_scnt.append(np.zeros(Mg, np.int64))
+                for lst in (mb_ucnt, mb_shcnt, mb_lccnt, mb_mlcnt):
+                    lst.append(np.zeros(Mg, np.int64))
                 owner_cnt.append(np.zeros((Mg, G), np.int64))
                 m0 = m1
                 continue
@@ -115,9 +117,7 @@ class PsgdPlan:
             key, order = torch.sort(key, stable=True)                           # samples stay ascending inside a column
             newcol = torch.ones(tot, dtype=torch.bool, device=dev)
             newcol[1:] = key[1:] != key[:-1]
-            lp = lpos[order]
-            self.e_pos[e0:e1] = torch.where(newcol, lp | torch.tensor(-2 ** 31, dtype=torch.int32, device=dev), lp)
-            del lp
+            self.e_pos[e0:e1] = lpos[order]
             self.e_x[e0:e1] = data[src[order]]
             del lpos
             ucol = torch.cumsum(newcol.to(i64), 0) - 1                          # group-relative column of every entry
@@ -142,39 +142,52 @@ class PsgdPlan:
                 del mb_sorted
                 owner_cnt.append(torch.bincount(umb * G + uowner, minlength=Mg * G).reshape(Mg, G).cpu().numpy())
             del src, order, key
-            # chunks
-            nch = (ecnt + CHUNK - 1) // CHUNK
-            mb_ccnt.append(nch.cpu().numpy())
-            ntc = int(nch.sum())
-            cptr_rel = torch.zeros(Mg + 1, dtype=i64, device=dev)
-            cptr_rel[1:] = torch.cumsum(nch, 0)
-            cmb = torch.repeat_interleave(torch.arange(Mg, dtype=i64, device=dev), nch, output_size=ntc)
-            c_in = torch.arange(ntc, dtype=i64, device=dev) - cptr_rel[cmb]
-            chunk_u0.append((ucol[eptr_rel[cmb] + c_in * CHUNK] + u_off).to(torch.int32))
-            del ucol
-            # columns spanning more than one chunk
+            # columns by length: short ones are summed by one group of lanes, longer ones are cut into chunks
             uend = torch.empty(nU, dtype=i64, device=dev)
             uend[:-1] = ustart[1:]
             uend[-1] = tot
-            s_rel = ustart - eptr_rel[umb]
-            e_rel = uend - eptr_rel[umb]
-            split = (s_rel // CHUNK) != ((e_rel - 1) // CHUNK)
-            sp_idx = torch.nonzero(split).squeeze(1)
-            split_u.append((sp_idx + u_off).to(torch.int32))
-            mb_scnt.append(torch.bincount(umb[sp_idx], minlength=Mg).cpu().numpy())
+            ulen = uend - ustart
+            is_short = ulen <= SHORT
+            sh_idx = torch.nonzero(is_short).squeeze(1)
+            short_u.append((sh_idx + u_off).to(torch.int32))
+            mb_shcnt.append(torch.bincount(umb[sh_idx], minlength=Mg).cpu().numpy())
+            lg_idx = torch.nonzero(~is_short).squeeze(1)
+            npieces = (ulen[lg_idx] + CHUNK - 1) // CHUNK
+            ntc = int(npieces.sum()) if lg_idx.numel() else 0
+            first_chunk = torch.cumsum(npieces, 0) - npieces                      # group-relative index of a column's first chunk
+            lcnt = torch.zeros(Mg, dtype=i64, device=dev)
+            lcnt.index_add_(0, umb[lg_idx], npieces)
+            lcptr_rel = torch.zeros(Mg + 1, dtype=i64, device=dev)
+            lcptr_rel[1:] = torch.cumsum(lcnt, 0)
+            mb_lccnt.append(lcnt.cpu().numpy())
+            if ntc:
+                col_of_chunk = torch.repeat_interleave(torch.arange(lg_idx.numel(), dtype=i64, device=dev), npieces, output_size=ntc)
+                piece = torch.arange(ntc, dtype=i64, device=dev) - first_chunk[col_of_chunk]
+                lc_u.append((lg_idx[col_of_chunk] + u_off).to(torch.int32))
+                lc_e0.append(ustart[lg_idx[col_of_chunk]] + piece * CHUNK + e0)
+            multi = npieces > 1
+            ml_idx = lg_idx[multi]
+            ml_u.append((ml_idx + u_off).to(torch.int32))
+            ml_c0.append((first_chunk[multi] - lcptr_rel[umb[ml_idx]]).to(torch.int32))   # relative to the minibatch's chunks
+            mb_mlcnt.append(torch.bincount(umb[ml_idx], minlength=Mg).cpu().numpy())
+            del ucol
             u_off += nU
             m0 = m1
         cat = lambda xs, dt: (torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev))   # noqa: E731
         self.u_feat = cat(u_feat, torch.int32)
         self.u_ptr = torch.cat([cat(u_ptr, i64), torch.tensor([E], dtype=i64, device=dev)])
-        self.chunk_u0 = cat(chunk_u0, torch.int32)
-        self.split_u = cat(split_u, torch.int32)
+        self.short_u = cat(short_u, torch.int32)
+        self.lc_u = cat(lc_u, torch.int32)
+        self.lc_e0 = cat(lc_e0, i64)
+        self.ml_u = cat(ml_u, torch.int32)
+        self.ml_c0 = cat(ml_c0, torch.int32)
         acc = lambda parts: np.concatenate([[0], np.cumsum(np.concatenate(parts) if parts else np.zeros(0, np.int64))]).astype(np.int64)  # noqa: E731
         self.mb_eptr = mb_eptr
         self.mb_uptr = acc(mb_ucnt)
-        self.mb_cptr = acc(mb_ccnt)
-        self.mb_sptr = acc(mb_scnt)
-        self.max_chunks = int(np.max(np.diff(self.mb_cptr))) if M else 0
+        self.mb_shptr = acc(mb_shcnt)
+        self.mb_lcptr = acc(mb_lccnt)
+        self.mb_mlptr = acc(mb_mlcnt)
+        self.max_chunks = int(np.max(np.diff(self.mb_lcptr))) if M else 0
         self.max_cols = int(np.max(np.diff(self.mb_uptr))) if M else 0
         self.n_entries = E
         self.n_cols = int(self.mb_uptr[-1])
@@ -256,13 +269,15 @@ class PsgdPlan:
 
     def _fill_struct(self):
         s = _lib.SpPsgdPlan()
-        s.n_minibatches, s.batch_local, s.n_local, s.chunk = self.n_minibatches, self.batch_local, self.n_local, CHUNK
+        s.n_minibatches, s.batch_local, s.n_local = self.n_minibatches, self.batch_local, self.n_local
+        s.chunk, s.short_max = CHUNK, SHORT
         hp = lambda a: a.ctypes.data                         # noqa: E731  (host arrays are kept alive by self)
         s.mb_eptr_host, s.mb_uptr_host = hp(self.mb_eptr), hp(self.mb_uptr)
-        s.mb_cptr_host, s.mb_sptr_host = hp(self.mb_cptr), hp(self.mb_sptr)
+        s.mb_shptr_host, s.mb_lcptr_host, s.mb_mlptr_host = hp(self.mb_shptr), hp(self.mb_lcptr), hp(self.mb_mlptr)
         s.e_pos, s.e_x = self.e_pos.data_ptr(), self.e_x.data_ptr()
         s.u_feat, s.u_ptr = self.u_feat.data_ptr(), self.u_ptr.data_ptr()
-        s.chunk_u0, s.split_u = self.chunk_u0.data_ptr(), self.split_u.data_ptr()
+        s.short_u, s.lc_u, s.lc_e0 = self.short_u.data_ptr(), self.lc_u.data_ptr(), self.lc_e0.data_ptr()
+        s.ml_u, s.ml_c0 = self.ml_u.data_ptr(), self.ml_c0.data_ptr()
         s.max_chunks, s.max_cols = self.max_chunks, self.max_cols
         if self.world > 1:
             s.csr_slot = self.csr_slot.data_ptr()
@@ -275,8 +290,8 @@ class PsgdPlan:
         return C.byref(self.struct)
 
     def nbytes(self):
-        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.chunk_u0, self.split_u, self.csr_slot, self.own_q,
-              self.own_src]
+        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.short_u, self.lc_u, self.lc_e0, self.ml_u, self.ml_c0,
+              self.csr_slot, self.own_q, self.own_src]
         return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
 
@@ -318,8 +333,8 @@ class PsgdContext:
         self.bufA = torch.empty(max(plan.batch_local * ar * k, 1), dtype=f64, device=dev)
         self.bufdL = torch.empty(max(plan.batch_local, 1), dtype=f64, device=dev)
         self.sample_loss = torch.zeros(max(plan.n_local, 1), dtype=f64, device=dev)
-        self.part_g = torch.empty(max(plan.max_chunks * 2 * ncolk, 1), dtype=f64, device=dev)
-        self.part_w = torch.empty(max(plan.max_chunks * 2, 1), dtype=f64, device=dev)
+        self.part_g = torch.empty(max(plan.max_chunks * ncolk, 1), dtype=f64, device=dev)
+        self.part_w = torch.empty(max(plan.max_chunks, 1), dtype=f64, device=dev)
         self.work = torch.zeros(int(L.sp_psgd_plan_work_doubles(self.n_orders, self.k)), dtype=f64, device=dev)
         xw = int(L.sp_psgd_plan_xwork_doubles(self.n_orders, self.k, self.world))
         s = _lib.SpPsgdCtx()
@@ -428,8 +443,8 @@ class PsgdContext:
             dev, f64 = plan.device, torch.float64
             ncolk = self.n_orders * self.k
             if plan.max_chunks > self.plan_dims[0]:
-                self.part_g = torch.empty(max(plan.max_chunks * 2 * ncolk, 1), dtype=f64, device=dev)
-                self.part_w = torch.empty(max(plan.max_chunks * 2, 1), dtype=f64, device=dev)
+                self.part_g = torch.empty(max(plan.max_chunks * ncolk, 1), dtype=f64, device=dev)
+                self.part_w = torch.empty(max(plan.max_chunks, 1), dtype=f64, device=dev)
                 self.struct.part_g, self.struct.part_w = self.part_g.data_ptr(), self.part_w.data_ptr()
             if self.world > 1 and plan.max_cols > self.plan_dims[1]:
                 self.stage = torch.empty(max(plan.max_cols * ncolk, 1), dtype=f64, device=dev)

@@ -56,3 +56,26 @@ def targets_from_scores(scores, seed, classification, noise=0.1):
     if classification:
         return np.where(y > np.median(y), 1.0, -1.0)
     return y
+
+
+def planted_fm_targets(X, model_seed, noise_seed, k_true=4, positive_frac=0.25, classification=True):
+    """Targets of a planted sparse degree-2 FM: linear + pairwise signal confined to a random
+    10 % of the features, plus noise; classification thresholds at the (1 - positive_frac) quantile.  Host
+    side only (scipy), so that both bench arms see the same data."""
+    n, d = X.shape
+    rng = np.random.RandomState(model_seed)
+    active = rng.choice(d, size=max(2, d // 10), replace=False)
+    Pt = np.zeros((d, k_true))
+    Pt[active] = 0.3 * rng.randn(active.size, k_true)
+    wt = np.zeros(d)
+    wt[active] = 0.3 * rng.randn(active.size)
+    X2 = X.copy()
+    X2.data = X2.data ** 2
+    XP = X @ Pt
+    s = X @ wt + 0.5 * (XP ** 2 - X2 @ (Pt ** 2)).sum(1)
+    s = np.asarray(s).ravel()
+    nrng = np.random.RandomState(noise_seed)
+    s = s + 0.1 * np.std(s) * nrng.randn(n)
+    if classification:
+        return np.where(s > np.quantile(s, 1.0 - positive_frac), 1.0, -1.0)
+    return s / np.std(s)

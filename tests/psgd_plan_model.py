@@ -6,6 +6,7 @@ just the other rank's arrays."""
 import numpy as np
 
 CH = 64
+SH = 8
 
 
 def st_true(r, T, invC):
@@ -77,7 +78,8 @@ class RankState:
         self.plan = plan
         self.e_pos, self.e_x = t(plan.e_pos), t(plan.e_x)
         self.u_feat, self.u_ptr = t(plan.u_feat), t(plan.u_ptr)
-        self.chunk_u0, self.split_u = t(plan.chunk_u0), t(plan.split_u)
+        self.short_u, self.lc_u, self.lc_e0 = t(plan.short_u), t(plan.lc_u), t(plan.lc_e0)
+        self.ml_u, self.ml_c0 = t(plan.ml_u), t(plan.ml_c0)
         self.csr_slot = t(plan.csr_slot)
         self.own_q, self.own_src = t(plan.own_q), t(plan.own_src)
         self.indptr, self.indices, self.data = (np.asarray(a) for a in csr)
@@ -120,7 +122,6 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                 pl = R.plan
                 e0, e1 = pl.mb_eptr[m], pl.mb_eptr[m + 1]
                 u0, u1 = pl.mb_uptr[m], pl.mb_uptr[m + 1]
-                c0 = pl.mb_cptr[m]
                 b0, b1 = m * bL, min((m + 1) * bL, pl.n_local)
                 # ---- pull (sharded) / direct reads: true rows of the minibatch's columns
                 feats = R.u_feat[u0:u1]
@@ -154,10 +155,7 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                     bufA[b - b0] = A
                     bufdL[b - b0] = dloss(loss, ypred, R.y[i])
                     R.sloss[b] = lossv(loss, ypred, R.y[i])
-                # ---- cols pass, chunk by chunk exactly like psgd_cols_kernel
-                nE = e1 - e0
-                nch = (nE + CH - 1) // CH
-                assert nch == pl.mb_cptr[m + 1] - c0
+                # ---- column pass exactly like psgd_cols_{short,long,combine}_kernel
                 part = {}
                 done = {}                                   # column -> (g [o,k], gw)
 
@@ -171,46 +169,54 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                         g[o] = (bufdL[pos] * lams) * dprev
                     return g, bufdL[pos] * x
 
-                for c in range(nch):
-                    ce0, ce1 = c * CH, min((c + 1) * CH, nE)
-                    ends_here = ce1 == nE or R.e_pos[e0 + ce1] < 0
-                    ucur = int(R.chunk_u0[c0 + c]) - 1
-                    have, first = False, True
-                    for e in range(ce0, ce1):
-                        ep = int(R.e_pos[e0 + e])
-                        nf = ep < 0 or e == ce0
-                        if nf:
-                            if have:
-                                (done if started else part)[(cur_u, ) if started else (c, 0 if first_col else 1)] = (g, gw)
-                            first_col = not have
-                            have = True
-                            ucur += 1
-                            cur_u = ucur
-                            started = ep < 0
-                            pold = stage[cur_u - u0]
-                            g, gw = np.zeros((n_orders, k)), 0.0
-                            assert R.u_ptr[cur_u] <= e0 + e < R.u_ptr[cur_u + 1]
-                        tg, tw = term(ep & 0x7fffffff, R.e_x[e0 + e], pold)
+                def sum_entries(ea, eb, pold):
+                    g, gw = np.zeros((n_orders, k)), 0.0
+                    for e in range(ea, eb):
+                        tg, tw = term(int(R.e_pos[e]), R.e_x[e], pold)
                         g = g + tg
                         gw = gw + tw
-                    if have:
-                        complete = started and ends_here
-                        (done if complete else part)[(cur_u, ) if complete else (c, 0 if first_col else 1)] = (g, gw)
-                # ---- split columns
-                s0, s1 = pl.mb_sptr[m], pl.mb_sptr[m + 1]
-                for u in R.split_u[s0:s1]:
-                    s_rel, e_rel = R.u_ptr[u] - e0, R.u_ptr[u + 1] - e0
-                    cc0, cc1 = s_rel // CH, (e_rel - 1) // CH
-                    assert cc1 > cc0
-                    g, gw = np.zeros((n_orders, k)), 0.0
-                    for c in range(cc0, cc1 + 1):
-                        slot = 1 if (c == cc0 and s_rel > cc0 * CH) else 0
-                        pg, pw = part.pop((c, slot))
+                    return g, gw
+
+                seen = np.zeros(u1 - u0, dtype=int)
+                for u in R.short_u[pl.mb_shptr[m]:pl.mb_shptr[m + 1]]:
+                    ea, eb = R.u_ptr[u], R.u_ptr[u + 1]
+                    assert 1 <= eb - ea <= SH and e0 <= ea and eb <= e1
+                    done[(int(u), )] = sum_entries(ea, eb, stage[u - u0])
+                    seen[u - u0] += 1
+                lc0, lc1 = pl.mb_lcptr[m], pl.mb_lcptr[m + 1]
+                for c in range(lc0, lc1):
+                    u, ce0 = int(R.lc_u[c]), int(R.lc_e0[c])
+                    cend = R.u_ptr[u + 1]
+                    assert cend - R.u_ptr[u] > SH and R.u_ptr[u] <= ce0 < cend and (ce0 - R.u_ptr[u]) % CH == 0
+                    ce1 = min(ce0 + CH, cend)
+                    res = sum_entries(ce0, ce1, stage[u - u0])
+                    if cend - R.u_ptr[u] <= CH:
+                        done[(u, )] = res
+                        seen[u - u0] += 1
+                    else:
+                        part[c - lc0] = res
+                for q in range(pl.mb_mlptr[m], pl.mb_mlptr[m + 1]):
+                    u, c0 = int(R.ml_u[q]), int(R.ml_c0[q])
+                    npc = -(-(R.u_ptr[u + 1] - R.u_ptr[u]) // CH)
+                    assert npc > 1
+                    GPB = 8                                  # groups of a block add strided pieces, then in group order
+                    gs = []
+                    for wg in range(min(GPB, npc)):
+                        g, gw = np.zeros((n_orders, k)), 0.0
+                        for pc in range(wg, npc, GPB):
+                            assert R.lc_u[lc0 + c0 + pc] == u
+                            pg, pw = part.pop(c0 + pc)
+                            g = g + pg
+                            gw = gw + pw
+                        gs.append((g, gw))
+                    g, gw = gs[0]
+                    for pg, pw in gs[1:]:
                         g = g + pg
                         gw = gw + pw
-                    done[(int(u), )] = (g, gw)
+                    done[(u, )] = (g, gw)
+                    seen[u - u0] += 1
                 assert not part, "a partial sum was never consumed"
-                assert len(done) == u1 - u0, "every column finished exactly once"
+                assert np.all(seen == 1), "every column finished exactly once"
                 # ---- apply (single rank) or push to the owners' inboxes
                 if G == 1:
                     for (u, ), (g, gw) in done.items():

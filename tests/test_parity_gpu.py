@@ -589,7 +589,7 @@ def _sharded_worker(rank, world, port, out_dir, n_dev):
     sys.path.insert(0, root)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank % n_dev)                     # one GPU: both ranks share it (time-sliced); else one each
+    torch.cuda.set_device(rank % n_dev)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sparsepoly_b200 as S
     from sparsepoly_b200 import distributed, synth
@@ -621,7 +621,7 @@ _SHARDED_CASES = [
 
 
 def test_sharded_psgd_two_ranks_matches_oracle(tmp_path):
-    """Two ranks (one process each; on a single-GPU box both share cuda:0, on a multi-GPU box one GPU each), samples
+    """Two ranks (one process and one GPU each), samples
     sharded, P sharded by rows in peer memory: pull / push / owner / statistics exchange of psgd_plan.cu against the
     oracle on the interleaved data set (reference optimizer/psgd.py:150-198), 1e-9; batch prediction sharded too."""
     import torch
@@ -630,6 +630,10 @@ def test_sharded_psgd_two_ranks_matches_oracle(tmp_path):
     from sparsepoly_b200 import synth
     from sparsepoly_b200.distributed import interleave_shards
     world = 2
+    if torch.cuda.device_count() < world:
+        # kernels of different ranks wait on one another through peer-memory flags; on ONE device nothing
+        # guarantees they are co-scheduled (B200_PROFILING.md: Xid 109).  profiles/r02_* hold the 2-GPU logs.
+        pytest.skip("needs one GPU per rank")
     port = 33500 + (os.getpid() % 2000)
     mp.spawn(_sharded_worker, args=(world, port, str(tmp_path), torch.cuda.device_count()), nprocs=world, join=True)
     z = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]

@@ -9,7 +9,7 @@ import torch
 from psgd_plan_model import RankState, run_model
 from sparsepoly_b200 import synth
 from sparsepoly_b200.distributed import interleave_shards
-from sparsepoly_b200.psgd_plan import CHUNK, PsgdPlan
+from sparsepoly_b200.psgd_plan import CHUNK, SHORT, PsgdPlan
 
 
 def _csr_t(X):
@@ -51,21 +51,24 @@ def test_plan_layout_matches_brute_force(b_loc, group_entries):
         u0, u1 = plan.mb_uptr[m], plan.mb_uptr[m + 1]
         got_feat = np.repeat(u_feat[u0:u1], np.diff(u_ptr[u0:u1 + 1]))
         assert np.array_equal(got_feat, [t[0] for t in want])
-        assert np.array_equal(e_pos[e0:e1] & 0x7fffffff, [t[1] for t in want])
+        assert np.array_equal(e_pos[e0:e1], [t[1] for t in want])
         assert np.array_equal(e_x[e0:e1], [t[2] for t in want])
-        starts = np.zeros(e1 - e0, bool)
-        starts[u_ptr[u0:u1] - e0] = True
-        assert np.array_equal(e_pos[e0:e1] < 0, starts)
-        nch = -(-(e1 - e0) // CHUNK)
-        assert plan.mb_cptr[m + 1] - plan.mb_cptr[m] == nch
-        cu0 = plan.chunk_u0.numpy()[plan.mb_cptr[m]:plan.mb_cptr[m + 1]]
-        for c in range(nch):
-            e = e0 + c * CHUNK
-            assert u_ptr[cu0[c]] <= e < u_ptr[cu0[c] + 1]
-        split = plan.split_u.numpy()[plan.mb_sptr[m]:plan.mb_sptr[m + 1]]
-        want_split = [u for u in range(u0, u1) if (u_ptr[u] - e0) // CHUNK != (u_ptr[u + 1] - 1 - e0) // CHUNK]
-        assert np.array_equal(split, want_split)
-    assert plan.max_chunks == np.max(np.diff(plan.mb_cptr)) and plan.max_cols == np.max(np.diff(plan.mb_uptr))
+        lens = np.diff(u_ptr[u0:u1 + 1])
+        short = plan.short_u.numpy()[plan.mb_shptr[m]:plan.mb_shptr[m + 1]]
+        assert np.array_equal(short, u0 + np.nonzero(lens <= SHORT)[0])
+        lc_u = plan.lc_u.numpy()[plan.mb_lcptr[m]:plan.mb_lcptr[m + 1]]
+        lc_e0 = plan.lc_e0.numpy()[plan.mb_lcptr[m]:plan.mb_lcptr[m + 1]]
+        want_u, want_e = [], []
+        for u in u0 + np.nonzero(lens > SHORT)[0]:
+            for e in range(u_ptr[u], u_ptr[u + 1], CHUNK):
+                want_u.append(u); want_e.append(e)
+        assert np.array_equal(lc_u, want_u) and np.array_equal(lc_e0, want_e)
+        ml_u = plan.ml_u.numpy()[plan.mb_mlptr[m]:plan.mb_mlptr[m + 1]]
+        ml_c0 = plan.ml_c0.numpy()[plan.mb_mlptr[m]:plan.mb_mlptr[m + 1]]
+        assert np.array_equal(ml_u, u0 + np.nonzero(lens > CHUNK)[0])
+        for u, c0 in zip(ml_u, ml_c0):
+            assert lc_u[c0] == u and lc_e0[c0] == u_ptr[u] and (c0 == 0 or lc_u[c0 - 1] != u)
+    assert plan.max_chunks == np.max(np.diff(plan.mb_lcptr)) and plan.max_cols == np.max(np.diff(plan.mb_uptr))
 
 
 def _oracle_fit(X, y, kw, epochs):
