@@ -247,6 +247,7 @@ typedef struct sp_psgd_plan {
     int32_t chunk, short_max;      /* must equal SP_PSGD_CHUNK / SP_PSGD_SHORT */
     const int64_t *mb_eptr_host;   /* [M+1] first nonzero of every minibatch */
     const int64_t *mb_uptr_host;   /* [M+1] first column (distinct feature) of every minibatch */
+    const int64_t *mb_sgptr_host;  /* [M+1] first entry of sg_* */
     const int64_t *mb_shptr_host;  /* [M+1] first entry of short_u */
     const int64_t *mb_lcptr_host;  /* [M+1] first entry of lc_u / lc_e0 */
     const int64_t *mb_mlptr_host;  /* [M+1] first entry of ml_u / ml_c0 */
@@ -254,7 +255,9 @@ typedef struct sp_psgd_plan {
     const double *e_x;             /* [E] value */
     const int32_t *u_feat;         /* [U] feature id of every column */
     const int64_t *u_ptr;          /* [U+1] first nonzero of every column */
-    const int32_t *short_u;        /* [Ns] columns of <= short_max nonzeros */
+    const int32_t *sg_u, *sg_feat, *sg_pos; /* [N1] columns of ONE nonzero: column, feature, position of the sample ... */
+    const double *sg_x;            /* [N1] ... and value */
+    const int32_t *short_u;        /* [Ns] columns of 2..short_max nonzeros */
     const int32_t *lc_u;           /* [Nc] chunks of the longer columns: column ... */
     const int64_t *lc_e0;          /* [Nc] ... and first nonzero; a chunk ends after `chunk` nonzeros or with its column */
     const int32_t *ml_u;           /* [Nm] columns of more than one chunk ... */

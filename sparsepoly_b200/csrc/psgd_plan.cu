@@ -93,7 +93,7 @@ struct RowsArgs {
 };
 
 template <int DEG, int NORD, int G, int KCH, bool STAGED>
-__global__ void __launch_bounds__(PL_THREADS, 2) psgd_rows_kernel(const RowsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
@@ -101,14 +101,23 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_rows_kernel(const RowsArgs
     const int n_groups = gridDim.x * gpb;
     const int k = a.k;
     const size_t dk = (size_t)a.d * k;
+    // The inner loop is branch-free: lanes past a row's end carry (column 0, x = 0), whose terms vanish, and
+    // lanes that own no component (s >= k) read a valid dummy address and are never written back.
     double lam[KCH], thr[KCH][NORD];
+    const double *Pl[KCH][NORD];                       // lane's element of row 0 of every order
+    const double invC = a.invC, invCw = a.invCw;
+    const size_t rstride = STAGED ? (size_t)NORD * k : (size_t)k;
 #pragma unroll
     for (int c = 0; c < KCH; c++) {
         const int s = lane + G * c;
         lam[c] = s < k ? a.lams[s] : 0.0;
 #pragma unroll
-        for (int o = 0; o < NORD; o++) thr[c][o] = (!STAGED && s < k) ? a.thr[o * k + s] : 0.0;
+        for (int o = 0; o < NORD; o++) {
+            thr[c][o] = (!STAGED && s < k) ? a.thr[o * k + s] : 0.0;
+            Pl[c][o] = a.Psrc + (s < k ? (STAGED ? (size_t)o * k + s : o * dk + s) : 0);
+        }
     }
+    const bool lin = a.fit_linear != 0;
     for (int b = a.b0 + blockIdx.x * gpb + threadIdx.x / G; b < a.b1; b += n_groups) {
         const int i = a.idx[b];
         const int st = a.indptr[i], en = a.indptr[i + 1];
@@ -122,53 +131,41 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_rows_kernel(const RowsArgs
                 for (int t = 1; t <= DEG; t++) A[c][o][t] = 0.0;
             }
         double ypred = 0.0;                                   // _pred, psgd.py:47-57
+        int jl = 0;
+        double xl = 0.0;
+        if (st + lane < en) { jl = a.colidx[st + lane]; xl = a.data[st + lane]; }
         for (int base = st; base < en; base += G) {
-            const int e = base + lane;
-            int jl = 0;
-            double xl = 0.0;
-            if (e < en) {
-                jl = a.colidx[e]; xl = a.data[e];
-                if (a.fit_linear) ypred += xl * (STAGED ? a.wsrc[jl] : a.wsrc[jl] * a.invCw);
-            }
+            int jn = 0;                                       // the next block of (column, value): in flight during this one
+            double xn = 0.0;
+            if (base + G + lane < en) { jn = a.colidx[base + G + lane]; xn = a.data[base + G + lane]; }
+            if (lin) ypred += xl * (STAGED ? a.wsrc[jl] : a.wsrc[jl] * invCw);
             const int cnt = min(G, en - base);
-            constexpr int UB = (16 / (KCH * NORD) > 8) ? 8 : ((16 / (KCH * NORD) < 1) ? 1 : 16 / (KCH * NORD));   // row gathers in flight
+            constexpr int UBR = 16 / (KCH * NORD);
+            constexpr int UB = UBR >= 8 ? 8 : (UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1));
             for (int q0 = 0; q0 < cnt; q0 += UB) {
                 double pv[UB][KCH][NORD], xv[UB];
 #pragma unroll
                 for (int u = 0; u < UB; u++) {                // UB independent row gathers in flight
-                    const int q = q0 + u;
-                    const int j = __shfl_sync(gmask, jl, q & (G - 1), G);
-                    xv[u] = __shfl_sync(gmask, xl, q & (G - 1), G);
+                    const size_t at = (size_t)__shfl_sync(gmask, jl, q0 + u, G) * rstride;
+                    xv[u] = __shfl_sync(gmask, xl, q0 + u, G);
+#pragma unroll
+                    for (int c = 0; c < KCH; c++)
+#pragma unroll
+                        for (int o = 0; o < NORD; o++) pv[u][c][o] = Pl[c][o][at];
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++)
 #pragma unroll
                     for (int c = 0; c < KCH; c++)
 #pragma unroll
                         for (int o = 0; o < NORD; o++) {
-                            const int s = lane + G * c;
-                            const size_t at = STAGED ? ((size_t)j * NORD + o) * k + s : o * dk + (size_t)j * k + s;
-                            pv[u][c][o] = (q < cnt && s < k) ? a.Psrc[at] : 0.0;
+                            const double p = STAGED ? pv[u][c][o] : st_true(pv[u][c][o], thr[c][o], invC);
+#pragma unroll
+                            for (int t = 0; t < DEG - o; t++)           // _anova, psgd.py:34-44
+                                A[c][o][DEG - o - t] += (A[c][o][DEG - o - t - 1] * xv[u]) * p;
                         }
-                }
-                if (!STAGED) {
-#pragma unroll
-                    for (int u = 0; u < UB; u++)
-#pragma unroll
-                        for (int c = 0; c < KCH; c++)
-#pragma unroll
-                            for (int o = 0; o < NORD; o++) pv[u][c][o] = st_true(pv[u][c][o], thr[c][o], a.invC);
-                }
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    if (q0 + u < cnt) {
-#pragma unroll
-                        for (int c = 0; c < KCH; c++)
-#pragma unroll
-                            for (int o = 0; o < NORD; o++)
-#pragma unroll
-                                for (int t = 0; t < DEG - o; t++)       // _anova, psgd.py:34-44
-                                    A[c][o][DEG - o - t] += (A[c][o][DEG - o - t - 1] * xv[u]) * pv[u][c][o];
-                    }
-                }
             }
+            jl = jn; xl = xn;
         }
 #pragma unroll
         for (int m = G / 2; m > 0; m >>= 1) ypred += __shfl_xor_sync(gmask, ypred, m, G);
@@ -217,7 +214,10 @@ struct ColsArgs {
     const int32_t *u_feat;               // ABSOLUTE column arrays
     const int64_t *u_ptr;
     long long u_base;                    // absolute column offset of the minibatch
-    const int32_t *short_u;              // minibatch-relative lists: short columns (<= SP_PSGD_SHORT nonzeros) ...
+    const int32_t *sg_u, *sg_feat, *sg_pos;   // minibatch-relative lists: columns of ONE nonzero (column, feature, position,
+    const double *sg_x;                       // value) ...
+    int n_single;
+    const int32_t *short_u;              // ... short columns (2..SP_PSGD_SHORT nonzeros) ...
     int n_short;
     const int32_t *lc_u;                 // ... chunks of the long columns (column, first nonzero) ...
     const int64_t *lc_e0;
@@ -324,13 +324,80 @@ __device__ __forceinline__ void add_term(double (&g)[KCH][NORD], double &gw, dou
         }
 }
 
-// ---- short columns (<= SP_PSGD_SHORT nonzeros; 95 % of a Criteo-shaped minibatch's columns): one group of lanes
-// per column, all of its table-row gathers in flight at once, terms added in sample order (the reference's)
+// ---- columns of a single nonzero (70 % of a Criteo-shaped minibatch's columns): the plan stores (feature, position,
+// value) per column, a group of G lanes fetches G of them at once and finishes UBC at a time -- row of P, table row
+// and dloss of all UBC in flight together, no dependence between them
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const ColsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const ColsArgs a) {
+    constexpr int AR = ARows<DEG, NORD>::value;
+    constexpr int UBR = 16 / (KCH * (AR + NORD));
+    constexpr int UBC = UBR >= 8 ? 8 : (UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1));
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
+    const int gpb = PL_THREADS / G;
+    const int k = a.k;
+    double lam[KCH], thr[KCH][NORD];
+    const double *Al[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; c++) {
+        const int s = lane + G * c;
+        lam[c] = s < k ? a.lams[s] : 0.0;
+        Al[c] = a.bufA + (s < k ? s : 0);
+#pragma unroll
+        for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
+    }
+    const size_t astride = (size_t)AR * k;
+    for (int qb = (blockIdx.x * gpb + threadIdx.x / G) * G; qb < a.n_single; qb += gridDim.x * gpb * G) {
+        int u_l = (int)a.u_base, feat_l = 0, pos_l = 0;       // (lanes past the end: a valid dummy column, never finished)
+        double x_l = 0.0;
+        if (qb + lane < a.n_single) {
+            u_l = a.sg_u[qb + lane]; feat_l = a.sg_feat[qb + lane]; pos_l = a.sg_pos[qb + lane]; x_l = a.sg_x[qb + lane];
+        }
+        const int ncol = (a.n_single - qb < G) ? a.n_single - qb : G;
+        for (int c0 = 0; c0 < ncol; c0 += UBC) {
+            double pold[UBC][KCH][NORD], av[UBC][KCH][AR], dl[UBC], xv[UBC];
+            int uu[UBC], ff[UBC];
+#pragma unroll
+            for (int t = 0; t < UBC; t++) {                     // gathers of UBC columns in flight
+                const int cc = (c0 + t) & (G - 1);
+                uu[t] = __shfl_sync(gmask, u_l, cc, G);
+                ff[t] = __shfl_sync(gmask, feat_l, cc, G);
+                const int pos = __shfl_sync(gmask, pos_l, cc, G);
+                xv[t] = __shfl_sync(gmask, x_l, cc, G);
+                load_row<NORD, G, KCH, MODE>(a, lane, ff[t], uu[t] - a.u_base, pold[t], thr);
+                dl[t] = a.bufdL[pos];
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int r = 0; r < AR; r++) av[t][c][r] = Al[c][(size_t)pos * astride + (size_t)r * k];
+            }
+#pragma unroll
+            for (int t = 0; t < UBC; t++) {
+                if (c0 + t >= ncol) break;
+                double g[KCH][NORD];
+                double gw = 0.0;
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+                add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold[t], lam);
+                finish_column<NORD, G, KCH, MODE>(a, lane, uu[t], ff[t], g, gw, pold[t], thr);
+            }
+        }
+    }
+}
+
+// ---- short columns (2..SP_PSGD_SHORT nonzeros; a quarter of a Criteo-shaped minibatch's columns; the plan keeps
+// single-nonzero columns apart).  A group of G lanes takes G columns at a time: lane l fetches column l's descriptor and first
+// nonzero (one dependent chain for G columns instead of one per column), then the columns are finished UBC at a
+// time with all their row gathers in flight.  Terms are added in sample order (the reference's).
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_short_kernel(const ColsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
     constexpr int SH = SP_PSGD_SHORT;
-    static_assert(SH <= 8 && G >= 8, "a group's lanes hold the column's nonzeros");
+    static_assert(SH <= 8 && G >= 8, "a group's lanes hold a column's nonzeros");
+    constexpr int UBR = 8 / (KCH * (AR + NORD));
+    constexpr int UBC = UBR > 4 ? 4 : (UBR < 1 ? 1 : UBR);      // columns finished together
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
@@ -343,52 +410,94 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const Co
 #pragma unroll
         for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
     }
-    for (int q = blockIdx.x * gpb + threadIdx.x / G; q < a.n_short; q += gridDim.x * gpb) {
-        const int u = a.short_u[q];
-        const long long e0 = a.u_ptr[u];
-        const int len = (int)(a.u_ptr[u + 1] - e0);
-        const int feat = a.u_feat[u];
-        int ep = 0;
-        double ex = 0.0;
-        if (lane < len) { ep = a.e_pos[e0 + lane]; ex = a.e_x[e0 + lane]; }
-        double pold[KCH][NORD];
-        load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
-        double g[KCH][NORD];
-        double gw = 0.0;
+    for (int qb = (blockIdx.x * gpb + threadIdx.x / G) * G; qb < a.n_short; qb += gridDim.x * gpb * G) {
+        // ---- descriptors of G columns, one per lane
+        int u_l = 0, feat_l = 0, len_l = 0, ep_l = 0;
+        long long e0_l = 0;
+        double ex_l = 0.0;
+        if (qb + lane < a.n_short) {
+            u_l = a.short_u[qb + lane];
+            e0_l = a.u_ptr[u_l];
+            len_l = (int)(a.u_ptr[u_l + 1] - e0_l);
+            feat_l = a.u_feat[u_l];
+            ep_l = a.e_pos[e0_l];
+            ex_l = a.e_x[e0_l];
+        }
+        const int ncol = (a.n_short - qb < G) ? a.n_short - qb : G;
+        for (int c0 = 0; c0 < ncol; c0 += UBC) {
+            double pold[UBC][KCH][NORD], av[UBC][KCH][AR], dl[UBC], xv[UBC];
+            int uu[UBC], ff[UBC], ln[UBC];
+            long long ee[UBC];
 #pragma unroll
-        for (int c = 0; c < KCH; c++)
+            for (int t = 0; t < UBC; t++) {                     // gathers of UBC columns in flight
+                const int cc = (c0 + t) & (G - 1);
+                uu[t] = __shfl_sync(gmask, u_l, cc, G);
+                ff[t] = __shfl_sync(gmask, feat_l, cc, G);
+                ln[t] = (c0 + t < ncol) ? __shfl_sync(gmask, len_l, cc, G) : 0;
+                ee[t] = __shfl_sync(gmask, e0_l, cc, G);
+                const int pos = __shfl_sync(gmask, ep_l, cc, G);
+                xv[t] = __shfl_sync(gmask, ex_l, cc, G);
+                if (ln[t] > 0) {
+                    load_row<NORD, G, KCH, MODE>(a, lane, ff[t], uu[t] - a.u_base, pold[t], thr);
+                    dl[t] = a.bufdL[pos];
 #pragma unroll
-            for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
-        constexpr int UBR = 16 / (KCH * AR);
-        constexpr int UB = UBR > SH ? SH : (UBR < 1 ? 1 : UBR);
-        for (int q0 = 0; q0 < len; q0 += UB) {
-            double av[UB][KCH][AR], dl[UB], xv[UB];
+                    for (int c = 0; c < KCH; c++) {
+                        const int s = lane + G * c;
 #pragma unroll
-            for (int t = 0; t < UB; t++) {
-                const int pos = __shfl_sync(gmask, ep, (q0 + t) & (G - 1), G);
-                xv[t] = __shfl_sync(gmask, ex, (q0 + t) & (G - 1), G);
-                const bool live = q0 + t < len;
-                dl[t] = live ? a.bufdL[pos] : 0.0;
-#pragma unroll
-                for (int c = 0; c < KCH; c++) {
-                    const int s = lane + G * c;
-#pragma unroll
-                    for (int r = 0; r < AR; r++) av[t][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                        for (int r = 0; r < AR; r++) av[t][c][r] = s < k ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                    }
                 }
             }
 #pragma unroll
-            for (int t = 0; t < UB; t++)
-                if (q0 + t < len) add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold, lam);
+            for (int t = 0; t < UBC; t++) {
+                if (ln[t] == 0) continue;
+                double g[KCH][NORD];
+                double gw = 0.0;
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+                add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold[t], lam);
+                if (ln[t] > 1) {                                 // 2..SH nonzeros: the rest, gathered together
+                    int ep = 0;
+                    double ex = 0.0;
+                    if (lane < ln[t]) { ep = a.e_pos[ee[t] + lane]; ex = a.e_x[ee[t] + lane]; }
+                    double av2[SH - 1][KCH][AR], dl2[SH - 1], x2[SH - 1];
+#pragma unroll
+                    for (int q = 1; q < SH; q++) {
+                        const int pos = __shfl_sync(gmask, ep, q, G);
+                        x2[q - 1] = __shfl_sync(gmask, ex, q, G);
+                        const bool live = q < ln[t];
+                        dl2[q - 1] = live ? a.bufdL[pos] : 0.0;
+#pragma unroll
+                        for (int c = 0; c < KCH; c++) {
+                            const int s = lane + G * c;
+#pragma unroll
+                            for (int r = 0; r < AR; r++)
+                                av2[q - 1][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 1; q < SH; q++)
+                        if (q < ln[t]) add_term<DEG, NORD, KCH, AR>(g, gw, x2[q - 1], dl2[q - 1], av2[q - 1], pold[t], lam);
+                }
+                finish_column<NORD, G, KCH, MODE>(a, lane, uu[t], ff[t], g, gw, pold[t], thr);
+            }
         }
-        finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
     }
 }
 
 // ---- long columns: cut into chunks of SP_PSGD_CHUNK nonzeros of ONE column -- a pure streaming sum, no column
-// bookkeeping inside.  A column of one chunk is finished right here, the others leave one partial per chunk.
+// bookkeeping inside; the gathers of the next UB nonzeros are in flight while the current UB are being added.
+// A column of one chunk is finished right here, the others leave one partial per chunk.
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_long_kernel(const ColsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const ColsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
+    constexpr int SETS = CH / G;                               // (position, value) pairs held per lane
+    constexpr int UBR = 16 / (KCH * AR);
+    constexpr int UB = UBR >= 8 ? 8 : (UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1));
+    constexpr int NB = CH / UB;
+    static_assert(G % UB == 0, "a batch never straddles two sets");
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
@@ -398,9 +507,17 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_long_kernel(const Col
     const int u = a.lc_u[chunk];
     const long long ce0 = a.lc_e0[chunk];
     const long long cend = a.u_ptr[u + 1];
-    const long long ce1 = ce0 + CH < cend ? ce0 + CH : cend;
+    const int cnt = (int)((cend - ce0 < CH) ? cend - ce0 : CH);
     const bool single = (cend - a.u_ptr[u]) <= CH;
     const int feat = a.u_feat[u];
+    int ep[SETS];
+    double ex[SETS];
+#pragma unroll
+    for (int sidx = 0; sidx < SETS; sidx++) {                  // nonzeros past the chunk's end: x = 0 and dloss = 0 below,
+        const int q = sidx * G + lane;                         // so their terms vanish without a branch
+        ep[sidx] = 0; ex[sidx] = 0.0;
+        if (q < cnt) { ep[sidx] = a.e_pos[ce0 + q]; ex[sidx] = a.e_x[ce0 + q]; }
+    }
     double lam[KCH], thr[KCH][NORD], pold[KCH][NORD], g[KCH][NORD];
     double gw = 0.0;
 #pragma unroll
@@ -411,36 +528,39 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_long_kernel(const Col
         for (int o = 0; o < NORD; o++) { thr[c][o] = s < k ? a.thr[o * k + s] : 0.0; g[c][o] = 0.0; }
     }
     load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
-    constexpr int UBR = 16 / (KCH * AR);
-    constexpr int UB = UBR > 8 ? 8 : (UBR < 1 ? 1 : UBR);
-    int ep = 0;
-    double ex = 0.0;
-    if (ce0 + lane < ce1) { ep = a.e_pos[ce0 + lane]; ex = a.e_x[ce0 + lane]; }
-    for (long long base = ce0; base < ce1; base += G) {
-        const int cnt = (int)((ce1 - base < G) ? ce1 - base : G);
-        int ep_n = 0;                                          // next block of (position, value): in flight during this one
-        double ex_n = 0.0;
-        if (base + G + lane < ce1) { ep_n = a.e_pos[base + G + lane]; ex_n = a.e_x[base + G + lane]; }
-        for (int q0 = 0; q0 < cnt; q0 += UB) {
-            double av[UB][KCH][AR], dl[UB], xv[UB];
+    // nonzeros past the chunk's end carry (position 0, x = 0): every one of their terms is a product with x, so the
+    // gathers below need no predicate; lanes that own no component read a valid dummy address and are not stored
+    const double *Al[KCH];
 #pragma unroll
-            for (int t = 0; t < UB; t++) {                      // UB independent gathers in flight
-                const int pos = __shfl_sync(gmask, ep, (q0 + t) & (G - 1), G);
-                xv[t] = __shfl_sync(gmask, ex, (q0 + t) & (G - 1), G);
-                const bool live = q0 + t < cnt;
-                dl[t] = live ? a.bufdL[pos] : 0.0;
+    for (int c = 0; c < KCH; c++) Al[c] = a.bufA + ((lane + G * c) < k ? lane + G * c : 0);
+    const size_t astride = (size_t)AR * k;
+    double av[2][UB][KCH][AR], dl[2][UB], xv[2][UB];
+    auto load_batch = [&](int buf, int b) {
 #pragma unroll
-                for (int c = 0; c < KCH; c++) {
-                    const int s = lane + G * c;
+        for (int t = 0; t < UB; t++) {
+            const int q = b * UB + t;
+            const int pos = __shfl_sync(gmask, ep[q / G], q & (G - 1), G);
+            xv[buf][t] = __shfl_sync(gmask, ex[q / G], q & (G - 1), G);
+            dl[buf][t] = a.bufdL[pos];
 #pragma unroll
-                    for (int r = 0; r < AR; r++) av[t][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
-                }
-            }
+            for (int c = 0; c < KCH; c++)
 #pragma unroll
-            for (int t = 0; t < UB; t++)
-                if (q0 + t < cnt) add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold, lam);
+                for (int r = 0; r < AR; r++) av[buf][t][c][r] = Al[c][(size_t)pos * astride + (size_t)r * k];
         }
-        ep = ep_n; ex = ex_n;
+    };
+    auto add_batch = [&](int buf) {
+#pragma unroll
+        for (int t = 0; t < UB; t++) add_term<DEG, NORD, KCH, AR>(g, gw, xv[buf][t], dl[buf][t], av[buf][t], pold, lam);
+    };
+    load_batch(0, 0);
+#pragma unroll
+    for (int b = 0; b < NB; b += 2) {
+        if (b + 1 < NB && (b + 1) * UB < cnt) load_batch(1, b + 1);
+        add_batch(0);
+        if ((b + 1) * UB >= cnt) break;
+        if (b + 2 < NB && (b + 2) * UB < cnt) load_batch(0, b + 2);
+        add_batch(1);
+        if ((b + 2) * UB >= cnt) break;
     }
     if (single) {
         finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
@@ -459,11 +579,12 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_long_kernel(const Col
 
 // long columns of several chunks: one block per column adds the chunks' partial sums -- group w the chunks w,
 // w+G', ... in order, then the groups' sums in group order (a fixed association: deterministic) -- and finishes it
+constexpr int CB_THREADS = 1024;
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS) psgd_cols_combine_kernel(const ColsArgs a) {
-    constexpr int GPB = PL_THREADS / G;
+__global__ void __launch_bounds__(CB_THREADS) psgd_cols_combine_kernel(const ColsArgs a) {
+    constexpr int GPB = CB_THREADS / G;
     constexpr int ROW = KCH * G * NORD + 1;
-    __shared__ double sh[GPB * ROW];
+    extern __shared__ double cb_sh[];                          // [GPB][ROW]
     const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
     const int k = a.k;
     const int u = a.ml_u[blockIdx.x];
@@ -490,8 +611,8 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_cols_combine_kernel(const Col
 #pragma unroll
     for (int c = 0; c < KCH; c++)
 #pragma unroll
-        for (int o = 0; o < NORD; o++) sh[grp * ROW + (c * NORD + o) * G + lane] = g[c][o];
-    if (lane == 0) sh[grp * ROW + ROW - 1] = gw;
+        for (int o = 0; o < NORD; o++) cb_sh[grp * ROW + (c * NORD + o) * G + lane] = g[c][o];
+    if (lane == 0) cb_sh[grp * ROW + ROW - 1] = gw;
     __syncthreads();
     if (grp != 0) return;
     const int ngrp = np < GPB ? np : GPB;
@@ -499,8 +620,8 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_cols_combine_kernel(const Col
 #pragma unroll
         for (int c = 0; c < KCH; c++)
 #pragma unroll
-            for (int o = 0; o < NORD; o++) g[c][o] += sh[w * ROW + (c * NORD + o) * G + lane];
-        gw += sh[w * ROW + ROW - 1];
+            for (int o = 0; o < NORD; o++) g[c][o] += cb_sh[w * ROW + (c * NORD + o) * G + lane];
+        gw += cb_sh[w * ROW + ROW - 1];
     }
     double thr[KCH][NORD], pold[KCH][NORD];
 #pragma unroll
@@ -1056,7 +1177,7 @@ int grid_for(long long groups, int G) {
 
 // ============================================================================================ host side
 struct PlanMb {                          // one minibatch of the plan, resolved on the host
-    long long e0, e1, u0, u1, sh0, sh1, lc0, lc1, ml0, ml1;
+    long long e0, e1, u0, u1, sg0, sg1, sh0, sh1, lc0, lc1, ml0, ml1;
     int b0, b1;
 };
 
@@ -1064,6 +1185,7 @@ static inline PlanMb plan_mb(const sp_psgd_plan *pl, int m) {
     PlanMb q;
     q.e0 = pl->mb_eptr_host[m]; q.e1 = pl->mb_eptr_host[m + 1];
     q.u0 = pl->mb_uptr_host[m]; q.u1 = pl->mb_uptr_host[m + 1];
+    q.sg0 = pl->mb_sgptr_host[m]; q.sg1 = pl->mb_sgptr_host[m + 1];
     q.sh0 = pl->mb_shptr_host[m]; q.sh1 = pl->mb_shptr_host[m + 1];
     q.lc0 = pl->mb_lcptr_host[m]; q.lc1 = pl->mb_lcptr_host[m + 1];
     q.ml0 = pl->mb_mlptr_host[m]; q.ml1 = pl->mb_mlptr_host[m + 1];
@@ -1101,6 +1223,8 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
     ca.e_pos = pl->e_pos; ca.e_x = pl->e_x;
     ca.u_feat = pl->u_feat; ca.u_ptr = pl->u_ptr;
     ca.u_base = mb.u0;
+    ca.sg_u = pl->sg_u + mb.sg0; ca.sg_feat = pl->sg_feat + mb.sg0; ca.sg_pos = pl->sg_pos + mb.sg0; ca.sg_x = pl->sg_x + mb.sg0;
+    ca.n_single = (int)(mb.sg1 - mb.sg0);
     ca.short_u = pl->short_u + mb.sh0; ca.n_short = (int)(mb.sh1 - mb.sh0);
     ca.lc_u = pl->lc_u + mb.lc0; ca.lc_e0 = pl->lc_e0 + mb.lc0; ca.n_chunks = (int)(mb.lc1 - mb.lc0);
     ca.ml_u = pl->ml_u + mb.ml0; ca.ml_c0 = pl->ml_c0 + mb.ml0; ca.n_multi = (int)(mb.ml1 - mb.ml0);
@@ -1126,12 +1250,26 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
         SP_LAUNCH_CHECK("psgd_cols_long_kernel");
     }
     if (ca.n_multi > 0) {
-        if (sharded) psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<ca.n_multi, PL_THREADS, 0, st>>>(ca);
-        else psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<ca.n_multi, PL_THREADS, 0, st>>>(ca);
+        const size_t csm = (size_t)(CB_THREADS / G) * (KCH * G * NORD + 1) * sizeof(double);
+        static bool attr_done = false;                       // (per template instance)
+        if (!attr_done && csm > 48 * 1024) {
+            SP_CUDA(cudaFuncSetAttribute(psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            SP_CUDA(cudaFuncSetAttribute(psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            attr_done = true;
+        }
+        if (sharded) psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<ca.n_multi, CB_THREADS, csm, st>>>(ca);
+        else psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<ca.n_multi, CB_THREADS, csm, st>>>(ca);
         SP_LAUNCH_CHECK("psgd_cols_combine_kernel");
     }
+    if (ca.n_single > 0) {
+        int sb = grid_for((ca.n_single + G - 1) / G, G);
+        if (sb > 148 * 12) sb = 148 * 12;
+        if (sharded) psgd_cols_single_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
+        else psgd_cols_single_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
+        SP_LAUNCH_CHECK("psgd_cols_single_kernel");
+    }
     if (ca.n_short > 0) {
-        int sb = grid_for(ca.n_short, G);
+        int sb = grid_for((ca.n_short + G - 1) / G, G);
         if (sb > 148 * 12) sb = 148 * 12;
         if (sharded) psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
         else psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);

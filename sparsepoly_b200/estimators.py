@@ -392,7 +392,17 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
             if abs(sizes[1] * world - sizes[0] ** 2) > 0.5:
                 raise ValueError("sharded psgd needs the same number of samples on every rank")
         planned = self.regularizer in solvers.PLANNED_REGS
-        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned, pin=planned)
+        import os
+        import time
+        timing = os.environ.get("SPARSEPOLY_B200_TIMING") == "1"
+
+        def _tick():
+            if timing:
+                torch.cuda.synchronize()
+            return time.perf_counter()
+        t0 = _tick()
+        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned)
+        t1 = _tick()
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         n_glob, nnz_glob = (global_sum([n, ds.nnz], group) if group is not None else (n, ds.nnz))
         if self.batch_size == "auto":
@@ -413,7 +423,9 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         if planned:
             from .psgd_plan import PsgdContext, PsgdPlan
             b_loc = max(1, batch_size // world)
+            t2 = _tick()
             st["plan"] = PsgdPlan(ds.csr, idx_dev, d, b_loc, world=world, rank=rank, group=group)
+            t3 = _tick()
             ctx = PsgdContext(st["plan"], P.shape[0], k, self.degree, self.regularizer, self.loss, self.fit_linear, lams,
                               group=group,
                               inbox_cap=(min(st["plan"].d_rows, b_loc * int(ds.max_row_nnz())) if self.shuffle else None))
@@ -421,7 +433,9 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
             solvers.psgd_planned_begin(ctx)
             self._psgd_stats = {"plan_bytes": st["plan"].nbytes(), "minibatches": st["plan"].n_minibatches,
                                 "columns_per_minibatch": st["plan"].n_cols / max(st["plan"].n_minibatches, 1),
-                                "batch_size": batch_size, "batch_local": b_loc, "world": world}
+                                "batch_size": batch_size, "batch_local": b_loc, "world": world,
+                                "setup_seconds": {"upload_X": t1 - t0, "upload_model": t2 - t1, "plan": t3 - t2,
+                                                  "context": _tick() - t3, "synchronised": timing}}
         else:
             grad_P = torch.zeros_like(P)
             grad_w = torch.zeros(d, dtype=_f64, device=dev)

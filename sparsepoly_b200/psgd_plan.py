@@ -84,7 +84,8 @@ class PsgdPlan:
         self.e_x = torch.empty(E, dtype=torch.float64, device=dev)
         self.csr_slot = torch.zeros(nnz_total, dtype=torch.int32, device=dev) if G > 1 else None
         u_feat, u_ptr, short_u, lc_u, lc_e0, ml_u, ml_c0 = [], [], [], [], [], [], []
-        mb_ucnt, mb_shcnt, mb_lccnt, mb_mlcnt, owner_cnt = [], [], [], [], []
+        sg_u, sg_feat, sg_pos, sg_x = [], [], [], []
+        mb_ucnt, mb_sgcnt, mb_shcnt, mb_lccnt, mb_mlcnt, owner_cnt = [], [], [], [], [], []
         u_off = 0
         m0 = 0
         while m0 < M:
@@ -96,7 +97,7 @@ class PsgdPlan:
             tot = e1 - e0
             Mg = m1 - m0
             if tot == 0:
-                for lst in (mb_ucnt, mb_shcnt, mb_lccnt, mb_mlcnt):
+                for lst in (mb_ucnt, mb_sgcnt, mb_shcnt, mb_lccnt, mb_mlcnt):
                     lst.append(np.zeros(Mg, np.int64))
                 owner_cnt.append(np.zeros((Mg, G), np.int64))
                 m0 = m1
@@ -114,7 +115,10 @@ class PsgdPlan:
             del pos_rep
             key = mb * Dkey + (feat % G) * dq + feat // G
             del feat
+            if Mg * Dkey < 2 ** 31:
+                key = key.to(torch.int32)                                       # half the radix passes
             key, order = torch.sort(key, stable=True)                           # samples stay ascending inside a column
+            key = key.to(i64)
             newcol = torch.ones(tot, dtype=torch.bool, device=dev)
             newcol[1:] = key[1:] != key[:-1]
             self.e_pos[e0:e1] = lpos[order]
@@ -148,7 +152,13 @@ class PsgdPlan:
             uend[-1] = tot
             ulen = uend - ustart
             is_short = ulen <= SHORT
-            sh_idx = torch.nonzero(is_short).squeeze(1)
+            sg_idx = torch.nonzero(ulen == 1).squeeze(1)                          # single-nonzero columns: kept apart, self-contained
+            sg_u.append((sg_idx + u_off).to(torch.int32))
+            sg_feat.append(u_feat[-1][sg_idx])
+            sg_pos.append(self.e_pos[e0:e1][ustart[sg_idx]])
+            sg_x.append(self.e_x[e0:e1][ustart[sg_idx]])
+            mb_sgcnt.append(torch.bincount(umb[sg_idx], minlength=Mg).cpu().numpy())
+            sh_idx = torch.nonzero(is_short & (ulen > 1)).squeeze(1)
             short_u.append((sh_idx + u_off).to(torch.int32))
             mb_shcnt.append(torch.bincount(umb[sh_idx], minlength=Mg).cpu().numpy())
             lg_idx = torch.nonzero(~is_short).squeeze(1)
@@ -176,6 +186,8 @@ class PsgdPlan:
         cat = lambda xs, dt: (torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev))   # noqa: E731
         self.u_feat = cat(u_feat, torch.int32)
         self.u_ptr = torch.cat([cat(u_ptr, i64), torch.tensor([E], dtype=i64, device=dev)])
+        self.sg_u, self.sg_feat, self.sg_pos = cat(sg_u, torch.int32), cat(sg_feat, torch.int32), cat(sg_pos, torch.int32)
+        self.sg_x = cat(sg_x, torch.float64)
         self.short_u = cat(short_u, torch.int32)
         self.lc_u = cat(lc_u, torch.int32)
         self.lc_e0 = cat(lc_e0, i64)
@@ -184,6 +196,7 @@ class PsgdPlan:
         acc = lambda parts: np.concatenate([[0], np.cumsum(np.concatenate(parts) if parts else np.zeros(0, np.int64))]).astype(np.int64)  # noqa: E731
         self.mb_eptr = mb_eptr
         self.mb_uptr = acc(mb_ucnt)
+        self.mb_sgptr = acc(mb_sgcnt)
         self.mb_shptr = acc(mb_shcnt)
         self.mb_lcptr = acc(mb_lccnt)
         self.mb_mlptr = acc(mb_mlcnt)
@@ -273,7 +286,9 @@ class PsgdPlan:
         s.chunk, s.short_max = CHUNK, SHORT
         hp = lambda a: a.ctypes.data                         # noqa: E731  (host arrays are kept alive by self)
         s.mb_eptr_host, s.mb_uptr_host = hp(self.mb_eptr), hp(self.mb_uptr)
+        s.mb_sgptr_host = hp(self.mb_sgptr)
         s.mb_shptr_host, s.mb_lcptr_host, s.mb_mlptr_host = hp(self.mb_shptr), hp(self.mb_lcptr), hp(self.mb_mlptr)
+        s.sg_u, s.sg_feat, s.sg_pos, s.sg_x = (t.data_ptr() for t in (self.sg_u, self.sg_feat, self.sg_pos, self.sg_x))
         s.e_pos, s.e_x = self.e_pos.data_ptr(), self.e_x.data_ptr()
         s.u_feat, s.u_ptr = self.u_feat.data_ptr(), self.u_ptr.data_ptr()
         s.short_u, s.lc_u, s.lc_e0 = self.short_u.data_ptr(), self.lc_u.data_ptr(), self.lc_e0.data_ptr()
@@ -290,7 +305,7 @@ class PsgdPlan:
         return C.byref(self.struct)
 
     def nbytes(self):
-        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.short_u, self.lc_u, self.lc_e0, self.ml_u, self.ml_c0,
+        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.sg_u, self.sg_feat, self.sg_pos, self.sg_x, self.short_u, self.lc_u, self.lc_e0, self.ml_u, self.ml_c0,
               self.csr_slot, self.own_q, self.own_src]
         return sum(t.numel() * t.element_size() for t in ts if t is not None)
 

@@ -79,6 +79,7 @@ class RankState:
         self.e_pos, self.e_x = t(plan.e_pos), t(plan.e_x)
         self.u_feat, self.u_ptr = t(plan.u_feat), t(plan.u_ptr)
         self.short_u, self.lc_u, self.lc_e0 = t(plan.short_u), t(plan.lc_u), t(plan.lc_e0)
+        self.sg_u, self.sg_feat, self.sg_pos, self.sg_x = t(plan.sg_u), t(plan.sg_feat), t(plan.sg_pos), t(plan.sg_x)
         self.ml_u, self.ml_c0 = t(plan.ml_u), t(plan.ml_c0)
         self.csr_slot = t(plan.csr_slot)
         self.own_q, self.own_src = t(plan.own_q), t(plan.own_src)
@@ -178,9 +179,16 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                     return g, gw
 
                 seen = np.zeros(u1 - u0, dtype=int)
+                for q in range(pl.mb_sgptr[m], pl.mb_sgptr[m + 1]):       # single-nonzero columns: self-contained records
+                    u = int(R.sg_u[q])
+                    assert R.u_ptr[u + 1] - R.u_ptr[u] == 1 and R.u_feat[u] == R.sg_feat[q]
+                    assert R.e_pos[R.u_ptr[u]] == R.sg_pos[q] and R.e_x[R.u_ptr[u]] == R.sg_x[q]
+                    tg, tw = term(int(R.sg_pos[q]), R.sg_x[q], stage[u - u0])
+                    done[(u, )] = (np.zeros((n_orders, k)) + tg, 0.0 + tw)
+                    seen[u - u0] += 1
                 for u in R.short_u[pl.mb_shptr[m]:pl.mb_shptr[m + 1]]:
                     ea, eb = R.u_ptr[u], R.u_ptr[u + 1]
-                    assert 1 <= eb - ea <= SH and e0 <= ea and eb <= e1
+                    assert 2 <= eb - ea <= SH and e0 <= ea and eb <= e1
                     done[(int(u), )] = sum_entries(ea, eb, stage[u - u0])
                     seen[u - u0] += 1
                 lc0, lc1 = pl.mb_lcptr[m], pl.mb_lcptr[m + 1]
@@ -199,7 +207,7 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                     u, c0 = int(R.ml_u[q]), int(R.ml_c0[q])
                     npc = -(-(R.u_ptr[u + 1] - R.u_ptr[u]) // CH)
                     assert npc > 1
-                    GPB = 8                                  # groups of a block add strided pieces, then in group order
+                    GPB = 32                                 # groups of a block add strided pieces, then in group order
                     gs = []
                     for wg in range(min(GPB, npc)):
                         g, gw = np.zeros((n_orders, k)), 0.0

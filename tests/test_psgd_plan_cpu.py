@@ -55,7 +55,11 @@ def test_plan_layout_matches_brute_force(b_loc, group_entries):
         assert np.array_equal(e_x[e0:e1], [t[2] for t in want])
         lens = np.diff(u_ptr[u0:u1 + 1])
         short = plan.short_u.numpy()[plan.mb_shptr[m]:plan.mb_shptr[m + 1]]
-        assert np.array_equal(short, u0 + np.nonzero(lens <= SHORT)[0])
+        assert np.array_equal(short, u0 + np.nonzero((lens <= SHORT) & (lens > 1))[0])
+        sg = slice(plan.mb_sgptr[m], plan.mb_sgptr[m + 1])
+        singles = u0 + np.nonzero(lens == 1)[0]
+        assert np.array_equal(plan.sg_u.numpy()[sg], singles) and np.array_equal(plan.sg_feat.numpy()[sg], u_feat[singles])
+        assert np.array_equal(plan.sg_pos.numpy()[sg], e_pos[u_ptr[singles]]) and np.array_equal(plan.sg_x.numpy()[sg], e_x[u_ptr[singles]])
         lc_u = plan.lc_u.numpy()[plan.mb_lcptr[m]:plan.mb_lcptr[m + 1]]
         lc_e0 = plan.lc_e0.numpy()[plan.mb_lcptr[m]:plan.mb_lcptr[m + 1]]
         want_u, want_e = [], []
