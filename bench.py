@@ -569,7 +569,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
     del est, epoch, sync, close
     torch.cuda.empty_cache()
     # ---- end to end through the public API: host buffers in, fitted host arrays out
-    e_epochs = max(1, min(args.steps, 5))
+    e_epochs = max(1, args.steps)                     # the same number of steps as the device-timed region
     est2 = S.SparseFactorizationMachineClassifier(max_iter=e_epochs, **kw)
     torch.cuda.synchronize()
     if group is not None:
@@ -596,6 +596,73 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
         result["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": 1, "kind": "port", "sample": desc}
     result["config"] = psgd_config(args, world, batch_mode)
     return result
+
+
+def run_predict_workload(args, rank, world, local):
+    """Batch prediction (base.py:52-100 -> kernels.poly_predict) of a C5-shaped model, samples sharded over the ranks,
+    no collective on the compute path: device-timed sp_predict on resident shards + e2e decision_function(X_host)."""
+    import torch
+    import sparsepoly_b200 as S
+    from sparsepoly_b200 import _lib, solvers
+    from sparsepoly_b200.dataset import DeviceDataset
+    wl = WORKLOADS["psgd"]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load().sp_set_device(local)
+    global ROWS_OVERRIDE
+    ROWS_OVERRIDE = min(args.rows_per_gpu or 2_000_000, 2_000_000)
+    X, _ = make_problem("psgd", args.scale, rank)
+    ROWS_OVERRIDE = args.rows_per_gpu
+    n, d = X.shape
+    k, r = wl["k"], wl["r"]
+    rng = np.random.RandomState(0)
+    est = S.SparseFactorizationMachineClassifier(**wl["kw"])
+    est.P_ = 0.01 * rng.randn(1, k, d) * (rng.rand(1, k, d) < 0.1)        # a sparse fitted model (10 % nonzero)
+    est.w_ = 0.01 * rng.randn(d)
+    est.lams_ = np.ones(k)
+    ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=False)
+    P_dk = solvers.transpose(torch.from_numpy(est.P_[0]).to(dev))
+    w = torch.from_numpy(est.w_).to(dev)
+    lams = torch.ones(k, dtype=torch.float64, device=dev)
+    out = torch.zeros(n, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        solvers.poly_predict(ds, P_dk, lams, 2, w=w, out=out)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    reps = 10
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        solvers.poly_predict(ds, P_dk, lams, 2, w=w, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    t0 = time.perf_counter()
+    pred = est.decision_function(X)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, dt = float(t[0].item()), float(t[1].item())
+    per_sample = r * 12 + r * k * 8 + r * 8 + 8                     # SURVEY.md 8d: 10.8 KB / sample
+    peak, peak_src = measured_peak()
+    value = reps * n * world / (ms / 1e3)
+    gbs = per_sample * reps * n / (ms / 1e3) / 1e9
+    return {"metric": "predict_samples_per_second", "value": value, "unit": "samples/s", "n_gpus": world, "steps": reps,
+            "warmup": 3, "ms_per_step": ms / reps, "higher_is_better": True, "scaling": "weak", "dtype": "f64",
+            "data": "synthetic",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "rows_all_kernel (rows.cu)",
+                         "algorithmic_bytes_per_launch": per_sample * n},
+            "e2e": {"value": n * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(X.nnz * 12 + (n + 1) * 4 + est.P_.nbytes + est.w_.nbytes),
+                    "d2h_bytes_per_step": int(pred.nbytes),
+                    "note": "decision_function(X_host) wall clock per rank: H2D of the CSR shard and the model, kernel, D2H of the scores"},
+            "gpu_launches": reps + 3,
+            "config": {"workload": "C5-shaped batch prediction: degree=2, k=32, d=1M, 39 nnz/row, model 10 % nonzero",
+                       "rows_per_gpu": n, "parallelism": "single GPU" if world == 1 else f"{world} ranks: samples sharded, model replicated, no collective"}}
 
 
 def run_reference(args, rank, world):
@@ -699,6 +766,7 @@ def main():
             r2.update(metric=metric_name("psgd"), unit="samples/s", n_gpus=world, steps=a2.steps, warmup=a2.warmup,
                       higher_is_better=True, scaling="strong", dtype="f64", data="synthetic")
             also.append(r2)
+        also.append(run_predict_workload(args, rank, world, local))
     if rank == 0:
         line = {"metric": metric_name(name), "value": res.pop("value"),
                 "unit": "samples/s" if name == "psgd" else "s/epoch", "n_gpus": world, "steps": args.steps,

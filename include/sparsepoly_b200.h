@@ -248,7 +248,7 @@ typedef struct sp_psgd_plan {
     const int64_t *mb_eptr_host;   /* [M+1] first nonzero of every minibatch */
     const int64_t *mb_uptr_host;   /* [M+1] first column (distinct feature) of every minibatch */
     const int64_t *mb_sgptr_host;  /* [M+1] first entry of sg_* */
-    const int64_t *mb_shptr_host;  /* [M+1] first entry of short_u */
+    const int64_t *mb_shptr_host;  /* [M+1] first entry of sc_ptr / sc_u / sc_feat */
     const int64_t *mb_lcptr_host;  /* [M+1] first entry of lc_u / lc_e0 */
     const int64_t *mb_mlptr_host;  /* [M+1] first entry of ml_u / ml_c0 */
     const int32_t *e_pos;          /* [E] position of the sample inside its minibatch */
@@ -257,8 +257,14 @@ typedef struct sp_psgd_plan {
     const int64_t *u_ptr;          /* [U+1] first nonzero of every column */
     const int32_t *sg_u, *sg_feat, *sg_pos; /* [N1] columns of ONE nonzero: column, feature, position of the sample ... */
     const double *sg_x;            /* [N1] ... and value */
-    const int32_t *short_u;        /* [Ns] columns of 2..short_max nonzeros */
+    const int64_t *sc_ptr;         /* [Ns+1] columns of 2..short_max nonzeros: offsets into sc_pos / sc_x (their nonzeros,
+                                      samples ascending, stored compactly) ... */
+    const int32_t *sc_u, *sc_feat; /* [Ns] ... column and feature */
+    const int32_t *sc_pos;         /* [Es] position of the sample inside its minibatch */
+    const double *sc_x;            /* [Es] value */
     const int32_t *lc_u;           /* [Nc] chunks of the longer columns: column ... */
+    const int32_t *lc_feat;        /* [Nc] ... its feature ... */
+    const int32_t *lc_cnt;         /* [Nc] ... nonzeros in the chunk, | 0x40000000 when it is the column's only chunk ... */
     const int64_t *lc_e0;          /* [Nc] ... and first nonzero; a chunk ends after `chunk` nonzeros or with its column */
     const int32_t *ml_u;           /* [Nm] columns of more than one chunk ... */
     const int32_t *ml_c0;          /* [Nm] ... and the index of their first chunk inside the minibatch's chunk list */

@@ -34,7 +34,7 @@ t0 = time.time()
 plan = PsgdPlan(ds.csr, idx, d, batch)
 torch.cuda.synchronize()
 print(f"plan {time.time()-t0:.2f}s M={plan.n_minibatches} cols/mb={plan.n_cols/plan.n_minibatches:.0f} "
-      f"single/mb={len(plan.sg_u)/plan.n_minibatches:.0f} short/mb={len(plan.short_u)/plan.n_minibatches:.0f} chunks/mb={len(plan.lc_u)/plan.n_minibatches:.0f} "
+      f"single/mb={len(plan.sg_u)/plan.n_minibatches:.0f} short/mb={len(plan.sc_u)/plan.n_minibatches:.0f} chunks/mb={len(plan.lc_u)/plan.n_minibatches:.0f} "
       f"multi/mb={len(plan.ml_u)/plan.n_minibatches:.0f} bytes={plan.nbytes()/1e9:.2f}GB", flush=True)
 lams = torch.ones(k, dtype=torch.float64, device=dev)
 ctx = PsgdContext(plan, 1, k, 2, reg, "logistic", True, lams)

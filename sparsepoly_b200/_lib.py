@@ -52,7 +52,8 @@ class SpPsgdPlan(C.Structure):
                 ("mb_eptr_host", _vp), ("mb_uptr_host", _vp), ("mb_sgptr_host", _vp), ("mb_shptr_host", _vp),
                 ("mb_lcptr_host", _vp), ("mb_mlptr_host", _vp),
                 ("e_pos", _vp), ("e_x", _vp), ("u_feat", _vp), ("u_ptr", _vp),
-                ("sg_u", _vp), ("sg_feat", _vp), ("sg_pos", _vp), ("sg_x", _vp), ("short_u", _vp), ("lc_u", _vp),
+                ("sg_u", _vp), ("sg_feat", _vp), ("sg_pos", _vp), ("sg_x", _vp),
+                ("sc_ptr", _vp), ("sc_u", _vp), ("sc_feat", _vp), ("sc_pos", _vp), ("sc_x", _vp), ("lc_u", _vp), ("lc_feat", _vp), ("lc_cnt", _vp),
                 ("lc_e0", _vp), ("ml_u", _vp), ("ml_c0", _vp),
                 ("max_chunks", C.c_int64), ("max_cols", C.c_int64),
                 ("csr_slot", _vp), ("mb_owner_start_host", _vp), ("mb_optr_host", _vp), ("own_q", _vp), ("own_src", _vp)]

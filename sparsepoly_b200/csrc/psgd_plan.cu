@@ -118,9 +118,23 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
         }
     }
     const bool lin = a.fit_linear != 0;
-    for (int b = a.b0 + blockIdx.x * gpb + threadIdx.x / G; b < a.b1; b += n_groups) {
-        const int i = a.idx[b];
-        const int st = a.indptr[i], en = a.indptr[i + 1];
+    // software pipeline over the group's samples: (row bounds) of sample b + 2 n_groups and (first block of column
+    // ids / values) of sample b + n_groups are in flight while sample b is processed
+    const int bfirst = a.b0 + blockIdx.x * gpb + threadIdx.x / G;
+    int i_c = 0, st_c = 0, en_c = 0, i_n = 0, st_n = 0, en_n = 0, i_nn = 0, st_nn = 0, en_nn = 0;
+    int jl_c = 0, jl_n = 0;
+    double xl_c = 0.0, xl_n = 0.0;
+    if (bfirst < a.b1) { i_c = a.idx[bfirst]; st_c = a.indptr[i_c]; en_c = a.indptr[i_c + 1]; }
+    if (bfirst + n_groups < a.b1) { i_n = a.idx[bfirst + n_groups]; st_n = a.indptr[i_n]; en_n = a.indptr[i_n + 1]; }
+    if (st_c + lane < en_c) { jl_c = a.colidx[st_c + lane]; xl_c = a.data[st_c + lane]; }
+    for (int b = bfirst; b < a.b1; b += n_groups) {
+        const int i = i_c;
+        const int st = st_c, en = en_c;
+        // stage loads for the following samples
+        i_nn = 0; st_nn = 0; en_nn = 0;
+        if (b + 2 * n_groups < a.b1) { i_nn = a.idx[b + 2 * n_groups]; st_nn = a.indptr[i_nn]; en_nn = a.indptr[i_nn + 1]; }
+        jl_n = 0; xl_n = 0.0;
+        if (st_n + lane < en_n) { jl_n = a.colidx[st_n + lane]; xl_n = a.data[st_n + lane]; }
         double A[KCH][NORD][DEG + 1];
 #pragma unroll
         for (int c = 0; c < KCH; c++)
@@ -131,9 +145,8 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
                 for (int t = 1; t <= DEG; t++) A[c][o][t] = 0.0;
             }
         double ypred = 0.0;                                   // _pred, psgd.py:47-57
-        int jl = 0;
-        double xl = 0.0;
-        if (st + lane < en) { jl = a.colidx[st + lane]; xl = a.data[st + lane]; }
+        int jl = jl_c;
+        double xl = xl_c;
         for (int base = st; base < en; base += G) {
             int jn = 0;                                       // the next block of (column, value): in flight during this one
             double xn = 0.0;
@@ -194,6 +207,8 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
             a.bufdL[b - a.b0] = sp_dloss_rt(a.loss, ypred, yi);
             a.sloss[b] = sp_loss_rt(a.loss, ypred, yi);        // psgd.py:155 (summed in fixed order at epoch end)
         }
+        i_c = i_n; st_c = st_n; en_c = en_n; jl_c = jl_n; xl_c = xl_n;
+        i_n = i_nn; st_n = st_nn; en_n = en_nn;
     }
 }
 
@@ -203,6 +218,7 @@ enum { MODE_APPLY = 0, MODE_PUSH = 1 };
 struct StepArgs {                        // psgd._update_params for one row (psgd.py:94-117) in the lazy frame
     double cP, denP, CnP;                // eta_P / batch, 1 + eta_P*beta, C * denP
     double cw, denw, Cnw;
+    double rP, rw;                       // 1 / denP, 1 / denw (host, correctly rounded)
     double invC, invCw;                  // frame the rows are read in
     int fit_linear;
 };
@@ -217,10 +233,12 @@ struct ColsArgs {
     const int32_t *sg_u, *sg_feat, *sg_pos;   // minibatch-relative lists: columns of ONE nonzero (column, feature, position,
     const double *sg_x;                       // value) ...
     int n_single;
-    const int32_t *short_u;              // ... short columns (2..SP_PSGD_SHORT nonzeros) ...
+    const int64_t *sc_ptr;               // ... short columns (2..SP_PSGD_SHORT nonzeros): offsets into the compact
+    const int32_t *sc_u, *sc_feat, *sc_pos;   // nonzero arrays sc_pos / sc_x, column, feature ...
+    const double *sc_x;
     int n_short;
-    const int32_t *lc_u;                 // ... chunks of the long columns (column, first nonzero) ...
-    const int64_t *lc_e0;
+    const int32_t *lc_u, *lc_feat, *lc_cnt;   // ... chunks of the long columns (column, feature, nonzeros | 2^30 when
+    const int64_t *lc_e0;                     // the column has one chunk only, first nonzero) ...
     int n_chunks;
     const int32_t *ml_u, *ml_c0;         // ... and the long columns of several chunks (column, its first chunk)
     int n_multi;
@@ -237,11 +255,19 @@ struct ColsArgs {
     double *inbox_w[SP_MAX_RANKS];       // [cap]
 };
 
+// v / den for a divisor that is the same for the whole minibatch: q = RN(v r), one fused residual correction
+// (Markstein): the correctly rounded quotient, in 3 instructions instead of the ~35 of a generic fp64 division
+__device__ __forceinline__ double div_const(double v, double den, double r) {
+    const double q = v * r;
+    const double rem = fma(-q, den, v);
+    return fma(rem, r, q);
+}
+
 // psgd._update_params on one row: P = (P - (eta/b) g) / (1 + eta beta), written back in the frame (CnP, T)
 template <int NORD, int G, int KCH>
 __device__ __forceinline__ void apply_row(const StepArgs &s, double *P, double *w, int d, int k, int j, int lane,
                                           const double (&g)[KCH][NORD], double gw, const double (&pold)[KCH][NORD],
-                                          const double (&thr)[KCH][NORD]) {
+                                          double wraw, const double (&thr)[KCH][NORD]) {
     const size_t dk = (size_t)d * k;
 #pragma unroll
     for (int c = 0; c < KCH; c++) {
@@ -251,16 +277,16 @@ __device__ __forceinline__ void apply_row(const StepArgs &s, double *P, double *
             for (int o = 0; o < NORD; o++) {
                 double gg = g[c][o] * s.cP;                 // grad *= eta / batch          psgd.py:113
                 double v = pold[c][o] - gg;                 // P -= grad                    psgd.py:114
-                v = v / s.denP;                             // P /= 1 + eta*beta            psgd.py:115
+                v = div_const(v, s.denP, s.rP);             // P /= 1 + eta*beta            psgd.py:115
                 P[o * dk + (size_t)j * k + sidx] = to_raw(v, thr[c][o], s.CnP);
             }
         }
     }
     if (s.fit_linear && lane == 0) {                        // psgd.py:109-112
-        const double wold = w[j] * s.invCw;
+        const double wold = wraw * s.invCw;                   // (raw value gathered together with the row)
         double gg = gw * s.cw;
         double v = wold - gg;
-        v = v / s.denw;
+        v = div_const(v, s.denw, s.rw);
         w[j] = v * s.Cnw;
     }
 }
@@ -268,10 +294,11 @@ __device__ __forceinline__ void apply_row(const StepArgs &s, double *P, double *
 // a column's gradient row is complete: apply the step (single rank) or push it to the owner's inbox
 template <int NORD, int G, int KCH, int MODE>
 __device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int ucol, int feat, const double (&g)[KCH][NORD],
-                                              double gw, const double (&pold)[KCH][NORD], const double (&thr)[KCH][NORD]) {
+                                              double gw, const double (&pold)[KCH][NORD], double wraw,
+                                              const double (&thr)[KCH][NORD]) {
     const int k = a.k;
     if (MODE == MODE_APPLY) {
-        apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d, k, feat, lane, g, gw, pold, thr);
+        apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d, k, feat, lane, g, gw, pold, wraw, thr);
     } else {
         const int su = (int)(ucol - a.u_base);
         const int owner = feat % a.world;
@@ -289,22 +316,30 @@ __device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int u
     }
 }
 
-// true (pre-update) values of row `feat` / staged slot `su`
+// RAW gather of row `feat` (single rank) / of the staged true values of slot `su` (sharded); row_values() turns
+// the raw values into the true (pre-update) ones afterwards, so that the gathers of a batch are issued back to back
 template <int NORD, int G, int KCH, int MODE>
 __device__ __forceinline__ void load_row(const ColsArgs &a, int lane, int feat, long long su, double (&p)[KCH][NORD],
-                                         const double (&thr)[KCH][NORD]) {
+                                         double &wraw, const double (&thr)[KCH][NORD]) {
     const int k = a.k;
     const size_t dk = (size_t)a.d * k;
+    wraw = (MODE == MODE_APPLY && a.s.fit_linear) ? a.w[feat] : 0.0;     // the row's w entry travels with it
 #pragma unroll
     for (int c = 0; c < KCH; c++) {
-        const int sidx = lane + G * c;
+        const int sidx = (lane + G * c) < k ? lane + G * c : 0;          // (lanes without a component: a valid dummy element)
 #pragma unroll
-        for (int o = 0; o < NORD; o++) {
-            if (sidx < k) {
-                if (MODE == MODE_APPLY) p[c][o] = st_true(a.P[o * dk + (size_t)feat * k + sidx], thr[c][o], a.s.invC);
-                else p[c][o] = a.stage[((size_t)su * NORD + o) * k + sidx];
-            } else p[c][o] = 0.0;
-        }
+        for (int o = 0; o < NORD; o++)
+            p[c][o] = (MODE == MODE_APPLY) ? a.P[o * dk + (size_t)feat * k + sidx] : a.stage[((size_t)su * NORD + o) * k + sidx];
+    }
+    (void)thr;
+}
+template <int NORD, int G, int KCH, int MODE>
+__device__ __forceinline__ void row_values(const ColsArgs &a, double (&p)[KCH][NORD], const double (&thr)[KCH][NORD]) {
+    if (MODE == MODE_APPLY) {
+#pragma unroll
+        for (int c = 0; c < KCH; c++)
+#pragma unroll
+            for (int o = 0; o < NORD; o++) p[c][o] = st_true(p[c][o], thr[c][o], a.s.invC);
     }
 }
 
@@ -330,8 +365,8 @@ __device__ __forceinline__ void add_term(double (&g)[KCH][NORD], double &gw, dou
 template <int DEG, int NORD, int G, int KCH, int MODE>
 __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const ColsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
-    constexpr int UBR = 16 / (KCH * (AR + NORD));
-    constexpr int UBC = UBR >= 8 ? 8 : (UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1));
+    constexpr int UBR = 8 / (KCH * (AR + NORD));                // (register budget: no spills at 3 blocks / SM)
+    constexpr int UBC = UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1);
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
@@ -355,7 +390,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const C
         }
         const int ncol = (a.n_single - qb < G) ? a.n_single - qb : G;
         for (int c0 = 0; c0 < ncol; c0 += UBC) {
-            double pold[UBC][KCH][NORD], av[UBC][KCH][AR], dl[UBC], xv[UBC];
+            double pold[UBC][KCH][NORD], av[UBC][KCH][AR], dl[UBC], xv[UBC], wraw[UBC];
             int uu[UBC], ff[UBC];
 #pragma unroll
             for (int t = 0; t < UBC; t++) {                     // gathers of UBC columns in flight
@@ -364,7 +399,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const C
                 ff[t] = __shfl_sync(gmask, feat_l, cc, G);
                 const int pos = __shfl_sync(gmask, pos_l, cc, G);
                 xv[t] = __shfl_sync(gmask, x_l, cc, G);
-                load_row<NORD, G, KCH, MODE>(a, lane, ff[t], uu[t] - a.u_base, pold[t], thr);
+                load_row<NORD, G, KCH, MODE>(a, lane, ff[t], uu[t] - a.u_base, pold[t], wraw[t], thr);
                 dl[t] = a.bufdL[pos];
 #pragma unroll
                 for (int c = 0; c < KCH; c++)
@@ -380,109 +415,90 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const C
                 for (int c = 0; c < KCH; c++)
 #pragma unroll
                     for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+                row_values<NORD, G, KCH, MODE>(a, pold[t], thr);
                 add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold[t], lam);
-                finish_column<NORD, G, KCH, MODE>(a, lane, uu[t], ff[t], g, gw, pold[t], thr);
+                finish_column<NORD, G, KCH, MODE>(a, lane, uu[t], ff[t], g, gw, pold[t], wraw[t], thr);
             }
         }
     }
 }
 
-// ---- short columns (2..SP_PSGD_SHORT nonzeros; a quarter of a Criteo-shaped minibatch's columns; the plan keeps
-// single-nonzero columns apart).  A group of G lanes takes G columns at a time: lane l fetches column l's descriptor and first
-// nonzero (one dependent chain for G columns instead of one per column), then the columns are finished UBC at a
-// time with all their row gathers in flight.  Terms are added in sample order (the reference's).
+// ---- short columns (2..SP_PSGD_SHORT nonzeros; a quarter of a Criteo-shaped minibatch's columns).  The plan keeps
+// their nonzeros in compact arrays (sc_ptr / sc_pos / sc_x), so a column's work is three dependent gathers:
+// descriptor -> its nonzeros -> their table rows.  A group of lanes walks its columns with the three stages of
+// three consecutive columns in flight (software pipeline): one memory round trip per column instead of three.
+// Terms are added in sample order (the reference's).
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_short_kernel(const ColsArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const ColsArgs a) {
     constexpr int AR = ARows<DEG, NORD>::value;
     constexpr int SH = SP_PSGD_SHORT;
     static_assert(SH <= 8 && G >= 8, "a group's lanes hold a column's nonzeros");
-    constexpr int UBR = 8 / (KCH * (AR + NORD));
-    constexpr int UBC = UBR > 4 ? 4 : (UBR < 1 ? 1 : UBR);      // columns finished together
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
+    const int ngroups = gridDim.x * gpb;
     const int k = a.k;
     double lam[KCH], thr[KCH][NORD];
+    const double *Al[KCH];
 #pragma unroll
     for (int c = 0; c < KCH; c++) {
         const int s = lane + G * c;
         lam[c] = s < k ? a.lams[s] : 0.0;
+        Al[c] = a.bufA + (s < k ? s : 0);
 #pragma unroll
         for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
     }
-    for (int qb = (blockIdx.x * gpb + threadIdx.x / G) * G; qb < a.n_short; qb += gridDim.x * gpb * G) {
-        // ---- descriptors of G columns, one per lane
-        int u_l = 0, feat_l = 0, len_l = 0, ep_l = 0;
-        long long e0_l = 0;
-        double ex_l = 0.0;
-        if (qb + lane < a.n_short) {
-            u_l = a.short_u[qb + lane];
-            e0_l = a.u_ptr[u_l];
-            len_l = (int)(a.u_ptr[u_l + 1] - e0_l);
-            feat_l = a.u_feat[u_l];
-            ep_l = a.e_pos[e0_l];
-            ex_l = a.e_x[e0_l];
-        }
-        const int ncol = (a.n_short - qb < G) ? a.n_short - qb : G;
-        for (int c0 = 0; c0 < ncol; c0 += UBC) {
-            double pold[UBC][KCH][NORD], av[UBC][KCH][AR], dl[UBC], xv[UBC];
-            int uu[UBC], ff[UBC], ln[UBC];
-            long long ee[UBC];
+    const size_t astride = (size_t)AR * k;
+    const int q0 = blockIdx.x * gpb + threadIdx.x / G;
+    // stage 1 (descriptor) of column q, stage 2 (nonzeros) of column q - ngroups, stage 3 (rows) of q - 2 ngroups
+    long long p0_1 = 0, p0_2 = 0;
+    int len_1 = 0, u_1 = 0, f_1 = 0, len_2 = 0, u_2 = 0, f_2 = 0, len_3 = 0, u_3 = 0, f_3 = 0;
+    int ep_2 = 0;
+    double ex_2 = 0.0;
+    double pold[KCH][NORD], av[SH][KCH][AR], dl[SH], xv[SH], wraw = 0.0;
+    for (int q = q0; q < a.n_short + 2 * ngroups; q += ngroups) {
+        // ---- stage 3 loads: rows of the column whose nonzeros arrived in the previous iteration
+        len_3 = len_2; u_3 = u_2; f_3 = f_2;
+        if (len_3 > 0) {
+            load_row<NORD, G, KCH, MODE>(a, lane, f_3, u_3 - a.u_base, pold, wraw, thr);
 #pragma unroll
-            for (int t = 0; t < UBC; t++) {                     // gathers of UBC columns in flight
-                const int cc = (c0 + t) & (G - 1);
-                uu[t] = __shfl_sync(gmask, u_l, cc, G);
-                ff[t] = __shfl_sync(gmask, feat_l, cc, G);
-                ln[t] = (c0 + t < ncol) ? __shfl_sync(gmask, len_l, cc, G) : 0;
-                ee[t] = __shfl_sync(gmask, e0_l, cc, G);
-                const int pos = __shfl_sync(gmask, ep_l, cc, G);
-                xv[t] = __shfl_sync(gmask, ex_l, cc, G);
-                if (ln[t] > 0) {
-                    load_row<NORD, G, KCH, MODE>(a, lane, ff[t], uu[t] - a.u_base, pold[t], thr);
+            for (int t = 0; t < SH; t++) {
+                const int pos = __shfl_sync(gmask, ep_2, t, G);       // (nonzeros past the column's end: position 0, x = 0)
+                xv[t] = __shfl_sync(gmask, ex_2, t, G);
+                if (t < len_3) {
                     dl[t] = a.bufdL[pos];
 #pragma unroll
-                    for (int c = 0; c < KCH; c++) {
-                        const int s = lane + G * c;
+                    for (int c = 0; c < KCH; c++)
 #pragma unroll
-                        for (int r = 0; r < AR; r++) av[t][c][r] = s < k ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
-                    }
+                        for (int r = 0; r < AR; r++) av[t][c][r] = Al[c][(size_t)pos * astride + (size_t)r * k];
                 }
             }
+        }
+        // ---- stage 2 loads: nonzeros of the column whose descriptor arrived in the previous iteration
+        len_2 = len_1; u_2 = u_1; f_2 = f_1; p0_2 = p0_1;
+        ep_2 = 0; ex_2 = 0.0;
+        if (lane < len_2) { ep_2 = a.sc_pos[p0_2 + lane]; ex_2 = a.sc_x[p0_2 + lane]; }
+        // ---- stage 1 loads: descriptor of column q
+        len_1 = 0;
+        if (q < a.n_short) {
+            p0_1 = a.sc_ptr[q];
+            len_1 = (int)(a.sc_ptr[q + 1] - p0_1);
+            u_1 = a.sc_u[q];
+            f_1 = a.sc_feat[q];
+        }
+        // ---- finish the stage-3 column
+        if (len_3 > 0) {
+            double g[KCH][NORD];
+            double gw = 0.0;
 #pragma unroll
-            for (int t = 0; t < UBC; t++) {
-                if (ln[t] == 0) continue;
-                double g[KCH][NORD];
-                double gw = 0.0;
+            for (int c = 0; c < KCH; c++)
 #pragma unroll
-                for (int c = 0; c < KCH; c++)
+                for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
+            row_values<NORD, G, KCH, MODE>(a, pold, thr);
 #pragma unroll
-                    for (int o = 0; o < NORD; o++) g[c][o] = 0.0;
-                add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold[t], lam);
-                if (ln[t] > 1) {                                 // 2..SH nonzeros: the rest, gathered together
-                    int ep = 0;
-                    double ex = 0.0;
-                    if (lane < ln[t]) { ep = a.e_pos[ee[t] + lane]; ex = a.e_x[ee[t] + lane]; }
-                    double av2[SH - 1][KCH][AR], dl2[SH - 1], x2[SH - 1];
-#pragma unroll
-                    for (int q = 1; q < SH; q++) {
-                        const int pos = __shfl_sync(gmask, ep, q, G);
-                        x2[q - 1] = __shfl_sync(gmask, ex, q, G);
-                        const bool live = q < ln[t];
-                        dl2[q - 1] = live ? a.bufdL[pos] : 0.0;
-#pragma unroll
-                        for (int c = 0; c < KCH; c++) {
-                            const int s = lane + G * c;
-#pragma unroll
-                            for (int r = 0; r < AR; r++)
-                                av2[q - 1][c][r] = (live && s < k) ? a.bufA[((size_t)pos * AR + r) * k + s] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 1; q < SH; q++)
-                        if (q < ln[t]) add_term<DEG, NORD, KCH, AR>(g, gw, x2[q - 1], dl2[q - 1], av2[q - 1], pold[t], lam);
-                }
-                finish_column<NORD, G, KCH, MODE>(a, lane, uu[t], ff[t], g, gw, pold[t], thr);
-            }
+            for (int t = 0; t < SH; t++)
+                if (t < len_3) add_term<DEG, NORD, KCH, AR>(g, gw, xv[t], dl[t], av[t], pold, lam);
+            finish_column<NORD, G, KCH, MODE>(a, lane, u_3, f_3, g, gw, pold, wraw, thr);
         }
     }
 }
@@ -506,10 +522,10 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
     const int k = a.k;
     const int u = a.lc_u[chunk];
     const long long ce0 = a.lc_e0[chunk];
-    const long long cend = a.u_ptr[u + 1];
-    const int cnt = (int)((cend - ce0 < CH) ? cend - ce0 : CH);
-    const bool single = (cend - a.u_ptr[u]) <= CH;
-    const int feat = a.u_feat[u];
+    const int cdesc = a.lc_cnt[chunk];
+    const int cnt = cdesc & 0x3fffffff;
+    const bool single = (cdesc & 0x40000000) != 0;
+    const int feat = a.lc_feat[chunk];
     int ep[SETS];
     double ex[SETS];
 #pragma unroll
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
         if (q < cnt) { ep[sidx] = a.e_pos[ce0 + q]; ex[sidx] = a.e_x[ce0 + q]; }
     }
     double lam[KCH], thr[KCH][NORD], pold[KCH][NORD], g[KCH][NORD];
-    double gw = 0.0;
+    double gw = 0.0, wraw = 0.0;
 #pragma unroll
     for (int c = 0; c < KCH; c++) {
         const int s = lane + G * c;
@@ -527,7 +543,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
 #pragma unroll
         for (int o = 0; o < NORD; o++) { thr[c][o] = s < k ? a.thr[o * k + s] : 0.0; g[c][o] = 0.0; }
     }
-    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
+    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, wraw, thr);
     // nonzeros past the chunk's end carry (position 0, x = 0): every one of their terms is a product with x, so the
     // gathers below need no predicate; lanes that own no component read a valid dummy address and are not stored
     const double *Al[KCH];
@@ -553,6 +569,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
         for (int t = 0; t < UB; t++) add_term<DEG, NORD, KCH, AR>(g, gw, xv[buf][t], dl[buf][t], av[buf][t], pold, lam);
     };
     load_batch(0, 0);
+    row_values<NORD, G, KCH, MODE>(a, pold, thr);
 #pragma unroll
     for (int b = 0; b < NB; b += 2) {
         if (b + 1 < NB && (b + 1) * UB < cnt) load_batch(1, b + 1);
@@ -563,7 +580,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
         if ((b + 2) * UB >= cnt) break;
     }
     if (single) {
-        finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
+        finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, wraw, thr);
     } else {
 #pragma unroll
         for (int c = 0; c < KCH; c++) {
@@ -623,7 +640,7 @@ __global__ void __launch_bounds__(CB_THREADS) psgd_cols_combine_kernel(const Col
             for (int o = 0; o < NORD; o++) g[c][o] += cb_sh[w * ROW + (c * NORD + o) * G + lane];
         gw += cb_sh[w * ROW + ROW - 1];
     }
-    double thr[KCH][NORD], pold[KCH][NORD];
+    double thr[KCH][NORD], pold[KCH][NORD], wraw = 0.0;
 #pragma unroll
     for (int c = 0; c < KCH; c++)
 #pragma unroll
@@ -632,8 +649,9 @@ __global__ void __launch_bounds__(CB_THREADS) psgd_cols_combine_kernel(const Col
             thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
         }
     const int feat = a.u_feat[u];
-    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, thr);
-    finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, thr);
+    load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, wraw, thr);
+    row_values<NORD, G, KCH, MODE>(a, pold, thr);
+    finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, wraw, thr);
 }
 
 // ------------------------------------------------------------------------------------ sharded: pull / owner
@@ -686,6 +704,7 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_owner_kernel(const OwnerArgs 
     const int q = a.own_q[r];
     double thr[KCH][NORD], g[KCH][NORD], pold[KCH][NORD];
     double gw = 0.0;
+    const double wraw = a.s.fit_linear ? a.w[q] : 0.0;
 #pragma unroll
     for (int c = 0; c < KCH; c++)
 #pragma unroll
@@ -708,7 +727,7 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_owner_kernel(const OwnerArgs 
         }
         gw += a.inbox_w[src][at];
     }
-    apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d_own, k, q, lane, g, gw, pold, thr);
+    apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d_own, k, q, lane, g, gw, pold, wraw, thr);
 }
 
 // ------------------------------------------------------------------------------------ cross-rank flags
@@ -1225,8 +1244,11 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
     ca.u_base = mb.u0;
     ca.sg_u = pl->sg_u + mb.sg0; ca.sg_feat = pl->sg_feat + mb.sg0; ca.sg_pos = pl->sg_pos + mb.sg0; ca.sg_x = pl->sg_x + mb.sg0;
     ca.n_single = (int)(mb.sg1 - mb.sg0);
-    ca.short_u = pl->short_u + mb.sh0; ca.n_short = (int)(mb.sh1 - mb.sh0);
+    ca.sc_ptr = pl->sc_ptr + mb.sh0; ca.sc_u = pl->sc_u + mb.sh0; ca.sc_feat = pl->sc_feat + mb.sh0;
+    ca.sc_pos = pl->sc_pos; ca.sc_x = pl->sc_x;
+    ca.n_short = (int)(mb.sh1 - mb.sh0);
     ca.lc_u = pl->lc_u + mb.lc0; ca.lc_e0 = pl->lc_e0 + mb.lc0; ca.n_chunks = (int)(mb.lc1 - mb.lc0);
+    ca.lc_feat = pl->lc_feat + mb.lc0; ca.lc_cnt = pl->lc_cnt + mb.lc0;
     ca.ml_u = pl->ml_u + mb.ml0; ca.ml_c0 = pl->ml_c0 + mb.ml0; ca.n_multi = (int)(mb.ml1 - mb.ml0);
     ca.bufA = cx->bufA; ca.bufdL = cx->bufdL;
     ca.lams = cx->lams; ca.thr = cx->thr;
@@ -1269,8 +1291,8 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
         SP_LAUNCH_CHECK("psgd_cols_single_kernel");
     }
     if (ca.n_short > 0) {
-        int sb = grid_for((ca.n_short + G - 1) / G, G);
-        if (sb > 148 * 12) sb = 148 * 12;
+        int sb = grid_for((ca.n_short + 3) / 4, G);               // ~4 columns per group: enough to fill the pipeline
+        if (sb > 148 * 3) sb = 148 * 3;
         if (sharded) psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
         else psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
         SP_LAUNCH_CHECK("psgd_cols_short_kernel");
@@ -1419,6 +1441,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
         sa.cP = eta_P / (double)b_glob; sa.denP = 1.0 + eta_P * beta; sa.CnP = cx->C * sa.denP;
         sa.cw = eta_w / (double)b_glob; sa.denw = 1.0 + eta_w * alpha; sa.Cnw = cx->fit_linear ? cx->Cw * sa.denw : cx->Cw;
         sa.invC = 1.0 / cx->C; sa.invCw = 1.0 / cx->Cw;
+        sa.rP = 1.0 / sa.denP; sa.rw = 1.0 / sa.denw;
         sa.fit_linear = cx->fit_linear;
         const double strength = gamma * eta_P / (1.0 + eta_P * beta);                     // psgd.py:122
         if (sharded) {

@@ -83,8 +83,9 @@ class PsgdPlan:
         self.e_pos = torch.empty(E, dtype=torch.int32, device=dev)
         self.e_x = torch.empty(E, dtype=torch.float64, device=dev)
         self.csr_slot = torch.zeros(nnz_total, dtype=torch.int32, device=dev) if G > 1 else None
-        u_feat, u_ptr, short_u, lc_u, lc_e0, ml_u, ml_c0 = [], [], [], [], [], [], []
+        u_feat, u_ptr, lc_u, lc_e0, lc_feat, lc_cnt, ml_u, ml_c0 = [], [], [], [], [], [], [], []
         sg_u, sg_feat, sg_pos, sg_x = [], [], [], []
+        sc_len, sc_u, sc_feat, sc_pos, sc_x = [], [], [], [], []
         mb_ucnt, mb_sgcnt, mb_shcnt, mb_lccnt, mb_mlcnt, owner_cnt = [], [], [], [], [], []
         u_off = 0
         m0 = 0
@@ -158,8 +159,18 @@ class PsgdPlan:
             sg_pos.append(self.e_pos[e0:e1][ustart[sg_idx]])
             sg_x.append(self.e_x[e0:e1][ustart[sg_idx]])
             mb_sgcnt.append(torch.bincount(umb[sg_idx], minlength=Mg).cpu().numpy())
-            sh_idx = torch.nonzero(is_short & (ulen > 1)).squeeze(1)
-            short_u.append((sh_idx + u_off).to(torch.int32))
+            sh_idx = torch.nonzero(is_short & (ulen > 1)).squeeze(1)              # 2..SHORT nonzeros: compact copies of them
+            sh_len = ulen[sh_idx]
+            nse = int(sh_len.sum()) if sh_idx.numel() else 0
+            sc_len.append(sh_len)
+            sc_u.append((sh_idx + u_off).to(torch.int32))
+            sc_feat.append(u_feat[-1][sh_idx])
+            if nse:
+                col = torch.repeat_interleave(torch.arange(sh_idx.numel(), dtype=i64, device=dev), sh_len, output_size=nse)
+                within = torch.arange(nse, dtype=i64, device=dev) - (torch.cumsum(sh_len, 0) - sh_len)[col]
+                src_e = ustart[sh_idx][col] + within
+                sc_pos.append(self.e_pos[e0:e1][src_e])
+                sc_x.append(self.e_x[e0:e1][src_e])
             mb_shcnt.append(torch.bincount(umb[sh_idx], minlength=Mg).cpu().numpy())
             lg_idx = torch.nonzero(~is_short).squeeze(1)
             npieces = (ulen[lg_idx] + CHUNK - 1) // CHUNK
@@ -175,6 +186,10 @@ class PsgdPlan:
                 piece = torch.arange(ntc, dtype=i64, device=dev) - first_chunk[col_of_chunk]
                 lc_u.append((lg_idx[col_of_chunk] + u_off).to(torch.int32))
                 lc_e0.append(ustart[lg_idx[col_of_chunk]] + piece * CHUNK + e0)
+                lc_feat.append(u_feat[-1][lg_idx[col_of_chunk]])
+                cn = torch.clamp(ulen[lg_idx[col_of_chunk]] - piece * CHUNK, max=CHUNK)
+                cn = cn + (npieces[col_of_chunk] == 1).to(i64) * (1 << 30)           # the column's only chunk
+                lc_cnt.append(cn.to(torch.int32))
             multi = npieces > 1
             ml_idx = lg_idx[multi]
             ml_u.append((ml_idx + u_off).to(torch.int32))
@@ -188,9 +203,14 @@ class PsgdPlan:
         self.u_ptr = torch.cat([cat(u_ptr, i64), torch.tensor([E], dtype=i64, device=dev)])
         self.sg_u, self.sg_feat, self.sg_pos = cat(sg_u, torch.int32), cat(sg_feat, torch.int32), cat(sg_pos, torch.int32)
         self.sg_x = cat(sg_x, torch.float64)
-        self.short_u = cat(short_u, torch.int32)
+        self.sc_u, self.sc_feat = cat(sc_u, torch.int32), cat(sc_feat, torch.int32)
+        self.sc_pos, self.sc_x = cat(sc_pos, torch.int32), cat(sc_x, torch.float64)
+        lens_all = cat(sc_len, i64)
+        self.sc_ptr = torch.zeros(lens_all.numel() + 1, dtype=i64, device=dev)
+        self.sc_ptr[1:] = torch.cumsum(lens_all, 0)
         self.lc_u = cat(lc_u, torch.int32)
         self.lc_e0 = cat(lc_e0, i64)
+        self.lc_feat, self.lc_cnt = cat(lc_feat, torch.int32), cat(lc_cnt, torch.int32)
         self.ml_u = cat(ml_u, torch.int32)
         self.ml_c0 = cat(ml_c0, torch.int32)
         acc = lambda parts: np.concatenate([[0], np.cumsum(np.concatenate(parts) if parts else np.zeros(0, np.int64))]).astype(np.int64)  # noqa: E731
@@ -289,9 +309,12 @@ class PsgdPlan:
         s.mb_sgptr_host = hp(self.mb_sgptr)
         s.mb_shptr_host, s.mb_lcptr_host, s.mb_mlptr_host = hp(self.mb_shptr), hp(self.mb_lcptr), hp(self.mb_mlptr)
         s.sg_u, s.sg_feat, s.sg_pos, s.sg_x = (t.data_ptr() for t in (self.sg_u, self.sg_feat, self.sg_pos, self.sg_x))
+        s.sc_ptr, s.sc_u, s.sc_feat = self.sc_ptr.data_ptr(), self.sc_u.data_ptr(), self.sc_feat.data_ptr()
+        s.sc_pos, s.sc_x = self.sc_pos.data_ptr(), self.sc_x.data_ptr()
         s.e_pos, s.e_x = self.e_pos.data_ptr(), self.e_x.data_ptr()
         s.u_feat, s.u_ptr = self.u_feat.data_ptr(), self.u_ptr.data_ptr()
-        s.short_u, s.lc_u, s.lc_e0 = self.short_u.data_ptr(), self.lc_u.data_ptr(), self.lc_e0.data_ptr()
+        s.lc_u, s.lc_e0 = self.lc_u.data_ptr(), self.lc_e0.data_ptr()
+        s.lc_feat, s.lc_cnt = self.lc_feat.data_ptr(), self.lc_cnt.data_ptr()
         s.ml_u, s.ml_c0 = self.ml_u.data_ptr(), self.ml_c0.data_ptr()
         s.max_chunks, s.max_cols = self.max_chunks, self.max_cols
         if self.world > 1:
@@ -305,7 +328,7 @@ class PsgdPlan:
         return C.byref(self.struct)
 
     def nbytes(self):
-        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.sg_u, self.sg_feat, self.sg_pos, self.sg_x, self.short_u, self.lc_u, self.lc_e0, self.ml_u, self.ml_c0,
+        ts = [self.e_pos, self.e_x, self.u_feat, self.u_ptr, self.sg_u, self.sg_feat, self.sg_pos, self.sg_x, self.sc_ptr, self.sc_u, self.sc_feat, self.sc_pos, self.sc_x, self.lc_u, self.lc_feat, self.lc_cnt, self.lc_e0, self.ml_u, self.ml_c0,
               self.csr_slot, self.own_q, self.own_src]
         return sum(t.numel() * t.element_size() for t in ts if t is not None)
 

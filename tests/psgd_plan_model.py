@@ -78,7 +78,9 @@ class RankState:
         self.plan = plan
         self.e_pos, self.e_x = t(plan.e_pos), t(plan.e_x)
         self.u_feat, self.u_ptr = t(plan.u_feat), t(plan.u_ptr)
-        self.short_u, self.lc_u, self.lc_e0 = t(plan.short_u), t(plan.lc_u), t(plan.lc_e0)
+        self.lc_u, self.lc_e0 = t(plan.lc_u), t(plan.lc_e0)
+        self.sc_ptr, self.sc_u, self.sc_feat, self.sc_pos, self.sc_x = (t(plan.sc_ptr), t(plan.sc_u), t(plan.sc_feat),
+                                                                        t(plan.sc_pos), t(plan.sc_x))
         self.sg_u, self.sg_feat, self.sg_pos, self.sg_x = t(plan.sg_u), t(plan.sg_feat), t(plan.sg_pos), t(plan.sg_x)
         self.ml_u, self.ml_c0 = t(plan.ml_u), t(plan.ml_c0)
         self.csr_slot = t(plan.csr_slot)
@@ -186,10 +188,18 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                     tg, tw = term(int(R.sg_pos[q]), R.sg_x[q], stage[u - u0])
                     done[(u, )] = (np.zeros((n_orders, k)) + tg, 0.0 + tw)
                     seen[u - u0] += 1
-                for u in R.short_u[pl.mb_shptr[m]:pl.mb_shptr[m + 1]]:
+                for q in range(pl.mb_shptr[m], pl.mb_shptr[m + 1]):       # short columns: compact copies of their nonzeros
+                    u = int(R.sc_u[q])
                     ea, eb = R.u_ptr[u], R.u_ptr[u + 1]
-                    assert 2 <= eb - ea <= SH and e0 <= ea and eb <= e1
-                    done[(int(u), )] = sum_entries(ea, eb, stage[u - u0])
+                    p0, p1 = R.sc_ptr[q], R.sc_ptr[q + 1]
+                    assert 2 <= eb - ea <= SH and e0 <= ea and eb <= e1 and p1 - p0 == eb - ea and R.sc_feat[q] == R.u_feat[u]
+                    assert np.array_equal(R.sc_pos[p0:p1], R.e_pos[ea:eb]) and np.array_equal(R.sc_x[p0:p1], R.e_x[ea:eb])
+                    g, gw = np.zeros((n_orders, k)), 0.0
+                    for e in range(p0, p1):
+                        tg, tw = term(int(R.sc_pos[e]), R.sc_x[e], stage[u - u0])
+                        g = g + tg
+                        gw = gw + tw
+                    done[(u, )] = (g, gw)
                     seen[u - u0] += 1
                 lc0, lc1 = pl.mb_lcptr[m], pl.mb_lcptr[m + 1]
                 for c in range(lc0, lc1):

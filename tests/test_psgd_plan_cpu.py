@@ -54,8 +54,10 @@ def test_plan_layout_matches_brute_force(b_loc, group_entries):
         assert np.array_equal(e_pos[e0:e1], [t[1] for t in want])
         assert np.array_equal(e_x[e0:e1], [t[2] for t in want])
         lens = np.diff(u_ptr[u0:u1 + 1])
-        short = plan.short_u.numpy()[plan.mb_shptr[m]:plan.mb_shptr[m + 1]]
+        short = plan.sc_u.numpy()[plan.mb_shptr[m]:plan.mb_shptr[m + 1]]
         assert np.array_equal(short, u0 + np.nonzero((lens <= SHORT) & (lens > 1))[0])
+        sc_ptr = plan.sc_ptr.numpy()[plan.mb_shptr[m]:plan.mb_shptr[m + 1] + 1]
+        assert np.array_equal(np.diff(sc_ptr), lens[short - u0])
         sg = slice(plan.mb_sgptr[m], plan.mb_sgptr[m + 1])
         singles = u0 + np.nonzero(lens == 1)[0]
         assert np.array_equal(plan.sg_u.numpy()[sg], singles) and np.array_equal(plan.sg_feat.numpy()[sg], u_feat[singles])
@@ -67,6 +69,10 @@ def test_plan_layout_matches_brute_force(b_loc, group_entries):
             for e in range(u_ptr[u], u_ptr[u + 1], CHUNK):
                 want_u.append(u); want_e.append(e)
         assert np.array_equal(lc_u, want_u) and np.array_equal(lc_e0, want_e)
+        lsl = slice(plan.mb_lcptr[m], plan.mb_lcptr[m + 1])
+        assert np.array_equal(plan.lc_feat.numpy()[lsl], u_feat[lc_u])
+        want_cnt = [min(CHUNK, u_ptr[u + 1] - e) + ((1 << 30) if u_ptr[u + 1] - u_ptr[u] <= CHUNK else 0) for u, e in zip(want_u, want_e)]
+        assert np.array_equal(plan.lc_cnt.numpy()[lsl], want_cnt)
         ml_u = plan.ml_u.numpy()[plan.mb_mlptr[m]:plan.mb_mlptr[m + 1]]
         ml_c0 = plan.ml_c0.numpy()[plan.mb_mlptr[m]:plan.mb_mlptr[m + 1]]
         assert np.array_equal(ml_u, u0 + np.nonzero(lens > CHUNK)[0])
