@@ -538,7 +538,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
     peak, peak_src = measured_peak()
     n_launch = args.steps * n_mb
     klass = {"psgd_rows_kernel": (float(ms[4]), rows_bytes * b_loc),
-             "psgd_cols_async_kernel + psgd_split_kernel": (float(ms[5]), cols_bytes * b_loc),
+             "psgd_cols_{long,combine,single,short}_kernel": (float(ms[5]), cols_bytes * b_loc),
              "psgd_stats_kernel + psgd_solve_kernel": (float(ms[6]), dense_bytes)}
     dom = max(klass, key=lambda q: klass[q][0])
     dom_ms, dom_bytes = klass[dom]
@@ -561,6 +561,8 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
                      "whole_step_frac": step_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
         "gpu_launches": int(args.steps * (n_mb * (5 if kw["regularizer"] == "squaredl12" else 4) + 1)
                             + (args.steps * n_mb * 5 if world > 1 else 0)),
+        "exchange_ms_per_minibatch": (float(ms[7]) / max(n_launch, 1) if world > 1 else 0.0),
+        "exchange_note": "pull + inbox barrier + owner update (CUDA events), sharded runs only",
         "clocks": clocks, "p_nonzero_frac": nz_frac, "mean_loss_after": last_loss,
         "details": {"minibatches_per_epoch": n_mb, "batch_local": b_loc, "global_batch": b_loc * world,
                     "batch_size_auto": batch_auto, "columns_per_minibatch": est._psgd_stats["columns_per_minibatch"],

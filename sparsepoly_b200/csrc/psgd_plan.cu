@@ -666,19 +666,36 @@ struct PullArgs {
     double *stage, *stage_w;             // [n_cols][n_orders][k], [n_cols]
 };
 
-// true values of the rows this rank's minibatch touches, read from the owners' HBM (NVLink peer loads;
-// .cv: peer lines must not be served from a stale L1)
+// true values of the rows this rank's minibatch touches, read from the owners' HBM (NVLink peer loads; .cv: peer
+// lines must not be served from a stale L1).  One warp per row batch, lane = element of the row, 8 rows in flight per
+// warp: the latency of a peer load (~2 us) is covered by ~130 KB in flight per SM, so the pass is NVLink-bound.
 __global__ void __launch_bounds__(PL_THREADS) psgd_pull_kernel(const PullArgs a) {
     const int k = a.k, rowlen = a.n_orders * k;
-    const long long total = (long long)a.n_cols * rowlen;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int u = (int)(t / rowlen), r = (int)(t % rowlen);
-        const int o = r / k, s = r % k;
-        const int j = a.u_feat[u];
-        const int owner = j % a.world, q = j / a.world;
-        const double raw = __ldcv(a.peer_P[owner] + ((size_t)o * a.d_own + q) * k + s);
-        a.stage[t] = st_true(raw, a.thr[o * k + s], a.invC);
-        if (r == 0 && a.fit_linear) a.stage_w[u] = __ldcv(a.peer_w[owner] + q) * a.invCw;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int UB = 8;
+    for (int u0 = warp * UB; u0 < a.n_cols; u0 += nwarps * UB) {
+        int jl = 0;
+        if (lane < UB && u0 + lane < a.n_cols) jl = a.u_feat[u0 + lane];
+        for (int e0 = 0; e0 < rowlen; e0 += 32) {
+            const int e = e0 + lane;
+            const int o = e / k, s = e - o * k;
+            double raw[UB];
+#pragma unroll
+            for (int t = 0; t < UB; t++) {
+                const int j = __shfl_sync(0xffffffffu, jl, t);
+                const int owner = j % a.world, q = j / a.world;
+                raw[t] = (e < rowlen && u0 + t < a.n_cols) ? __ldcv(a.peer_P[owner] + ((size_t)o * a.d_own + q) * k + s) : 0.0;
+            }
+            if (e < rowlen) {
+                const double T = a.thr[o * k + s];
+#pragma unroll
+                for (int t = 0; t < UB; t++)
+                    if (u0 + t < a.n_cols) a.stage[(size_t)(u0 + t) * rowlen + e] = st_true(raw[t], T, a.invC);
+            }
+        }
+        if (a.fit_linear && lane < UB && u0 + lane < a.n_cols)
+            a.stage_w[u0 + lane] = __ldcv(a.peer_w[jl % a.world] + jl / a.world) * a.invCw;
     }
 }
 
@@ -1452,9 +1469,12 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             pa.thr = cx->thr; pa.invC = sa.invC; pa.invCw = sa.invCw; pa.n_orders = nord; pa.fit_linear = cx->fit_linear;
             pa.stage = cx->stage; pa.stage_w = cx->stage_w;
             if (pa.n_cols > 0) {
-                long long blocks = ((long long)pa.n_cols * nord * k + PL_THREADS - 1) / PL_THREADS;
-                if (blocks > 148 * 16) blocks = 148 * 16;
+                long long blocks = ((long long)(pa.n_cols + 7) / 8 + 7) / 8;          // 8 rows per warp pass, 8 warps per block
+                if (blocks > 148 * 8) blocks = 148 * 8;
+                if (blocks < 1) blocks = 1;
+                sp_prof_begin(SP_PROF_PLAN, st);                                     // (class 7: cross-rank exchange)
                 psgd_pull_kernel<<<(int)blocks, PL_THREADS, 0, st>>>(pa);
+                sp_prof_end(st);
                 SP_LAUNCH_CHECK("psgd_pull_kernel");
             }
         }
@@ -1476,9 +1496,10 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
 #undef SP_MB
         if (rc) return rc;
         if (sharded) {
+            sp_prof_begin(SP_PROF_PLAN, st);
             cx->seq += 1;
             rc = xbarrier(cx, 0, cx->seq, st);                     // every rank's partial rows are in the inboxes
-            if (rc) return rc;
+            if (rc) { sp_prof_end(st); return rc; }
 #define SP_OW(N, GG, KC) rc = launch_owner<N, GG, KC>(cx, pl, m, sa, st)
 #define SP_OW_K(N)                                                                         \
             if (k <= 8) SP_OW(N, 8, 1);                                                    \
@@ -1494,6 +1515,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             }
 #undef SP_OW_K
 #undef SP_OW
+            sp_prof_end(st);
             if (rc) return rc;
         }
         cx->C = sa.CnP; cx->Cw = sa.Cnw;
