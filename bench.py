@@ -561,8 +561,9 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
                      "whole_step_frac": step_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
         "gpu_launches": int(args.steps * (n_mb * (5 if kw["regularizer"] == "squaredl12" else 4) + 1)
                             + (args.steps * n_mb * 5 if world > 1 else 0)),
-        "exchange_ms_per_minibatch": (float(ms[7]) / max(n_launch, 1) if world > 1 else 0.0),
-        "exchange_note": "pull + inbox barrier + owner update (CUDA events), sharded runs only",
+        "exchange_us_per_minibatch": ({"pull": 1e3 * float(ms[0]) / max(n_launch, 1), "inbox_barrier": 1e3 * float(ms[1]) / max(n_launch, 1),
+                                       "owner_update": 1e3 * float(ms[2]) / max(n_launch, 1)} if world > 1 else None),
+        "exchange_note": "sharded runs: peer-memory pull of the touched rows, flag barrier after the pushes, owner-side update (CUDA events)",
         "clocks": clocks, "p_nonzero_frac": nz_frac, "mean_loss_after": last_loss,
         "details": {"minibatches_per_epoch": n_mb, "batch_local": b_loc, "global_batch": b_loc * world,
                     "batch_size_auto": batch_auto, "columns_per_minibatch": est._psgd_stats["columns_per_minibatch"],

@@ -710,41 +710,76 @@ struct OwnerArgs {
     StepArgs s;
 };
 
+// A group of lanes walks its rows: the next row's descriptor (local row, inbox index of every rank) is fetched while
+// the current row's partial rows -- all ranks' at once, absent ranks contribute +0.0 -- are gathered and added in
+// rank order (deterministic), then the step is applied.
 template <int NORD, int G, int KCH>
-__global__ void __launch_bounds__(PL_THREADS) psgd_owner_kernel(const OwnerArgs a) {
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_owner_kernel(const OwnerArgs a) {
     const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
-    const int r = blockIdx.x * gpb + threadIdx.x / G;
-    if (r >= a.n_rows) return;
-    const int k = a.k;
+    const int ngroups = gridDim.x * gpb;
+    const int k = a.k, world = a.world;
     const size_t dk = (size_t)a.d_own * k;
-    const int q = a.own_q[r];
-    double thr[KCH][NORD], g[KCH][NORD], pold[KCH][NORD];
-    double gw = 0.0;
-    const double wraw = a.s.fit_linear ? a.w[q] : 0.0;
+    double thr[KCH][NORD];
 #pragma unroll
     for (int c = 0; c < KCH; c++)
 #pragma unroll
-        for (int o = 0; o < NORD; o++) {
-            const int s = lane + G * c;
-            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
-            g[c][o] = 0.0;
-            pold[c][o] = s < k ? st_true(a.P[o * dk + (size_t)q * k + s], thr[c][o], a.s.invC) : 0.0;
+        for (int o = 0; o < NORD; o++) thr[c][o] = (lane + G * c) < k ? a.thr[o * k + lane + G * c] : 0.0;
+    int r = blockIdx.x * gpb + threadIdx.x / G;
+    int q_n = 0, at_n = -1;
+    if (r < a.n_rows) {
+        q_n = a.own_q[r];
+        if (lane < world) at_n = a.own_src[(size_t)r * world + lane];
+    }
+    for (; r < a.n_rows; r += ngroups) {
+        const int q = q_n, at_l = at_n;
+        q_n = 0; at_n = -1;
+        if (r + ngroups < a.n_rows) {
+            q_n = a.own_q[r + ngroups];
+            if (lane < world) at_n = a.own_src[(size_t)(r + ngroups) * world + lane];
         }
-    for (int src = 0; src < a.world; src++) {               // fixed rank order: deterministic
-        const int at = a.own_src[(size_t)r * a.world + src];
-        if (at < 0) continue;
+        double g[KCH][NORD], pold[KCH][NORD];
+        double gw = 0.0;
+        const double wraw = a.s.fit_linear ? a.w[q] : 0.0;
 #pragma unroll
-        for (int c = 0; c < KCH; c++) {
-            const int s = lane + G * c;
-            if (s < k) {
+        for (int c = 0; c < KCH; c++)
 #pragma unroll
-                for (int o = 0; o < NORD; o++) g[c][o] += a.inbox_g[src][((size_t)at * NORD + o) * k + s];
+            for (int o = 0; o < NORD; o++) {
+                const int s = (lane + G * c) < k ? lane + G * c : 0;
+                g[c][o] = 0.0;
+                pold[c][o] = a.P[o * dk + (size_t)q * k + s];
+            }
+        constexpr int SB = 4;                                 // ranks gathered together
+        for (int s0 = 0; s0 < world; s0 += SB) {
+            double gi[SB][KCH][NORD], gwi[SB];
+#pragma unroll
+            for (int t = 0; t < SB; t++) {
+                const int at = (s0 + t < world) ? __shfl_sync(gmask, at_l, (s0 + t) & (G - 1), G) : -1;
+                gwi[t] = at >= 0 ? a.inbox_w[s0 + t][at] : 0.0;
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int o = 0; o < NORD; o++) {
+                        const int s = (lane + G * c) < k ? lane + G * c : 0;
+                        gi[t][c][o] = at >= 0 ? a.inbox_g[s0 + t][((size_t)at * NORD + o) * k + s] : 0.0;
+                    }
+            }
+#pragma unroll
+            for (int t = 0; t < SB; t++) {                    // fixed rank order
+                gw += gwi[t];
+#pragma unroll
+                for (int c = 0; c < KCH; c++)
+#pragma unroll
+                    for (int o = 0; o < NORD; o++) g[c][o] += gi[t][c][o];
             }
         }
-        gw += a.inbox_w[src][at];
+#pragma unroll
+        for (int c = 0; c < KCH; c++)
+#pragma unroll
+            for (int o = 0; o < NORD; o++) pold[c][o] = st_true(pold[c][o], thr[c][o], a.s.invC);
+        apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d_own, k, q, lane, g, gw, pold, wraw, thr);
     }
-    apply_row<NORD, G, KCH>(a.s, a.P, a.w, a.d_own, k, q, lane, g, gw, pold, wraw, thr);
 }
 
 // ------------------------------------------------------------------------------------ cross-rank flags
@@ -1329,7 +1364,9 @@ static int launch_owner(const sp_psgd_ctx *cx, const sp_psgd_plan *pl, int m, co
     for (int r = 0; r < cx->world; r++) { oa.inbox_g[r] = cx->inbox_g + (size_t)r * cx->inbox_cap * cx->n_orders * cx->k; oa.inbox_w[r] = cx->inbox_w + (size_t)r * cx->inbox_cap; }
     oa.thr = cx->thr; oa.P = cx->P; oa.w = cx->w; oa.s = sa;
     if (oa.n_rows > 0) {
-        psgd_owner_kernel<NORD, G, KCH><<<grid_for(oa.n_rows, G), PL_THREADS, 0, st>>>(oa);
+        int ob = grid_for((oa.n_rows + 3) / 4, G);                 // ~4 rows per group
+        if (ob > 148 * 3) ob = 148 * 3;
+        psgd_owner_kernel<NORD, G, KCH><<<ob, PL_THREADS, 0, st>>>(oa);
         SP_LAUNCH_CHECK("psgd_owner_kernel");
     }
     return SP_OK;
@@ -1472,7 +1509,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
                 long long blocks = ((long long)(pa.n_cols + 7) / 8 + 7) / 8;          // 8 rows per warp pass, 8 warps per block
                 if (blocks > 148 * 8) blocks = 148 * 8;
                 if (blocks < 1) blocks = 1;
-                sp_prof_begin(SP_PROF_PLAN, st);                                     // (class 7: cross-rank exchange)
+                sp_prof_begin(SP_PROF_ROWS, st);                                     // (sharded psgd: class 0 = pull)
                 psgd_pull_kernel<<<(int)blocks, PL_THREADS, 0, st>>>(pa);
                 sp_prof_end(st);
                 SP_LAUNCH_CHECK("psgd_pull_kernel");
@@ -1496,10 +1533,12 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
 #undef SP_MB
         if (rc) return rc;
         if (sharded) {
-            sp_prof_begin(SP_PROF_PLAN, st);
+            sp_prof_begin(SP_PROF_REGCACHE, st);                   // (sharded psgd: class 1 = inbox barrier, 2 = owner)
             cx->seq += 1;
             rc = xbarrier(cx, 0, cx->seq, st);                     // every rank's partial rows are in the inboxes
-            if (rc) { sp_prof_end(st); return rc; }
+            sp_prof_end(st);
+            if (rc) return rc;
+            sp_prof_begin(SP_PROF_SWEEP_PCD, st);
 #define SP_OW(N, GG, KC) rc = launch_owner<N, GG, KC>(cx, pl, m, sa, st)
 #define SP_OW_K(N)                                                                         \
             if (k <= 8) SP_OW(N, 8, 1);                                                    \
