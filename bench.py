@@ -567,7 +567,8 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
         "clocks": clocks, "p_nonzero_frac": nz_frac, "mean_loss_after": last_loss,
         "details": {"minibatches_per_epoch": n_mb, "batch_local": b_loc, "global_batch": b_loc * world,
                     "batch_size_auto": batch_auto, "columns_per_minibatch": est._psgd_stats["columns_per_minibatch"],
-                    "plan_bytes": est._psgd_stats["plan_bytes"], "data_generation_s": t_gen, "setup_s": t_setup},
+                    "plan_bytes": est._psgd_stats["plan_bytes"], "data_generation_s": t_gen, "setup_s": t_setup,
+                    "setup_seconds": est._psgd_stats.get("setup_seconds")},
     }
     del est, epoch, sync, close
     torch.cuda.empty_cache()

@@ -363,7 +363,7 @@ __device__ __forceinline__ void add_term(double (&g)[KCH][NORD], double &gw, dou
 // value) per column, a group of G lanes fetches G of them at once and finishes UBC at a time -- row of P, table row
 // and dloss of all UBC in flight together, no dependence between them
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const ColsArgs a) {
+__device__ __forceinline__ void cols_single_part(const ColsArgs &a, int bidx, int nblk) {
     constexpr int AR = ARows<DEG, NORD>::value;
     constexpr int UBR = 8 / (KCH * (AR + NORD));                // (register budget: no spills at 3 blocks / SM)
     constexpr int UBC = UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1);
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const C
         for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
     }
     const size_t astride = (size_t)AR * k;
-    for (int qb = (blockIdx.x * gpb + threadIdx.x / G) * G; qb < a.n_single; qb += gridDim.x * gpb * G) {
+    for (int qb = (bidx * gpb + threadIdx.x / G) * G; qb < a.n_single; qb += nblk * gpb * G) {
         int u_l = (int)a.u_base, feat_l = 0, pos_l = 0;       // (lanes past the end: a valid dummy column, never finished)
         double x_l = 0.0;
         if (qb + lane < a.n_single) {
@@ -429,14 +429,14 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_single_kernel(const C
 // three consecutive columns in flight (software pipeline): one memory round trip per column instead of three.
 // Terms are added in sample order (the reference's).
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const ColsArgs a) {
+__device__ __forceinline__ void cols_short_part(const ColsArgs &a, int bidx, int nblk) {
     constexpr int AR = ARows<DEG, NORD>::value;
     constexpr int SH = SP_PSGD_SHORT;
     static_assert(SH <= 8 && G >= 8, "a group's lanes hold a column's nonzeros");
     const int lane = threadIdx.x & (G - 1);
     const unsigned gmask = group_mask<G>();
     const int gpb = PL_THREADS / G;
-    const int ngroups = gridDim.x * gpb;
+    const int ngroups = nblk * gpb;
     const int k = a.k;
     double lam[KCH], thr[KCH][NORD];
     const double *Al[KCH];
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_short_kernel(const Co
         for (int o = 0; o < NORD; o++) thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
     }
     const size_t astride = (size_t)AR * k;
-    const int q0 = blockIdx.x * gpb + threadIdx.x / G;
+    const int q0 = bidx * gpb + threadIdx.x / G;
     // stage 1 (descriptor) of column q, stage 2 (nonzeros) of column q - ngroups, stage 3 (rows) of q - 2 ngroups
     long long p0_1 = 0, p0_2 = 0;
     int len_1 = 0, u_1 = 0, f_1 = 0, len_2 = 0, u_2 = 0, f_2 = 0, len_3 = 0, u_3 = 0, f_3 = 0;
@@ -596,16 +596,15 @@ __global__ void __launch_bounds__(PL_THREADS, 2) psgd_cols_long_kernel(const Col
 
 // long columns of several chunks: one block per column adds the chunks' partial sums -- group w the chunks w,
 // w+G', ... in order, then the groups' sums in group order (a fixed association: deterministic) -- and finishes it
-constexpr int CB_THREADS = 1024;
+constexpr int CB_THREADS = PL_THREADS;
 template <int DEG, int NORD, int G, int KCH, int MODE>
-__global__ void __launch_bounds__(CB_THREADS) psgd_cols_combine_kernel(const ColsArgs a) {
+__device__ __forceinline__ void cols_combine_part(const ColsArgs &a, int bidx, double *cb_sh) {
     constexpr int GPB = CB_THREADS / G;
     constexpr int ROW = KCH * G * NORD + 1;
-    extern __shared__ double cb_sh[];                          // [GPB][ROW]
     const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
     const int k = a.k;
-    const int u = a.ml_u[blockIdx.x];
-    const int c0 = a.ml_c0[blockIdx.x];
+    const int u = a.ml_u[bidx];
+    const int c0 = a.ml_c0[bidx];
     const int np = (int)((a.u_ptr[u + 1] - a.u_ptr[u] + CH - 1) / CH);
     double g[KCH][NORD];
     double gw = 0.0;
@@ -652,6 +651,19 @@ __global__ void __launch_bounds__(CB_THREADS) psgd_cols_combine_kernel(const Col
     load_row<NORD, G, KCH, MODE>(a, lane, feat, u - a.u_base, pold, wraw, thr);
     row_values<NORD, G, KCH, MODE>(a, pold, thr);
     finish_column<NORD, G, KCH, MODE>(a, lane, u, feat, g, gw, pold, wraw, thr);
+}
+
+// One launch for everything that follows the long-column chunks: blocks [0, n_multi) combine the multi-chunk
+// columns (latency-bound: scheduled first, hidden behind the rest), the next nb_single blocks finish the
+// single-nonzero columns, the remaining ones the short columns.
+template <int DEG, int NORD, int G, int KCH, int MODE>
+__global__ void __launch_bounds__(PL_THREADS, 3) psgd_cols_tail_kernel(const ColsArgs a, int nb_single, int nb_short) {
+    constexpr int ROW = KCH * G * NORD + 1;
+    __shared__ double cb_sh[(PL_THREADS / G) * ROW];
+    const int b = blockIdx.x;
+    if (b < a.n_multi) cols_combine_part<DEG, NORD, G, KCH, MODE>(a, b, cb_sh);
+    else if (b < a.n_multi + nb_single) cols_single_part<DEG, NORD, G, KCH, MODE>(a, b - a.n_multi, nb_single);
+    else cols_short_part<DEG, NORD, G, KCH, MODE>(a, b - a.n_multi - nb_single, nb_short);
 }
 
 // ------------------------------------------------------------------------------------ sharded: pull / owner
@@ -1323,31 +1335,17 @@ static int launch_minibatch(const sp_psgd_ctx *cx, const sp_dataset *ds, const s
         else psgd_cols_long_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<cb, PL_THREADS, 0, st>>>(ca);
         SP_LAUNCH_CHECK("psgd_cols_long_kernel");
     }
-    if (ca.n_multi > 0) {
-        const size_t csm = (size_t)(CB_THREADS / G) * (KCH * G * NORD + 1) * sizeof(double);
-        static bool attr_done = false;                       // (per template instance)
-        if (!attr_done && csm > 48 * 1024) {
-            SP_CUDA(cudaFuncSetAttribute(psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            SP_CUDA(cudaFuncSetAttribute(psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            attr_done = true;
+    {
+        int nb_single = ca.n_single > 0 ? grid_for((ca.n_single + G - 1) / G, G) : 0;
+        if (nb_single > 148 * 12) nb_single = 148 * 12;
+        int nb_short = ca.n_short > 0 ? grid_for((ca.n_short + 3) / 4, G) : 0;      // ~4 columns per group: enough to fill the pipeline
+        if (nb_short > 148 * 3) nb_short = 148 * 3;
+        const int nb = ca.n_multi + nb_single + nb_short;
+        if (nb > 0) {
+            if (sharded) psgd_cols_tail_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<nb, PL_THREADS, 0, st>>>(ca, nb_single, nb_short);
+            else psgd_cols_tail_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<nb, PL_THREADS, 0, st>>>(ca, nb_single, nb_short);
+            SP_LAUNCH_CHECK("psgd_cols_tail_kernel");
         }
-        if (sharded) psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<ca.n_multi, CB_THREADS, csm, st>>>(ca);
-        else psgd_cols_combine_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<ca.n_multi, CB_THREADS, csm, st>>>(ca);
-        SP_LAUNCH_CHECK("psgd_cols_combine_kernel");
-    }
-    if (ca.n_single > 0) {
-        int sb = grid_for((ca.n_single + G - 1) / G, G);
-        if (sb > 148 * 12) sb = 148 * 12;
-        if (sharded) psgd_cols_single_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
-        else psgd_cols_single_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
-        SP_LAUNCH_CHECK("psgd_cols_single_kernel");
-    }
-    if (ca.n_short > 0) {
-        int sb = grid_for((ca.n_short + 3) / 4, G);               // ~4 columns per group: enough to fill the pipeline
-        if (sb > 148 * 3) sb = 148 * 3;
-        if (sharded) psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_PUSH><<<sb, PL_THREADS, 0, st>>>(ca);
-        else psgd_cols_short_kernel<DEG, NORD, G, KCH, MODE_APPLY><<<sb, PL_THREADS, 0, st>>>(ca);
-        SP_LAUNCH_CHECK("psgd_cols_short_kernel");
     }
     sp_prof_end(st);
     return SP_OK;

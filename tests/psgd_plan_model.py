@@ -217,7 +217,7 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                     u, c0 = int(R.ml_u[q]), int(R.ml_c0[q])
                     npc = -(-(R.u_ptr[u + 1] - R.u_ptr[u]) // CH)
                     assert npc > 1
-                    GPB = 32                                 # groups of a block add strided pieces, then in group order
+                    GPB = 8                                  # groups of a block add strided pieces, then in group order
                     gs = []
                     for wg in range(min(GPB, npc)):
                         g, gw = np.zeros((n_orders, k)), 0.0
