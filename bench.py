@@ -57,7 +57,8 @@ WORKLOADS = {
                        random_state=0, tol=-1.0)),
     "psgd": dict(tag="C5", n_per_gpu=6_250_000, d=1_000_000, r=39, seed=4, k=32, degree=2, clf=True,
                  kw=dict(degree=2, loss="logistic", n_components=32, solver="psgd",
-                         regularizer="squaredl12", alpha=1e-7, beta=1e-7, gamma=1e-6, fit_linear=True,
+                         # gamma: 20-30 % of P_ still nonzero after 5 epochs (1 220 updates), 6 % after the 26 of a default run
+                         regularizer="squaredl12", alpha=1e-7, beta=1e-7, gamma=2e-8, fit_linear=True,
                          fit_lower="explicit", batch_size="auto", eta0=0.1, learning_rate="optimal",
                          power_t=1.0, shuffle=False, random_state=0, tol=-1.0, n_iter_no_change=10 ** 9)),
 }
@@ -254,6 +255,47 @@ def cpu_reference_epoch_seconds(name, X, y, budget_s):
         desc = (f"C oracle port of the numba path, 1 core: {d_s}/{d} leading columns ({frac:.3%} of nnz), "
                 f"all {n} rows, all {kk} components, extrapolated linearly")
     return t_total, desc
+
+
+_REAL_REF = {}
+
+
+def real_reference_psgd_samples_per_s(X, y, budget_s):
+    """The UNMODIFIED reference (numba) on the host: oracle/_ref/reference_pkg is a git-ignored copy staged in the
+    build container (scripts/run_reference_suite.py --stage); returns None when it (or numba) is not there."""
+    pkg = os.path.join(ROOT, "oracle", "_ref", "reference_pkg")
+    if not os.path.isdir(os.path.join(pkg, "sparsepoly")):
+        return None
+    try:
+        if "cls" not in _REAL_REF:
+            sys.path.insert(0, pkg)
+            os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+            import sparsepoly as ref_pkg
+            _REAL_REF["cls"] = ref_pkg.SparseFactorizationMachineClassifier
+            sys.path.remove(pkg)
+    except Exception as e:                                   # numba missing / import error: fall back to the port
+        _REAL_REF["error"] = repr(e)
+        return None
+    import warnings
+    wl = WORKLOADS["psgd"]
+    kw = dict(wl["kw"])
+    n, d = X.shape
+    batch = int(n * d / X.nnz)
+    kw["batch_size"] = batch
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if not _REAL_REF.get("warm"):                        # JIT compilation of this specialisation (not timed)
+            _REAL_REF["cls"](max_iter=1, **dict(kw, batch_size=64)).fit(X[:256], y[:256])
+            _REAL_REF["warm"] = True
+        # ~3 s per minibatch on one core (25 641 samples + dense update / prox of 32 M entries)
+        nb = max(1, int(budget_s / 3.0))
+        ns = min(n, nb * batch)
+        t0 = time.perf_counter()
+        _REAL_REF["cls"](max_iter=1, **kw).fit(X[:ns], y[:ns])
+        dt = time.perf_counter() - t0
+    return ns / dt, (f"the unmodified reference (numba {__import__('numba').__version__}, 1 core): fit(max_iter=1) on the first "
+                     f"{ns} samples = {ns // batch} minibatches of {batch} at full d={d}, k={wl['k']} (includes its host-side "
+                     f"P_ initialisation and CSR conversion)")
 
 
 def cpu_reference_psgd_samples_per_s(X, y, budget_s):
@@ -524,6 +566,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
     sync()
     nz_frac = float(np.mean(est.P_ != 0))
     close()
+    selection = est._psgd_stats.get("selection")
     if group is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -568,7 +611,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
         "details": {"minibatches_per_epoch": n_mb, "batch_local": b_loc, "global_batch": b_loc * world,
                     "batch_size_auto": batch_auto, "columns_per_minibatch": est._psgd_stats["columns_per_minibatch"],
                     "plan_bytes": est._psgd_stats["plan_bytes"], "data_generation_s": t_gen, "setup_s": t_setup,
-                    "setup_seconds": est._psgd_stats.get("setup_seconds")},
+                    "setup_seconds": est._psgd_stats.get("setup_seconds"), "squaredl12_selection": selection},
     }
     del est, epoch, sync, close
     torch.cuda.empty_cache()
@@ -681,9 +724,14 @@ def run_reference(args, rank, world):
     vals = []
     desc = ""
     t_run0 = time.perf_counter()
+    kind = "port"
     for s in range(args.warmup + args.steps):
         if name == "psgd":
-            v, desc = cpu_reference_psgd_samples_per_s(X, y, per_step_budget)
+            real = real_reference_psgd_samples_per_s(X, y, per_step_budget)
+            if real is not None:
+                (v, desc), kind = real, "reference"
+            else:
+                v, desc = cpu_reference_psgd_samples_per_s(X, y, per_step_budget)
         else:
             v, desc = cpu_reference_epoch_seconds(name, X, y, per_step_budget)
         if s >= args.warmup:
@@ -697,7 +745,7 @@ def run_reference(args, rank, world):
             "higher_is_better": name == "psgd", "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": psgd_config(args, args.gpus, "weak") if name == "psgd" else sweep_config(name, args, X, 1),
-            "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
 

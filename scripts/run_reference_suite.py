@@ -37,7 +37,14 @@ def stage():
     for name, body in SHIM.items():
         with open(os.path.join(DEST, "sparsepoly", name), "w") as f:
             f.write(body)
-    print("staged", DEST)
+    # the unmodified reference package itself, for bench.py --impl reference (numba is part of the image): the
+    # reference arm then times the REAL reference on the GPU box's host cores instead of the C port
+    pkg = os.path.join(ROOT, "oracle", "_ref", "reference_pkg")
+    if os.path.isdir(pkg):
+        shutil.rmtree(pkg)
+    shutil.copytree(os.path.join(REF, "sparsepoly"), os.path.join(pkg, "sparsepoly"),
+                    ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    print("staged", DEST, "and", pkg)
 
 
 def main():

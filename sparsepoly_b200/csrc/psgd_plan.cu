@@ -901,16 +901,15 @@ __device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, doub
             }
             lsum[v] = 0.0; lcnt[v] = 0.0;
         }
-        auto take = [&](double raw, int v) {
-            const double m = fabs(raw) - Tc[v];
-            if (m > 0.0) {
-                const double val = m * a.invC;
-                if (val > hi[v]) { lsum[v] += val; lcnt[v] += 1.0; }
-                else if (band_on[v] && val > lo[v]) {
-                    const int cidx = o * k + cq * VEC + v;
-                    const int bi = atomicAdd(a.band_n + cidx, 1);
-                    if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = val;
-                }
+        auto take = [&](double raw, int v) {                  // branch-free on the common paths (zero entry / counted entry)
+            const double val = (fabs(raw) - Tc[v]) * a.invC;   // <= 0 for entries the lazy threshold has zeroed
+            const bool above = val > hi[v];
+            lsum[v] += above ? val : 0.0;
+            lcnt[v] += above ? 1.0 : 0.0;
+            if (band_on[v] && !above && val > lo[v]) {          // (rare: inside the band)
+                const int cidx = o * k + cq * VEC + v;
+                const int bi = atomicAdd(a.band_n + cidx, 1);
+                if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = val;
             }
         };
         if (act) {
@@ -1443,6 +1442,20 @@ static int ctx_check(const sp_psgd_ctx *cx) {
         sp_set_error("sp_psgd_plan_*: sharded context without peer buffers");
         return SP_ERR_INVALID;
     }
+    return SP_OK;
+}
+
+// diagnostics of the squared-l1,2 selection since sp_psgd_plan_begin: out_host[0] = prox calls, [1] = solved from the
+// band, [2] = needed the generic passes, [3] = current band half-width
+extern "C" int sp_psgd_plan_solver_stats(const sp_psgd_ctx *cx, double *out_host, sp_stream stream) {
+    int rc = ctx_check(cx);
+    if (rc) return rc;
+    if (!out_host) { sp_set_error("sp_psgd_plan_solver_stats: null pointer"); return SP_ERR_INVALID; }
+    const WorkLayout L = work_layout((size_t)cx->n_orders * cx->k, cx->world);
+    double st[8];
+    SP_CUDA(cudaMemcpyAsync(st, cx->work + L.state, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    out_host[0] = st[1]; out_host[1] = st[2]; out_host[2] = st[3]; out_host[3] = st[4] > 0.0 ? st[4] : BAND_DELTA;
     return SP_OK;
 }
 

@@ -483,6 +483,8 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
 
         def close():
             if planned:
+                if self.regularizer == "squaredl12":
+                    self._psgd_stats["selection"] = solvers.psgd_planned_solver_stats(ctx)
                 ctx.close()
 
         return epoch, sync, close

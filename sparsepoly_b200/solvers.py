@@ -161,6 +161,13 @@ def psgd_planned_run(ctx, ds, plan, y, idx_samples, alpha, beta, gamma, eta0, le
     return it_c.value
 
 
+def psgd_planned_solver_stats(ctx):
+    """(prox calls, solved from the band, needed generic passes, band half-width) of the squared-l1,2 selection."""
+    out = (C.c_double * 4)()
+    _lib.check(_L().sp_psgd_plan_solver_stats(ctx.ref(), out, _stream()))
+    return {"prox_calls": int(out[0]), "band_solves": int(out[1]), "generic_solves": int(out[2]), "band_half_width": out[3]}
+
+
 def psgd_planned_end(ctx, n_local, loss_sum, materialize):
     """End of an epoch: loss_sum[0] += the epoch's loss sum (fixed order); materialize=True turns the lazily
     scaled / thresholded storage back into the model."""
