@@ -17,6 +17,7 @@ from sparsepoly_b200.psgd_plan import PsgdContext, PsgdPlan  # noqa: E402
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 reg = sys.argv[3] if len(sys.argv) > 3 else "squaredl12"
+gamma = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-6
 d, k = 1_000_000, 32
 t0 = time.time()
 X = synth.criteo_like(rows, d, 4000)
@@ -50,7 +51,7 @@ for ep in range(epochs):
     torch.cuda.synchronize()
     t0 = time.time()
     loss.zero_()
-    it = solvers.psgd_planned_run(ctx, ds, plan, yd, idx, 1e-7, 1e-7, 1e-6, 0.1, 1, 1.0, it)
+    it = solvers.psgd_planned_run(ctx, ds, plan, yd, idx, 1e-7, 1e-7, gamma, 0.1, 1, 1.0, it)
     solvers.psgd_planned_end(ctx, rows, loss, False)
     torch.cuda.synchronize()
     dt = time.time() - t0
@@ -64,9 +65,9 @@ for ep in range(epochs):
 # unprofiled epoch (no event overhead)
 torch.cuda.synchronize()
 t0 = time.time()
-it = solvers.psgd_planned_run(ctx, ds, plan, yd, idx, 1e-7, 1e-7, 1e-6, 0.1, 1, 1.0, it)
+it = solvers.psgd_planned_run(ctx, ds, plan, yd, idx, 1e-7, 1e-7, gamma, 0.1, 1, 1.0, it)
 solvers.psgd_planned_end(ctx, rows, loss, True)
 torch.cuda.synchronize()
 dt = time.time() - t0
 ctx.store_model(P, w)
-print(f"plain epoch: {dt*1e3:.1f} ms  {rows/dt/1e6:.1f} M samples/s  nonzero frac {float((P != 0).double().mean()):.4f}")
+print(f"plain epoch: {dt*1e3:.1f} ms  {rows/dt/1e6:.1f} M samples/s  nonzero frac {float((P != 0).double().mean()):.4f}", solvers.psgd_planned_solver_stats(ctx))

@@ -53,6 +53,9 @@ def host_csr(X):
                 Xr.data.astype(np.float64, copy=False))
     X = np.asarray(X, dtype=np.float64)
     n, d = X.shape
+    if n * d >= 2 ** 31:
+        raise ValueError("dense input with n_samples * n_features >= 2^31 is not supported (int32 indptr, reference "
+                         "dataset.py:60-66); pass a scipy sparse matrix")
     indptr = (np.arange(n + 1, dtype=np.int64) * d).astype(np.int32)
     indices = np.tile(np.arange(d, dtype=np.int32), n)
     return indptr, indices, np.ascontiguousarray(X).reshape(-1)
@@ -70,6 +73,9 @@ def host_csc(X):
                 Xc.data.astype(np.float64, copy=False))
     X = np.asarray(X, dtype=np.float64)
     n, d = X.shape
+    if n * d >= 2 ** 31:
+        raise ValueError("dense input with n_samples * n_features >= 2^31 is not supported (int32 indptr, reference "
+                         "dataset.py:60-66); pass a scipy sparse matrix")
     indptr = (np.arange(d + 1, dtype=np.int64) * n).astype(np.int32)
     indices = np.tile(np.arange(n, dtype=np.int32), d)
     return indptr, indices, np.ascontiguousarray(X.T).reshape(-1)

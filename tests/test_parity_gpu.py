@@ -659,3 +659,15 @@ def test_sharded_psgd_two_ranks_matches_oracle(tmp_path):
         Xte = sp.vstack([synth.criteo_like(50 + 10 * r, _SH_D, 77 + r) for r in range(world)]).tocsr()
         want = O.fm_output(Xte, out["P_"], out["w_"], out["lams_"], kw["degree"], True, kw.get("fit_lower", "explicit"))
         assert rel_err(z[0][tag + "/pred"], want) <= TOL and np.array_equal(z[0][tag + "/pred"], z[1][tag + "/pred"])
+
+
+def test_transpose_handles_more_than_two_million_rows():
+    """sp_transpose_f64 used grid.y for the row tiles (<= 65 535 tiles = 2.1 M rows); pbcd / psgd transpose
+    P [d, k] at every sync, so a sparse CTR feature space of d > 2.1 M made fit() fail at its very end."""
+    import torch
+    from sparsepoly_b200 import solvers
+    t = torch.arange(2_200_003 * 3, dtype=torch.float64, device="cuda").reshape(2_200_003, 3)
+    out = solvers.transpose(t)
+    assert out.shape == (3, 2_200_003) and torch.equal(out, t.t().contiguous())
+    out2 = solvers.transpose(out)
+    assert torch.equal(out2, t)
