@@ -582,7 +582,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
     n_launch = args.steps * n_mb
     klass = {"psgd_rows_kernel": (float(ms[4]), rows_bytes * b_loc),
              "psgd_cols_{long,combine,single,short}_kernel": (float(ms[5]), cols_bytes * b_loc),
-             "psgd_stats_kernel + psgd_solve_kernel": (float(ms[6]), dense_bytes)}
+             "psgd_stats_kernel + psgd_solve_kernel": (float(ms[6]) + float(ms[7]), dense_bytes)}
     dom = max(klass, key=lambda q: klass[q][0])
     dom_ms, dom_bytes = klass[dom]
     achieved = dom_bytes * n_launch / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -604,6 +604,7 @@ def run_psgd_workload(args, rank, world, local, batch_mode="weak"):
                      "whole_step_frac": step_bytes * args.steps / (ms_total / 1e3) / 1e9 / peak},
         "gpu_launches": int(args.steps * (n_mb * (5 if kw["regularizer"] == "squaredl12" else 4) + 1)
                             + (args.steps * n_mb * 5 if world > 1 else 0)),
+        "stats_us_per_minibatch": 1e3 * float(ms[6]) / max(n_launch, 1), "solve_us_per_minibatch": 1e3 * float(ms[7]) / max(n_launch, 1),
         "exchange_us_per_minibatch": ({"pull": 1e3 * float(ms[0]) / max(n_launch, 1), "inbox_barrier": 1e3 * float(ms[1]) / max(n_launch, 1),
                                        "owner_update": 1e3 * float(ms[2]) / max(n_launch, 1)} if world > 1 else None),
         "exchange_note": "sharded runs: peer-memory pull of the touched rows, flag barrier after the pushes, owner-side update (CUDA events)",

@@ -324,8 +324,9 @@ int sp_psgd_plan_run(sp_psgd_ctx *ctx, const sp_dataset *ds, const sp_psgd_plan 
 int sp_psgd_plan_end(sp_psgd_ctx *ctx, int n_local, double *loss_sum, int materialize, sp_stream stream);
 
 /* diagnostics of the squared-l1,2 selection since sp_psgd_plan_begin (synchronises the stream): out_host[0] = prox
- * calls, [1] = solved from the band, [2] = needed generic passes, [3] = band half-width */
-int sp_psgd_plan_solver_stats(const sp_psgd_ctx *ctx, double *out_host /*[4]*/, sp_stream stream);
+ * calls, [1] = solved from the band, [2] = needed generic passes, [3] = band half-width, [4] / [5] = mean / largest
+ * band size per column at the last call */
+int sp_psgd_plan_solver_stats(const sp_psgd_ctx *ctx, double *out_host /*[6]*/, sp_stream stream);
 
 /* peer-visible device memory for the sharded path (cudaMalloc + CUDA IPC); handle64: 64 bytes */
 int sp_shm_alloc(size_t bytes, void **out_host);

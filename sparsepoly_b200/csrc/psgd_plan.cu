@@ -36,6 +36,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "sparsepoly_b200.h"
 
@@ -872,8 +874,10 @@ __device__ __forceinline__ double predict_tau(const double *state, int ncol, int
 // threshold of every column -- the band's upper edge (band pass) or a.tau[c] (generic pass) -- and, in a
 // band pass, the values inside the band.  Partials are combined in fixed order.  VEC = 2: a thread owns two
 // adjacent columns and streams 16-byte loads, 8 in flight (needs an even k); ssum / scnt hold VEC*blockDim.
+constexpr int BAND_BLK = 16;                        // band values a block stages per column before one global reservation
 template <int VEC>
-__device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, double *scnt, bool band_pass) {
+__device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, double *scnt, bool band_pass,
+                                           int *s_bn = nullptr, double *s_bv = nullptr) {
     const int tid = threadIdx.x, T = blockDim.x, nblk = gridDim.x, k = a.k, d = a.d;
     const int ncol = a.n_orders * k;
     const int tpr = k / VEC;                        // threads per row (host: k <= 128, k % VEC == 0)
@@ -885,6 +889,10 @@ __device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, doub
         const double *P = a.P + (size_t)o * d * k;
         double Tc[VEC], hi[VEC], lo[VEC], lsum[VEC], lcnt[VEC];
         bool band_on[VEC];
+        if (s_bn != nullptr) {                                 // per-block staging of the band values of this order's columns
+            for (int c = tid; c < k; c += T) s_bn[c] = 0;
+            __syncthreads();
+        }
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
             const int cidx = o * k + (act ? cq * VEC + v : 0);
@@ -907,9 +915,14 @@ __device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, doub
             lsum[v] += above ? val : 0.0;
             lcnt[v] += above ? 1.0 : 0.0;
             if (band_on[v] && !above && val > lo[v]) {          // (rare: inside the band)
-                const int cidx = o * k + cq * VEC + v;
-                const int bi = atomicAdd(a.band_n + cidx, 1);
-                if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = val;
+                const int cl = cq * VEC + v, cidx = o * k + cl;
+                int sb = BAND_BLK;
+                if (s_bn != nullptr) sb = atomicAdd(s_bn + cl, 1);          // shared-memory slot first: the global counter
+                if (sb < BAND_BLK) s_bv[cl * BAND_BLK + sb] = val;          // of a column would serialise thousands of atomics
+                else {
+                    const int bi = atomicAdd(a.band_n + cidx, 1);
+                    if (bi < BAND_CAP) a.band[(size_t)cidx * BAND_CAP + bi] = val;
+                }
             }
         };
         if (act) {
@@ -949,6 +962,14 @@ __device__ __forceinline__ void stats_pass(const StatArgs &a, double *ssum, doub
             for (int r = 0; r < rpp; r++) { sm += ssum[v * T + r * tpr + q]; n += scnt[v * T + r * tpr + q]; }
             a.psum[(size_t)blockIdx.x * ncol + o * k + tid] = sm;
             a.pcnt[(size_t)blockIdx.x * ncol + o * k + tid] = n;
+            if (s_bn != nullptr) {                             // flush the block's staged band values: one reservation per column
+                const int nb = s_bn[tid] < BAND_BLK ? s_bn[tid] : BAND_BLK;
+                if (nb > 0) {
+                    const int base = atomicAdd(a.band_n + o * k + tid, nb);
+                    for (int q2 = 0; q2 < nb; q2++)
+                        if (base + q2 < BAND_CAP) a.band[(size_t)(o * k + tid) * BAND_CAP + base + q2] = s_bv[tid * BAND_BLK + q2];
+                }
+            }
         }
         __syncthreads();
     }
@@ -974,8 +995,10 @@ __device__ __forceinline__ void reduce_partials(const StatArgs &a, int cidx, int
 // band pass as its own streaming launch
 __global__ void __launch_bounds__(PL_THREADS, 3) psgd_stats_kernel(const StatArgs a) {
     __shared__ double ssum[2 * PL_THREADS], scnt[2 * PL_THREADS];
-    if ((a.k & 1) == 0) stats_pass<2>(a, ssum, scnt, true);
-    else stats_pass<1>(a, ssum, scnt, true);
+    __shared__ int s_bn[128];                                  // (k <= 128)
+    __shared__ double s_bv[128 * BAND_BLK];
+    if ((a.k & 1) == 0) stats_pass<2>(a, ssum, scnt, true, s_bn, s_bv);
+    else stats_pass<1>(a, ssum, scnt, true, s_bn, s_bv);
 }
 
 // sharded: block c reduces column c's partials (fixed order) and publishes this rank's statistics + band to
@@ -1028,7 +1051,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
     const bool band_on = st.state[0] > 0.0 && st.strength > 0.0;
     // ---- band path: every column's fixed point from (statistics above the band) + (the band's values)
     if (!band_on) {
-        if (blockIdx.x == 0 && tid == 0) a.fail[0] = 1;
+        if (blockIdx.x == 0) {
+            if (tid == 0) a.fail[0] = 1;
+            if (world == 1) for (int c = tid; c < ncol; c += T) st.band_n[c] = 0;
+        }
     } else {
         for (int cidx = blockIdx.x; cidx < ncol; cidx += nblk) {
             double sumA = 0.0, cntA = 0.0;
@@ -1049,6 +1075,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
                 }
             }
             if (nbv > BAND_TOTAL) { ok = false; if (tid == 0) a.fail[1] = 1; }
+            if (tid == 0) st.state[8 + 2 * ncol + cidx] = (double)nbv;
             if (ok) {
                 const double tau_pred = predict_tau(st.state, ncol, cidx, st.strength);
                 const double b_hi = tau_pred * (1.0 + bdelta), b_lo = tau_pred * (1.0 - bdelta);
@@ -1081,50 +1108,63 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
                         }
                         __syncthreads();
                     }
-                {                                                    // inclusive prefix sums, fixed order
-                    const int per = (np2 + T - 1) / T;
-                    const int q0 = tid * per, q1 = min(np2, q0 + per);
-                    double acc = 0.0;
-                    for (int q = q0; q < q1; q++) acc += (q < nbv) ? sband[q] : 0.0;
-                    ssum[tid] = acc;
+                {                                                    // inclusive prefix sums of the sorted band (Hillis-Steele:
+                    for (int q = tid; q < np2; q += T) spref[q] = (q < nbv) ? sband[q] : 0.0;   // a fixed association, log2 steps)
                     __syncthreads();
-                    if (tid == 0) {
-                        double run = 0.0;
-                        for (int b = 0; b < T; b++) { const double v = ssum[b]; ssum[b] = run; run += v; }
+                    for (int off = 1; off < np2; off <<= 1) {
+                        double add[BAND_TOTAL / SOLVE_THREADS];
+#pragma unroll
+                        for (int i = 0; i < BAND_TOTAL / SOLVE_THREADS; i++) {
+                            const int q = tid + i * T;
+                            add[i] = (q < np2 && q >= off) ? spref[q - off] : 0.0;
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int i = 0; i < BAND_TOTAL / SOLVE_THREADS; i++) {
+                            const int q = tid + i * T;
+                            if (q < np2 && q >= off) spref[q] += add[i];
+                        }
+                        __syncthreads();
                     }
-                    __syncthreads();
-                    acc = ssum[tid];
-                    for (int q = q0; q < q1; q++) { acc += (q < nbv) ? sband[q] : 0.0; spref[q] = acc; }
-                    __syncthreads();
                 }
-                if (tid == 0) {
-                    double tau = b_hi;
-                    int m_prev = -1;
-                    bool good = false;
-                    for (int it = 0; it < 200; it++) {
-                        int lo_i = 0, hi_i = nbv;                      // m = #{band > tau}
-                        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (sband[mid] > tau) lo_i = mid + 1; else hi_i = mid; }
-                        const int m = lo_i;
+                // the prox keeps the theta largest values with  v_(theta) > 2 s S_theta / (1 + 2 s theta)  (utils.py:26-70: the
+                // largest such theta).  Everything above the band is kept whenever the threshold lands inside the band,
+                // so theta = cntA + m with m the largest band prefix that satisfies the condition -- evaluated for
+                // all m at once instead of iterating the fixed point.
+                {
+                    int best = 0;
+                    for (int q = tid; q < nbv; q += T) {
+                        const double sum = sumA + spref[q];
+                        const double cnt = cntA + (double)(q + 1);
+                        const double tq = 2.0 * st.strength * sum / (1.0 + 2.0 * st.strength * cnt);
+                        if (sband[q] > tq) best = q + 1;
+                    }
+                    scnt[tid] = (double)best;
+                    __syncthreads();
+                    for (int off = T / 2; off > 0; off >>= 1) {
+                        if (tid < off) scnt[tid] = scnt[tid] > scnt[tid + off] ? scnt[tid] : scnt[tid + off];
+                        __syncthreads();
+                    }
+                    if (tid == 0) {
+                        const int m = (int)scnt[0];
                         const double sum = m > 0 ? sumA + spref[m - 1] : sumA;
                         const double cnt = cntA + (double)m;
                         const double tnew = 2.0 * st.strength * sum / (1.0 + 2.0 * st.strength * cnt);
-                        if (!(tnew > b_lo) || tnew > b_hi) break;
-                        if (m == m_prev) { a.tau[cidx] = tnew; good = true; break; }
-                        m_prev = m;
-                        tau = tnew;
+                        const bool good = tnew > b_lo && tnew <= b_hi && (m == nbv || !(sband[m] > tnew));
+                        if (good) a.tau[cidx] = tnew;
+                        s_flag = good ? 1 : 0;
                     }
-                    s_flag = good ? 1 : 0;
                 }
                 __syncthreads();
                 ok = s_flag != 0;
                 __syncthreads();
             }
             if (!ok && tid == 0) a.fail[0] = 1;
+            if (world == 1) {                                    // this column's band counter: ready for the next minibatch
+                __syncthreads();                                 // (only the block that owns the column touches it)
+                if (tid == 0) st.band_n[cidx] = 0;
+            }
         }
-    }
-    if (world == 1) {                                            // band counters: ready for the next minibatch
-        __syncthreads();
-        for (int c = blockIdx.x * T + tid; c < ncol; c += nblk * T) st.band_n[c] = 0;
     }
     __threadfence();
     grid.sync();
@@ -1391,7 +1431,7 @@ static WorkLayout work_layout(size_t ncol, int world) {
     L.pcnt = at; at += (size_t)STAT_PART_MAX * ncol;
     L.colres = at; at += 2 * ncol;
     L.tau = at; at += ncol;
-    L.state = at; at += 8 + 2 * ncol;
+    L.state = at; at += 8 + 3 * ncol;                  // (+ the band size of every column at the last call: diagnostics)
     L.band = at; at += ncol * (size_t)BAND_CAP;
     L.ints = at; at += (ncol + 8) / 2 + 4;            // band counters + ticket | fail[2]
     L.total = at;
@@ -1408,13 +1448,17 @@ extern "C" size_t sp_psgd_plan_xwork_doubles(int n_orders, int k, int world) {
     return (size_t)world * statbox_doubles(ncol) + (size_t)world * 2 * 2 * ncol + 64;
 }
 
-static int solve_grid(int *nblk_out) {
+static int solve_grid(int *nblk_out, int ncol) {
     int dev = 0, sms = 0, occ = 0;
     SP_CUDA(cudaGetDevice(&dev));
     SP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, psgd_solve_kernel, SOLVE_THREADS, 0));
     if (occ < 1) { sp_set_error("psgd_solve_kernel does not fit on an SM"); return SP_ERR_CUDA; }
-    *nblk_out = sms;                       // one block per SM: leaves room when two ranks share a device (tests)
+    // one block per column is all the band path needs (a smaller cooperative grid launches and synchronises faster);
+    // the generic passes -- first minibatches of a fit, a band miss every few thousand minibatches -- are
+    // correspondingly slower, which is the right trade
+    int nb = ncol < 16 ? 16 : ncol;
+    *nblk_out = nb < sms ? nb : sms;
     return SP_OK;
 }
 
@@ -1446,16 +1490,21 @@ static int ctx_check(const sp_psgd_ctx *cx) {
 }
 
 // diagnostics of the squared-l1,2 selection since sp_psgd_plan_begin: out_host[0] = prox calls, [1] = solved from the
-// band, [2] = needed the generic passes, [3] = current band half-width
+// band, [2] = needed the generic passes, [3] = current band half-width, [4] / [5] = mean / largest band size of the
+// columns at the last call
 extern "C" int sp_psgd_plan_solver_stats(const sp_psgd_ctx *cx, double *out_host, sp_stream stream) {
     int rc = ctx_check(cx);
     if (rc) return rc;
     if (!out_host) { sp_set_error("sp_psgd_plan_solver_stats: null pointer"); return SP_ERR_INVALID; }
     const WorkLayout L = work_layout((size_t)cx->n_orders * cx->k, cx->world);
-    double st[8];
-    SP_CUDA(cudaMemcpyAsync(st, cx->work + L.state, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    const size_t ncol = (size_t)cx->n_orders * cx->k;
+    std::vector<double> st(8 + 3 * ncol);
+    SP_CUDA(cudaMemcpyAsync(st.data(), cx->work + L.state, st.size() * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     SP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     out_host[0] = st[1]; out_host[1] = st[2]; out_host[2] = st[3]; out_host[3] = st[4] > 0.0 ? st[4] : BAND_DELTA;
+    double mx = 0.0, sm = 0.0;
+    for (size_t c = 0; c < ncol; c++) { const double v = st[8 + 2 * ncol + c]; sm += v; if (v > mx) mx = v; }
+    out_host[4] = ncol ? sm / (double)ncol : 0.0; out_host[5] = mx;
     return SP_OK;
 }
 
@@ -1494,7 +1543,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
     const WorkLayout L = work_layout(ncol, cx->world);
     const bool sharded = cx->world > 1;
     int solve_blocks = 0;
-    if (cx->reg == SP_REG_SQL12) { rc = solve_grid(&solve_blocks); if (rc) return rc; }
+    if (cx->reg == SP_REG_SQL12) { rc = solve_grid(&solve_blocks, (int)ncol); if (rc) return rc; }
     int64_t it = *it_io_host;
     for (int m = m_begin; m < m_end; m++) {
         const PlanMb mb = plan_mb(pl, m);
@@ -1603,6 +1652,8 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
                 rc = xbarrier(cx, 0, cx->seq, st);
                 if (rc) { sp_prof_end(st); return rc; }
             }
+            sp_prof_end(st);
+            sp_prof_begin(SP_PROF_PLAN, st);                       // (psgd: class 6 = statistics pass, class 7 = solve)
             SolveArgs so;
             so.st = sg;
             so.Cn = cx->C; so.thr = cx->thr; so.tau = cx->work + L.tau; so.colres = cx->work + L.colres;

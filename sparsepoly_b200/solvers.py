@@ -163,9 +163,10 @@ def psgd_planned_run(ctx, ds, plan, y, idx_samples, alpha, beta, gamma, eta0, le
 
 def psgd_planned_solver_stats(ctx):
     """(prox calls, solved from the band, needed generic passes, band half-width) of the squared-l1,2 selection."""
-    out = (C.c_double * 4)()
+    out = (C.c_double * 6)()
     _lib.check(_L().sp_psgd_plan_solver_stats(ctx.ref(), out, _stream()))
-    return {"prox_calls": int(out[0]), "band_solves": int(out[1]), "generic_solves": int(out[2]), "band_half_width": out[3]}
+    return {"prox_calls": int(out[0]), "band_solves": int(out[1]), "generic_solves": int(out[2]), "band_half_width": out[3],
+            "band_values_per_column_mean": out[4], "band_values_per_column_max": out[5]}
 
 
 def psgd_planned_end(ctx, n_local, loss_sum, materialize):
