@@ -982,13 +982,13 @@ __device__ __forceinline__ void reduce_partials(const StatArgs &a, int cidx, int
     const int ncol = a.n_orders * a.k;
     double s = 0.0, n = 0.0;
     for (int b = tid; b < npart; b += T) { s += a.psum[(size_t)b * ncol + cidx]; n += a.pcnt[(size_t)b * ncol + cidx]; }
-    ssum[tid] = s; scnt[tid] = n;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s += __shfl_down_sync(0xffffffffu, s, off); n += __shfl_down_sync(0xffffffffu, n, off); }
+    if ((tid & 31) == 0) { ssum[tid >> 5] = s; scnt[tid >> 5] = n; }
     __syncthreads();
-    for (int off = T / 2; off > 0; off >>= 1) {
-        if (tid < off) { ssum[tid] += ssum[tid + off]; scnt[tid] += scnt[tid + off]; }
-        __syncthreads();
-    }
-    *osum = ssum[0]; *ocnt = scnt[0];
+    s = 0.0; n = 0.0;
+    for (int w = 0; w < T / 32; w++) { s += ssum[w]; n += scnt[w]; }
+    *osum = s; *ocnt = n;
     __syncthreads();
 }
 
@@ -1041,8 +1041,8 @@ constexpr int SOLVE_THREADS = 512;
 __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double ssum[SOLVE_THREADS], scnt[SOLVE_THREADS];
-    __shared__ double sband[BAND_TOTAL], spref[BAND_TOTAL];
-    __shared__ int s_flag;
+    __shared__ double sband[BAND_TOTAL];
+    __shared__ uint4 sred[2 * (SOLVE_THREADS / 32)];
     const StatArgs &st = a.st;
     const int tid = threadIdx.x, T = SOLVE_THREADS, nblk = gridDim.x;
     const int ncol = st.n_orders * st.k, world = st.world;
@@ -1079,10 +1079,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
             if (ok) {
                 const double tau_pred = predict_tau(st.state, ncol, cidx, st.strength);
                 const double b_hi = tau_pred * (1.0 + bdelta), b_lo = tau_pred * (1.0 - bdelta);
-                int np2 = 1;
-                while (np2 < nbv) np2 <<= 1;
-                for (int q = tid; q < np2; q += T) sband[q] = -1.0;
-                __syncthreads();
                 if (world == 1) {
                     for (int q = tid; q < nbv; q += T) sband[q] = st.band[(size_t)cidx * BAND_CAP + q];
                 } else {
@@ -1096,67 +1092,62 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
                     }
                 }
                 __syncthreads();
-                for (int kk = 2; kk <= np2; kk <<= 1)               // bitonic sort, descending
-                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                        for (int q = tid; q < np2; q += T) {
-                            const int x = q ^ jj;
-                            if (x > q) {
-                                const double va = sband[q], vb = sband[x];
-                                const bool desc = (q & kk) == 0;
-                                if (desc ? (va < vb) : (va > vb)) { sband[q] = vb; sband[x] = va; }
-                            }
-                        }
-                        __syncthreads();
-                    }
-                {                                                    // inclusive prefix sums of the sorted band (Hillis-Steele:
-                    for (int q = tid; q < np2; q += T) spref[q] = (q < nbv) ? sband[q] : 0.0;   // a fixed association, log2 steps)
-                    __syncthreads();
-                    for (int off = 1; off < np2; off <<= 1) {
-                        double add[BAND_TOTAL / SOLVE_THREADS];
+                // The prox keeps the values above tau = 2 s S / (1 + 2 s theta), S / theta the sum / number of the kept
+                // values (utils.py:26-70).  Everything above the band is kept whenever tau lands inside the band, so
+                // only the band's members are undecided: start with all of them kept and drop the ones at or below
+                // tau until none drops (the kept set only shrinks, tau only rises, and the fixed point is the set
+                // utils.py selects).  The band arrives in no particular order (atomic reservations), so its sums
+                // are taken EXACTLY: all members lie in (2^(E-2), 2^E) -- the band is at most +-10 % wide -- hence
+                // v * 2^(54-E) is an integer below 2^54, summed as three 18-bit limbs in 32-bit integers
+                // (<= 2048 members) and rounded once.  The result does not depend on the order.
+                constexpr int VPT = BAND_TOTAL / SOLVE_THREADS;
+                const int E = ilogb(b_hi) + 1;
+                const double up = scalbn(1.0, 54 - E), down = scalbn(1.0, E - 54);
+                const double vmin = scalbn(1.0, E - 2), vmax = scalbn(1.0, E);
+                double bv[VPT];
+                unsigned l0[VPT], l1[VPT], l2[VPT];
+                bool bad = !(bdelta <= 0.1) || E - 54 < -1000 || 54 - E < -1000;
 #pragma unroll
-                        for (int i = 0; i < BAND_TOTAL / SOLVE_THREADS; i++) {
-                            const int q = tid + i * T;
-                            add[i] = (q < np2 && q >= off) ? spref[q - off] : 0.0;
+                for (int i = 0; i < VPT; i++) {
+                    const int q = tid + i * T;
+                    bv[i] = -1.0; l0[i] = l1[i] = l2[i] = 0u;
+                    if (q < nbv) {
+                        const double b = sband[q];
+                        if (!(b > vmin && b < vmax)) bad = true;
+                        else {
+                            const unsigned long long I = (unsigned long long)(b * up);
+                            bv[i] = b;
+                            l0[i] = (unsigned)(I & 0x3ffffull); l1[i] = (unsigned)((I >> 18) & 0x3ffffull); l2[i] = (unsigned)(I >> 36);
                         }
-                        __syncthreads();
-#pragma unroll
-                        for (int i = 0; i < BAND_TOTAL / SOLVE_THREADS; i++) {
-                            const int q = tid + i * T;
-                            if (q < np2 && q >= off) spref[q] += add[i];
-                        }
-                        __syncthreads();
                     }
                 }
-                // the prox keeps the theta largest values with  v_(theta) > 2 s S_theta / (1 + 2 s theta)  (utils.py:26-70: the
-                // largest such theta).  Everything above the band is kept whenever the threshold lands inside the band,
-                // so theta = cntA + m with m the largest band prefix that satisfies the condition -- evaluated for
-                // all m at once instead of iterating the fixed point.
-                {
-                    int best = 0;
-                    for (int q = tid; q < nbv; q += T) {
-                        const double sum = sumA + spref[q];
-                        const double cnt = cntA + (double)(q + 1);
-                        const double tq = 2.0 * st.strength * sum / (1.0 + 2.0 * st.strength * cnt);
-                        if (sband[q] > tq) best = q + 1;
+                double tau = b_lo;                                   // every member of the band is above b_lo
+                int prev_n = -1;
+                bool conv = false;
+                for (int iter = 0; iter < 64; iter++) {
+                    unsigned c = bad ? 1u << 20 : 0u, s0 = 0u, s1 = 0u, s2 = 0u;
+#pragma unroll
+                    for (int i = 0; i < VPT; i++) {
+                        const bool act = bv[i] > tau;
+                        c += act ? 1u : 0u; s0 += act ? l0[i] : 0u; s1 += act ? l1[i] : 0u; s2 += act ? l2[i] : 0u;
                     }
-                    scnt[tid] = (double)best;
+                    c = __reduce_add_sync(0xffffffffu, c); s0 = __reduce_add_sync(0xffffffffu, s0);
+                    s1 = __reduce_add_sync(0xffffffffu, s1); s2 = __reduce_add_sync(0xffffffffu, s2);
+                    uint4 *red = sred + (iter & 1) * (SOLVE_THREADS / 32);
+                    if ((tid & 31) == 0) red[tid >> 5] = make_uint4(c, s0, s1, s2);
                     __syncthreads();
-                    for (int off = T / 2; off > 0; off >>= 1) {
-                        if (tid < off) scnt[tid] = scnt[tid] > scnt[tid + off] ? scnt[tid] : scnt[tid + off];
-                        __syncthreads();
-                    }
-                    if (tid == 0) {
-                        const int m = (int)scnt[0];
-                        const double sum = m > 0 ? sumA + spref[m - 1] : sumA;
-                        const double cnt = cntA + (double)m;
-                        const double tnew = 2.0 * st.strength * sum / (1.0 + 2.0 * st.strength * cnt);
-                        const bool good = tnew > b_lo && tnew <= b_hi && (m == nbv || !(sband[m] > tnew));
-                        if (good) a.tau[cidx] = tnew;
-                        s_flag = good ? 1 : 0;
-                    }
+                    unsigned long long t0 = 0, t1 = 0, t2 = 0;
+                    unsigned n = 0;
+#pragma unroll
+                    for (int w = 0; w < SOLVE_THREADS / 32; w++) { const uint4 r = red[w]; n += r.x; t0 += r.y; t1 += r.z; t2 += r.w; }
+                    if (n >= (1u << 20)) break;                        // a member outside the exact range: generic path
+                    if ((int)n == prev_n) { conv = true; break; }      // nothing dropped: tau is the fixed point
+                    prev_n = (int)n;
+                    const double sum = ((double)t2 * 68719476736.0 + (double)((t1 << 18) + t0)) * down;
+                    tau = 2.0 * st.strength * (sumA + sum) / (1.0 + 2.0 * st.strength * (cntA + (double)n));
                 }
-                __syncthreads();
-                ok = s_flag != 0;
+                ok = conv && tau > b_lo && tau <= b_hi;
+                if (ok && tid == 0) a.tau[cidx] = tau;
                 __syncthreads();
             }
             if (!ok && tid == 0) a.fail[0] = 1;
