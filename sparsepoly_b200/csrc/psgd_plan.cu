@@ -1026,7 +1026,8 @@ struct SolveArgs {
     double *thr;                         // [ncol] raw-space thresholds (updated)
     double *tau;                         // [ncol] scratch: new thresholds in value units
     double *colres;                      // [2*ncol] reduced (sum, cnt) of a generic pass
-    int *fail;                           // [2] (zeroed before the launch): a column could not use its band / overflow
+    int *fail;                           // [2] = call_id when a column could not use its band / overflowed in THIS call
+    int call_id;                         // > 0, different in every call (no reset between launches)
     int npart;                           // single rank: rows of st.psum / st.pcnt the statistics pass wrote
     const double *statbox_all;           // local statboxes of all ranks [world][statbox_doubles]
     double *xbuf[SP_MAX_RANKS];          // every rank's exchange buffer region of THIS rank [2][2*ncol] (generic passes)
@@ -1052,7 +1053,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
     // ---- band path: every column's fixed point from (statistics above the band) + (the band's values)
     if (!band_on) {
         if (blockIdx.x == 0) {
-            if (tid == 0) a.fail[0] = 1;
+            if (tid == 0) a.fail[0] = a.call_id;
             if (world == 1) for (int c = tid; c < ncol; c += T) st.band_n[c] = 0;
         }
     } else {
@@ -1063,18 +1064,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
             if (world == 1) {                                    // partials + band straight from the statistics pass
                 reduce_partials(st, cidx, a.npart, ssum, scnt, &sumA, &cntA);
                 const int nb = st.band_n[cidx];
-                if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = 1; }
+                if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = a.call_id; }
                 nbv = nb < BAND_CAP ? nb : BAND_CAP;
             } else {
                 for (int r = 0; r < world; r++) {                // rank order: identical on every rank
                     const double *box = a.statbox_all + (size_t)r * boxlen;
                     sumA += box[cidx]; cntA += box[ncol + cidx];
                     const int nb = (int)box[2 * ncol + cidx];
-                    if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = 1; }
+                    if (nb > BAND_CAP) { ok = false; if (tid == 0) a.fail[1] = a.call_id; }
                     nbv += nb < BAND_CAP ? nb : BAND_CAP;
                 }
             }
-            if (nbv > BAND_TOTAL) { ok = false; if (tid == 0) a.fail[1] = 1; }
+            if (nbv > BAND_TOTAL) { ok = false; if (tid == 0) a.fail[1] = a.call_id; }
             if (tid == 0) st.state[8 + 2 * ncol + cidx] = (double)nbv;
             if (ok) {
                 const double tau_pred = predict_tau(st.state, ncol, cidx, st.strength);
@@ -1150,7 +1151,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
                 if (ok && tid == 0) a.tau[cidx] = tau;
                 __syncthreads();
             }
-            if (!ok && tid == 0) a.fail[0] = 1;
+            if (!ok && tid == 0) a.fail[0] = a.call_id;
             if (world == 1) {                                    // this column's band counter: ready for the next minibatch
                 __syncthreads();                                 // (only the block that owns the column touches it)
                 if (tid == 0) st.band_n[cidx] = 0;
@@ -1159,8 +1160,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) psgd_solve_kernel(const SolveAr
     }
     __threadfence();
     grid.sync();
-    const bool fb = *reinterpret_cast<volatile int *>(a.fail) != 0;
-    const bool over = *reinterpret_cast<volatile int *>(a.fail + 1) != 0;
+    const bool fb = *reinterpret_cast<volatile int *>(a.fail) == a.call_id;
+    const bool over = *reinterpret_cast<volatile int *>(a.fail + 1) == a.call_id;
     if (!fb) {
         if (blockIdx.x == 0) {
             for (int c = tid; c < ncol; c += T) {
@@ -1662,7 +1663,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             so.seq_out = nullptr;
             so.max_iter = 500;
             cx->seq_generic += (unsigned long long)so.max_iter;     // sequence numbers reserved for this call's exchanges
-            SP_CUDA(cudaMemsetAsync(so.fail, 0, 2 * sizeof(int), st));
+            so.call_id = (int)((cx->seq_generic / (unsigned long long)so.max_iter) & 0x3fffffffull) + 1;
             void *args[] = {(void *)&so};
             cudaError_t e = cudaLaunchCooperativeKernel((void *)psgd_solve_kernel, dim3(solve_blocks), dim3(SOLVE_THREADS), args, 0, st);
             sp_prof_end(st);
