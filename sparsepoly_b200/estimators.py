@@ -24,7 +24,7 @@ from sklearn.exceptions import NotFittedError
 from sklearn.preprocessing import LabelBinarizer, add_dummy_feature
 from sklearn.utils import check_random_state
 from sklearn.utils.multiclass import type_of_target
-from sklearn.utils.validation import check_array, check_X_y
+from sklearn.utils.validation import check_array, check_consistent_length, check_X_y
 
 from . import _lib, solvers
 from .dataset import DeviceDataset, SweepPlan, _device
@@ -144,7 +144,30 @@ class SparsePolyClassifierMixin(ClassifierMixin):
         raise ValueError("Probability estimates only available for loss='logistic'. You may use "
                          "probability calibration methods from scikit-learn instead.")
 
+    @staticmethod
+    def _binary_labels(y):
+        """(classes, y in {-1, +1}) of a 1-D numeric label array with exactly two integer-valued classes, else
+        None.  Same result as type_of_target + LabelBinarizer(pos_label=1, neg_label=-1) below, without their
+        sorts: a few streaming passes (0.03 s instead of 0.4 s at 6 M labels)."""
+        if not isinstance(y, np.ndarray) or y.ndim != 1 or y.size == 0 or y.dtype.kind not in "fiu":
+            return None
+        lo, hi = y.min(), y.max()
+        if not (np.isfinite(lo) and np.isfinite(hi) and lo < hi) or lo != np.floor(lo) or hi != np.floor(hi):
+            return None
+        is_hi = y == hi
+        if not np.all(is_hi | (y == lo)):
+            return None
+        return np.array([lo, hi], dtype=y.dtype), np.where(is_hi, 1.0, -1.0)
+
     def _check_X_y(self, X, y):
+        fast = self._binary_labels(y)
+        if fast is not None:
+            X = check_array(X, dtype=np.double, accept_sparse=True)
+            check_consistent_length(X, y)
+            lb = LabelBinarizer(pos_label=1, neg_label=-1)
+            lb.classes_, lb.y_type_, lb.sparse_input_ = fast[0], "binary", False
+            self.label_binarizer_ = lb
+            return X, fast[1]
         is_2d = hasattr(y, "shape") and len(y.shape) > 1 and y.shape[1] >= 2
         if is_2d or type_of_target(y) != "binary":
             raise TypeError("Only binary targets supported. For training multiclass or multilabel "
@@ -368,7 +391,25 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         return converged, it
 
     # ---------------------------------------------------------------- psgd
-    def _psgd_setup(self, X, y, rng, dev):
+    def _start_upload(self, X, dev):
+        """psgd: X moves to the device on a helper thread while fit() draws the initial P on this one (numpy's
+        generators and the copies both release the GIL); _psgd_setup joins it."""
+        import threading
+        box = {}
+        planned = self.regularizer in solvers.PLANNED_REGS
+
+        def work():
+            try:
+                torch.cuda.set_device(dev)
+                _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+                box["ds"] = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned)
+            except BaseException as e:          # re-raised by the joining thread
+                box["error"] = e
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        return th, box
+
+    def _psgd_setup(self, X, y, rng, dev, upload=None):
         """Move everything to the device and return (epoch, sync, close): epoch() runs one psgd.psgd_epoch
         (sparse_factorization_machines.py:123-150) and returns the epoch's mean loss (None with
         read_back=False).  l1 / squaredl12 run the planned path (psgd_plan.cu: gather passes over a batch-CSC
@@ -401,7 +442,13 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
                 torch.cuda.synchronize()
             return time.perf_counter()
         t0 = _tick()
-        ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned)
+        if upload is not None:
+            upload[0].join()
+            if "error" in upload[1]:
+                raise upload[1]["error"]
+            ds = upload[1]["ds"]
+        else:
+            ds = DeviceDataset(X, need_csr=True, need_csc=False, device=dev, hot_features=not planned)
         t1 = _tick()
         self._h2d_bytes = ds.h2d_bytes + y.nbytes + self.P_.nbytes + self.w_.nbytes
         n_glob, nnz_glob = (global_sum([n, ds.nnz], group) if group is not None else (n, ds.nnz))
@@ -489,9 +536,9 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
 
         return epoch, sync, close
 
-    def _fit_psgd(self, X, y, rng, dev):
+    def _fit_psgd(self, X, y, rng, dev, upload=None):
         """sparse_factorization_machines.py:94-173 (epoch loop, plateau stopping rule :157-170)."""
-        epoch_fn, sync, close = self._psgd_setup(X, y, rng, dev)
+        epoch_fn, sync, close = self._psgd_setup(X, y, rng, dev, upload)
         converged, epoch = False, 0
         no_improvement_count, best_loss = 0, np.inf
         try:
@@ -533,6 +580,7 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         self._check_combination(self.solver, self.regularizer, self.degree)
         dev = _device()
         _lib.check(_lib.load().sp_set_device(dev.index if dev.index is not None else 0))
+        upload = self._start_upload(X, dev) if self.solver == "psgd" else None
 
         if not (self.warm_start and hasattr(self, "w_")):
             self.w_ = np.zeros(n_features, dtype=np.double)
@@ -551,7 +599,7 @@ class _BaseSparseFactorizationMachine(_SparsePolyBase, metaclass=ABCMeta):
         else:
             if not (self.warm_start and hasattr(self, "it_")):
                 self.it_ = 1
-            converged, self.n_iter_ = self._fit_psgd(X, y, rng, dev)
+            converged, self.n_iter_ = self._fit_psgd(X, y, rng, dev, upload)
         if not converged:
             warnings.warn("Objective did not converge. Increase max_iter.")
         return self
