@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 3
+#define SP_ABI_VERSION 4
 #define SP_MAX_HOT_FEATURES 16
 #define SP_PBCD_ENT_PER_SLOT 3  /* pbcd window plan: hot nonzeros per window <= 3*slot_cap (pcd: 2*slot_cap) */
 #define SP_WINDOW_MAX 256    /* most positions per window of the pipelined sweep */
@@ -44,7 +44,7 @@ extern "C" {
 #define SP_PSGD_SHORT 8       /* columns of at most this many nonzeros are summed by one group of lanes */
 #define SP_PSGD_BAND_CAP 2048 /* band values per column and rank of the squared-l1,2 selection */
 #define SP_MAX_RANKS 8        /* most ranks (GPUs of one NVSwitch domain) a psgd fit is sharded over */
-#define SP_PSGD_CHANNELS 2    /* flag channels per rank: 0 step barriers, 1 exchanges inside the selection */
+#define SP_PSGD_CHANNELS 3    /* flag channels per rank: 0 step barriers, 1 exchanges inside the selection, 2 early pull */
 
 typedef void *sp_stream;
 
@@ -305,6 +305,11 @@ typedef struct sp_psgd_ctx {
     double *peer_inbox_g[SP_MAX_RANKS], *peer_inbox_w[SP_MAX_RANKS];   /* region of THIS rank in rank r's inbox */
     double *peer_xwork[SP_MAX_RANKS];
     uint64_t *peer_flags[SP_MAX_RANKS];    /* [SP_PSGD_CHANNELS][SP_MAX_RANKS] per rank; [rank] is local */
+    /* owned by the library (zero-initialised by the caller, released by sp_psgd_plan_release): the stream and
+     * events of the early pull -- the next minibatch's rows are fetched from the owners while this minibatch's
+     * selection runs -- and that channel's sequence number */
+    uint64_t seq_pull;
+    void *aux_stream, *aux_event[2];
 } sp_psgd_ctx;
 
 size_t sp_psgd_plan_work_doubles(int n_orders, int k);
@@ -322,6 +327,8 @@ int sp_psgd_plan_run(sp_psgd_ctx *ctx, const sp_dataset *ds, const sp_psgd_plan 
 /* end of an epoch: *loss_sum (device, may be NULL) += sum of the per-sample losses of positions
  * [0, n_local) in fixed order; materialize != 0 rewrites P / w as the model (thr = 0, C = Cw = 1). */
 int sp_psgd_plan_end(sp_psgd_ctx *ctx, int n_local, double *loss_sum, int materialize, sp_stream stream);
+/* destroys the library-owned stream / events of ctx (idempotent) */
+int sp_psgd_plan_release(sp_psgd_ctx *ctx);
 
 /* diagnostics of the squared-l1,2 selection since sp_psgd_plan_begin (synchronises the stream): out_host[0] = prox
  * calls, [1] = solved from the band, [2] = needed generic passes, [3] = band half-width, [4] / [5] = mean / largest

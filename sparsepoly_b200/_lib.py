@@ -72,7 +72,8 @@ class SpPsgdCtx(C.Structure):
                 ("err", _vp),
                 ("peer_P", _vp * MAX_RANKS), ("peer_w", _vp * MAX_RANKS),
                 ("peer_inbox_g", _vp * MAX_RANKS), ("peer_inbox_w", _vp * MAX_RANKS),
-                ("peer_xwork", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS)]
+                ("peer_xwork", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
+                ("seq_pull", C.c_uint64), ("aux_stream", _vp), ("aux_event", _vp * 2)]
 
 
 _DSP = C.POINTER(SpDataset)
@@ -120,6 +121,7 @@ SIGNATURES = {
     "sp_psgd_plan_begin": (_i, [_PCP, _vp]),
     "sp_psgd_plan_run": (_i, [_PCP, _DSP, _PPP, _vp, _vp, _d, _d, _d, _d, _i, _d, _i, _i, C.POINTER(C.c_int64), _vp]),
     "sp_psgd_plan_end": (_i, [_PCP, _i, _vp, _i, _vp]),
+    "sp_psgd_plan_release": (_i, [_PCP]),
     "sp_psgd_plan_solver_stats": (_i, [_PCP, C.POINTER(_d), _vp]),
     "sp_shm_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "sp_shm_free": (_i, [_vp]),
@@ -158,7 +160,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.sp_abi_version() != 3:
+    if lib.sp_abi_version() != 4:
         raise ImportError("libsparsepoly_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -85,7 +85,7 @@ struct RowsArgs {
     int k, d;
     const int32_t *indptr, *colidx;      // colidx: feature ids, or (STAGED) slots in the minibatch's column list
     const double *data, *y;
-    const double *Psrc, *wsrc;           // raw P [n_orders,d,k] / raw w [d]; STAGED: staged true values [U][n_orders][k] / [U]
+    const double *Psrc, *wsrc;           // raw P [n_orders,d,k] / raw w [d]; STAGED: staged raw rows [U][n_orders][k] / [U]
     const double *lams, *thr;
     double invC, invCw;
     int loss, fit_linear;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
         lam[c] = s < k ? a.lams[s] : 0.0;
 #pragma unroll
         for (int o = 0; o < NORD; o++) {
-            thr[c][o] = (!STAGED && s < k) ? a.thr[o * k + s] : 0.0;
+            thr[c][o] = s < k ? a.thr[o * k + s] : 0.0;
             Pl[c][o] = a.Psrc + (s < k ? (STAGED ? (size_t)o * k + s : o * dk + s) : 0);
         }
     }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
             int jn = 0;                                       // the next block of (column, value): in flight during this one
             double xn = 0.0;
             if (base + G + lane < en) { jn = a.colidx[base + G + lane]; xn = a.data[base + G + lane]; }
-            if (lin) ypred += xl * (STAGED ? a.wsrc[jl] : a.wsrc[jl] * invCw);
+            if (lin) ypred += xl * (a.wsrc[jl] * invCw);
             const int cnt = min(G, en - base);
             constexpr int UBR = 16 / (KCH * NORD);
             constexpr int UB = UBR >= 8 ? 8 : (UBR >= 4 ? 4 : (UBR >= 2 ? 2 : 1));
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) psgd_rows_kernel(const RowsArgs
                     for (int c = 0; c < KCH; c++)
 #pragma unroll
                         for (int o = 0; o < NORD; o++) {
-                            const double p = STAGED ? pv[u][c][o] : st_true(pv[u][c][o], thr[c][o], invC);
+                            const double p = st_true(pv[u][c][o], thr[c][o], invC);
 #pragma unroll
                             for (int t = 0; t < DEG - o; t++)           // _anova, psgd.py:34-44
                                 A[c][o][DEG - o - t] += (A[c][o][DEG - o - t - 1] * xv[u]) * p;
@@ -318,7 +318,7 @@ __device__ __forceinline__ void finish_column(const ColsArgs &a, int lane, int u
     }
 }
 
-// RAW gather of row `feat` (single rank) / of the staged true values of slot `su` (sharded); row_values() turns
+// RAW gather of row `feat` (single rank) / of the staged raw row of slot `su` (sharded); row_values() turns
 // the raw values into the true (pre-update) ones afterwards, so that the gathers of a batch are issued back to back
 template <int NORD, int G, int KCH, int MODE>
 __device__ __forceinline__ void load_row(const ColsArgs &a, int lane, int feat, long long su, double (&p)[KCH][NORD],
@@ -337,12 +337,10 @@ __device__ __forceinline__ void load_row(const ColsArgs &a, int lane, int feat, 
 }
 template <int NORD, int G, int KCH, int MODE>
 __device__ __forceinline__ void row_values(const ColsArgs &a, double (&p)[KCH][NORD], const double (&thr)[KCH][NORD]) {
-    if (MODE == MODE_APPLY) {
 #pragma unroll
-        for (int c = 0; c < KCH; c++)
+    for (int c = 0; c < KCH; c++)
 #pragma unroll
-            for (int o = 0; o < NORD; o++) p[c][o] = st_true(p[c][o], thr[c][o], a.s.invC);
-    }
+        for (int o = 0; o < NORD; o++) p[c][o] = st_true(p[c][o], thr[c][o], a.s.invC);
 }
 
 // one term of psgd._update_grads (psgd.py:60-91) for nonzero x of a sample with table rows av, dloss dl
@@ -674,14 +672,13 @@ struct PullArgs {
     const int32_t *u_feat;               // the minibatch's columns (minibatch-relative pointer)
     const double *peer_P[SP_MAX_RANKS];  // owners' raw rows [n_orders][d_own][k]
     const double *peer_w[SP_MAX_RANKS];  // owners' raw w [d_own]
-    const double *thr;
-    double invC, invCw;
     int n_orders, fit_linear;
     double *stage, *stage_w;             // [n_cols][n_orders][k], [n_cols]
 };
 
-// true values of the rows this rank's minibatch touches, read from the owners' HBM (NVLink peer loads; .cv: peer
-// lines must not be served from a stale L1).  One warp per row batch, lane = element of the row, 8 rows in flight per
+// RAW rows this rank's minibatch touches, read from the owners' HBM (NVLink peer loads; .cv: peer lines must
+// not be served from a stale L1).  Raw, because the pull of minibatch m+1 runs on its own stream WHILE the
+// selection of minibatch m runs: that only moves the frame (thresholds, scale), which the readers of the stage apply.  One warp per row batch, lane = element of the row, 8 rows in flight per
 // warp: the latency of a peer load (~2 us) is covered by ~130 KB in flight per SM, so the pass is NVLink-bound.
 __global__ void __launch_bounds__(PL_THREADS) psgd_pull_kernel(const PullArgs a) {
     const int k = a.k, rowlen = a.n_orders * k;
@@ -702,14 +699,13 @@ __global__ void __launch_bounds__(PL_THREADS) psgd_pull_kernel(const PullArgs a)
                 raw[t] = (e < rowlen && u0 + t < a.n_cols) ? __ldcv(a.peer_P[owner] + ((size_t)o * a.d_own + q) * k + s) : 0.0;
             }
             if (e < rowlen) {
-                const double T = a.thr[o * k + s];
 #pragma unroll
                 for (int t = 0; t < UB; t++)
-                    if (u0 + t < a.n_cols) a.stage[(size_t)(u0 + t) * rowlen + e] = st_true(raw[t], T, a.invC);
+                    if (u0 + t < a.n_cols) a.stage[(size_t)(u0 + t) * rowlen + e] = raw[t];
             }
         }
         if (a.fit_linear && lane < UB && u0 + lane < a.n_cols)
-            a.stage_w[u0 + lane] = __ldcv(a.peer_w[jl % a.world] + jl / a.world) * a.invCw;
+            a.stage_w[u0 + lane] = __ldcv(a.peer_w[jl % a.world] + jl / a.world);
     }
 }
 
@@ -1412,6 +1408,27 @@ static int xbarrier(const sp_psgd_ctx *cx, int chan, unsigned long long seq, cud
     return SP_OK;
 }
 
+// the context's own stream (high priority: its few blocks slot in between the statistics pass's) and events
+static int aux_init(sp_psgd_ctx *cx) {
+    if (cx->aux_stream != nullptr) return SP_OK;
+    int lo = 0, hi = 0;
+    SP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    SP_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    cudaEvent_t e0, e1;
+    SP_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    SP_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    cx->aux_stream = s; cx->aux_event[0] = e0; cx->aux_event[1] = e1;
+    return SP_OK;
+}
+extern "C" int sp_psgd_plan_release(sp_psgd_ctx *cx) {
+    if (cx == nullptr) return SP_OK;
+    if (cx->aux_stream != nullptr) { cudaStreamSynchronize((cudaStream_t)cx->aux_stream); cudaStreamDestroy((cudaStream_t)cx->aux_stream); }
+    for (int i = 0; i < 2; i++) if (cx->aux_event[i] != nullptr) cudaEventDestroy((cudaEvent_t)cx->aux_event[i]);
+    cx->aux_stream = nullptr; cx->aux_event[0] = cx->aux_event[1] = nullptr;
+    return SP_OK;
+}
+
 // layout of cx->work (doubles)
 struct WorkLayout {
     size_t psum, pcnt, colres, tau, state, band, statbox, xbuf, ints, total;
@@ -1537,6 +1554,43 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
     int solve_blocks = 0;
     if (cx->reg == SP_REG_SQL12) { rc = solve_grid(&solve_blocks, (int)ncol); if (rc) return rc; }
     int64_t it = *it_io_host;
+    // sharded: the raw rows minibatch m touches are pulled on the context's own stream -- for the first minibatch
+    // of the call right away (every owner's rows are final: the previous step ended with a barrier), for the
+    // others as soon as every rank's owner update of minibatch m-1 is done (flag barrier on channel 2 of that
+    // stream), i.e. WHILE the statistics pass / selection of m-1 run here: those only move the frame.
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_own = nullptr, ev_pull = nullptr;
+    auto pull = [&](int m) -> int {
+        const PlanMb pm = plan_mb(pl, m);
+        PullArgs pa;
+        pa.k = k; pa.d_own = cx->d_rows; pa.world = cx->world; pa.n_cols = (int)(pm.u1 - pm.u0);
+        pa.u_feat = pl->u_feat + pm.u0;
+        for (int r = 0; r < SP_MAX_RANKS; r++) { pa.peer_P[r] = r < cx->world ? cx->peer_P[r] : nullptr; pa.peer_w[r] = r < cx->world ? cx->peer_w[r] : nullptr; }
+        pa.n_orders = nord; pa.fit_linear = cx->fit_linear;
+        pa.stage = cx->stage; pa.stage_w = cx->stage_w;
+        if (pa.n_cols > 0) {
+            long long blocks = ((long long)(pa.n_cols + 7) / 8 + 7) / 8;          // 8 rows per warp pass, 8 warps per block
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            if (blocks < 1) blocks = 1;
+            sp_prof_begin(SP_PROF_ROWS, s2);                                     // (sharded psgd: class 0 = pull)
+            psgd_pull_kernel<<<(int)blocks, PL_THREADS, 0, s2>>>(pa);
+            sp_prof_end(s2);
+            SP_LAUNCH_CHECK("psgd_pull_kernel");
+        }
+        SP_CUDA(cudaEventRecord(ev_pull, s2));
+        return SP_OK;
+    };
+    if (sharded) {
+        rc = aux_init(cx);
+        if (rc) return rc;
+        s2 = (cudaStream_t)cx->aux_stream; ev_own = (cudaEvent_t)cx->aux_event[0]; ev_pull = (cudaEvent_t)cx->aux_event[1];
+        if (m_begin < m_end) {
+            SP_CUDA(cudaEventRecord(ev_own, st));
+            SP_CUDA(cudaStreamWaitEvent(s2, ev_own, 0));
+            rc = pull(m_begin);
+            if (rc) return rc;
+        }
+    }
     for (int m = m_begin; m < m_end; m++) {
         const PlanMb mb = plan_mb(pl, m);
         const long long b_glob = (long long)(mb.b1 - mb.b0) * cx->world;
@@ -1550,23 +1604,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
         sa.rP = 1.0 / sa.denP; sa.rw = 1.0 / sa.denw;
         sa.fit_linear = cx->fit_linear;
         const double strength = gamma * eta_P / (1.0 + eta_P * beta);                     // psgd.py:122
-        if (sharded) {
-            PullArgs pa;
-            pa.k = k; pa.d_own = cx->d_rows; pa.world = cx->world; pa.n_cols = (int)(mb.u1 - mb.u0);
-            pa.u_feat = pl->u_feat + mb.u0;
-            for (int r = 0; r < SP_MAX_RANKS; r++) { pa.peer_P[r] = r < cx->world ? cx->peer_P[r] : nullptr; pa.peer_w[r] = r < cx->world ? cx->peer_w[r] : nullptr; }
-            pa.thr = cx->thr; pa.invC = sa.invC; pa.invCw = sa.invCw; pa.n_orders = nord; pa.fit_linear = cx->fit_linear;
-            pa.stage = cx->stage; pa.stage_w = cx->stage_w;
-            if (pa.n_cols > 0) {
-                long long blocks = ((long long)(pa.n_cols + 7) / 8 + 7) / 8;          // 8 rows per warp pass, 8 warps per block
-                if (blocks > 148 * 8) blocks = 148 * 8;
-                if (blocks < 1) blocks = 1;
-                sp_prof_begin(SP_PROF_ROWS, st);                                     // (sharded psgd: class 0 = pull)
-                psgd_pull_kernel<<<(int)blocks, PL_THREADS, 0, st>>>(pa);
-                sp_prof_end(st);
-                SP_LAUNCH_CHECK("psgd_pull_kernel");
-            }
-        }
+        if (sharded) SP_CUDA(cudaStreamWaitEvent(st, ev_pull, 0));          // this minibatch's rows are staged
 #define SP_MB(D, N, GG, KC) rc = launch_minibatch<D, N, GG, KC>(cx, ds, pl, y, idx_samples, mb, sa, st)
 #define SP_MB_K(D, N)                                                                      \
         if (k <= 8) SP_MB(D, N, 8, 1);                                                     \
@@ -1608,6 +1646,15 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
 #undef SP_OW
             sp_prof_end(st);
             if (rc) return rc;
+            if (m + 1 < m_end) {                                   // next minibatch's rows: see above
+                SP_CUDA(cudaEventRecord(ev_own, st));
+                SP_CUDA(cudaStreamWaitEvent(s2, ev_own, 0));
+                cx->seq_pull += 1;
+                rc = xbarrier(cx, 2, cx->seq_pull, s2);
+                if (rc) return rc;
+                rc = pull(m + 1);
+                if (rc) return rc;
+            }
         }
         cx->C = sa.CnP; cx->Cw = sa.Cnw;
         const double invCn = 1.0 / cx->C;
@@ -1633,6 +1680,7 @@ extern "C" int sp_psgd_plan_run(sp_psgd_ctx *cx, const sp_dataset *ds, const sp_
             const int tpr = (k & 1) ? k : k / 2, rpp = PL_THREADS / tpr;
             long long nblk = ((long long)cx->d_rows + rpp - 1) / rpp;
             if (nblk > STAT_PART_MAX) nblk = STAT_PART_MAX;
+            if (sharded && nblk > 148 * 2) nblk = 148 * 2;         // (leaves room on every SM for the early pull's blocks)
             if (nblk < 1) nblk = 1;
             sp_prof_begin(SP_PROF_PROX, st);
             psgd_stats_kernel<<<(int)nblk, PL_THREADS, 0, st>>>(sg);

@@ -25,7 +25,7 @@ from . import _lib
 CHUNK = 64            # SP_PSGD_CHUNK
 SHORT = 8             # SP_PSGD_SHORT
 MAX_RANKS = 8         # SP_MAX_RANKS
-CHANNELS = 2          # SP_PSGD_CHANNELS
+CHANNELS = 3          # SP_PSGD_CHANNELS
 _GROUP_ENTRIES = 48_000_000     # nonzeros sorted at a time while building (bounds the temporaries)
 
 
@@ -433,7 +433,9 @@ class PsgdContext:
         s.world, s.rank = self.world, self.rank
         s.bufA, s.bufdL, s.sample_loss = self.bufA.data_ptr(), self.bufdL.data_ptr(), self.sample_loss.data_ptr()
         s.part_g, s.part_w, s.work = self.part_g.data_ptr(), self.part_w.data_ptr(), self.work.data_ptr()
-        s.C, s.Cw, s.seq, s.seq_generic = 1.0, 1.0, 0, 0
+        s.C, s.Cw, s.seq, s.seq_generic, s.seq_pull = 1.0, 1.0, 0, 0, 0
+        s.aux_stream = None
+        s.aux_event[0] = s.aux_event[1] = None
         self.struct = s
 
     def ref(self):
@@ -494,6 +496,9 @@ class PsgdContext:
 
     def close(self):
         L = _lib.load()
+        if getattr(self, "struct", None) is not None and self.struct.aux_stream:
+            torch.cuda.synchronize()
+            L.sp_psgd_plan_release(self.ref())
         if self._slab is not None:
             torch.cuda.synchronize()
             if self.group is not None:

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.sp_abi_version() == 3
+    assert lib.sp_abi_version() == 4
 
 
 def test_get_eta_matches_oracle():
