@@ -22,13 +22,14 @@
 //   stats (psgd_stats_kernel) squaredl12 only: one read-only streaming pass over the raw matrix collects,
 //                             per column, (count, sum) of |value| above a band around the predicted
 //                             threshold and the band's values;
-//   solve (psgd_solve_kernel) sorts each band and runs the fixed-point iteration
-//                             tau <- 2 s S(tau) / (1 + 2 s C(tau)) to the (theta, S) that the reference's
-//                             randomized-pivot search finds (utils.py:26-70); generic read-only passes
-//                             when a band misses.
+//   solve (psgd_solve_kernel) runs the fixed-point iteration tau <- 2 s S(tau) / (1 + 2 s C(tau)) over each
+//                             band (members in registers, exact order-independent sums) to the (theta, S)
+//                             that the reference's randomized-pivot search finds (utils.py:26-70); generic
+//                             read-only passes when a band misses.
 //
 // Sharded over G ranks (one process per GPU, samples sharded, P sharded by rows j % G): the ranks PULL
-// the rows their minibatch touches from the owners' HBM over NVLink peer memory (psgd_pull_kernel),
+// the raw rows their minibatch touches from the owners' HBM over NVLink peer memory (psgd_pull_kernel, on
+// the context's own stream: minibatch m+1's rows travel while minibatch m's selection runs),
 // PUSH their partial gradient rows into the owners' inboxes (cols kernel epilogue), the owner adds
 // them in rank order and updates its rows (psgd_owner_kernel), and the column statistics are
 // exchanged through peer memory as well -- no NCCL on the data path.
@@ -1265,14 +1266,23 @@ __global__ void psgd_zero_kernel(double *p, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
 }
 
-// fixed-order sum of the per-sample losses of positions [b0, b1) (single block; epoch end)
-__global__ void __launch_bounds__(1024) psgd_loss_sum_kernel(const double *sloss, long long b0, long long b1, double *out) {
+// fixed-order sum of the per-sample losses of positions [b0, b1) (epoch end): LOSS_BLOCKS grid-strided block sums,
+// then one block adds them to *out -- the same association for the same n on every run
+constexpr int LOSS_BLOCKS = 148;
+__global__ void __launch_bounds__(1024) psgd_loss_part_kernel(const double *sloss, long long b0, long long b1, double *part) {
     __shared__ double sh[1024];
     double acc = 0.0;
-    for (long long b = b0 + threadIdx.x; b < b1; b += 1024) acc += sloss[b];
+    for (long long b = b0 + (long long)blockIdx.x * 1024 + threadIdx.x; b < b1; b += (long long)LOSS_BLOCKS * 1024) acc += sloss[b];
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) psgd_loss_sum_kernel(const double *part, double *out) {
+    __shared__ double sh[256];
+    sh[threadIdx.x] = (int)threadIdx.x < LOSS_BLOCKS ? part[threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
     if (threadIdx.x == 0) out[0] = out[0] + sh[0];
 }
 
@@ -1730,7 +1740,11 @@ extern "C" int sp_psgd_plan_end(sp_psgd_ctx *cx, int n_local, double *loss_sum, 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (loss_sum && n_local > 0) {
-        psgd_loss_sum_kernel<<<1, 1024, 0, st>>>(cx->sample_loss, 0, n_local, loss_sum);
+        const WorkLayout L = work_layout((size_t)cx->n_orders * cx->k, cx->world);
+        double *part = cx->work + L.psum;                          // (free between minibatches; >= 444 doubles)
+        psgd_loss_part_kernel<<<LOSS_BLOCKS, 1024, 0, st>>>(cx->sample_loss, 0, n_local, part);
+        SP_LAUNCH_CHECK("psgd_loss_part_kernel");
+        psgd_loss_sum_kernel<<<1, 256, 0, st>>>(part, loss_sum);
         SP_LAUNCH_CHECK("psgd_loss_sum_kernel");
     }
     if (materialize) {

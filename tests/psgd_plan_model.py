@@ -72,6 +72,41 @@ def michelot(vals, strength):
     raise RuntimeError("no fixed point")
 
 
+def band_exact_sum(vals, E):
+    """psgd_solve_kernel's order-independent band sum: every member lies in (2^(E-2), 2^E), so v * 2^(54-E) is an
+    integer below 2^54; three 18-bit limbs are added in (32-bit) integers and the total is rounded once."""
+    vals = np.asarray(vals, dtype=np.float64)
+    I = np.ldexp(vals, 54 - E)
+    assert np.all(I == np.floor(I)) and np.all(I < 2.0 ** 54)
+    I = I.astype(np.uint64)
+    l0 = int(np.sum(I & np.uint64(0x3ffff), dtype=np.uint64))
+    l1 = int(np.sum((I >> np.uint64(18)) & np.uint64(0x3ffff), dtype=np.uint64))
+    l2 = int(np.sum(I >> np.uint64(36), dtype=np.uint64))
+    assert max(l0, l1, l2) < 2 ** 32 or len(vals) > 2048
+    return float(np.ldexp(float(l2) * 68719476736.0 + float((l1 << 18) + l0), E - 54))
+
+
+def band_solve(band, sumA, cntA, strength, b_lo, b_hi, max_iter=64):
+    """psgd_solve_kernel's band path for one column: (sumA, cntA) = sum / number of the values above the band,
+    `band` = the values inside (b_lo, b_hi] in ANY order.  Returns tau, or None where the kernel falls back to
+    the generic passes."""
+    band = np.asarray(band, dtype=np.float64)
+    E = int(np.floor(np.log2(b_hi))) + 1
+    if band.size and not (np.all(band > 2.0 ** (E - 2)) and np.all(band < 2.0 ** E)):
+        return None
+    tau, prev_n = b_lo, -1
+    for _ in range(max_iter):
+        act = band > tau
+        n = int(act.sum())
+        if n == prev_n:
+            return tau if b_lo < tau <= b_hi else None
+        prev_n = n
+        s = band_exact_sum(band[act], E) if n else 0.0
+        tau = 2.0 * strength * (sumA + s) / (1.0 + 2.0 * strength * (cntA + n))
+    return None
+
+
+
 class RankState:
     def __init__(self, plan, csr, y, idx, n_orders, k, degree):
         t = lambda a: None if a is None else a.cpu().numpy()      # noqa: E731

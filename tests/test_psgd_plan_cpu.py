@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import psgd_plan_model as M
 from psgd_plan_model import RankState, run_model
 from sparsepoly_b200 import synth
 from sparsepoly_b200.distributed import interleave_shards
@@ -133,3 +134,59 @@ def test_plan_model_matches_oracle(case, world):
     assert it == out["it_"]
     assert abs(sum_loss / (n_loc * world) - out["trace"][-1]) <= 1e-9 * abs(out["trace"][-1])
     assert 0.02 < np.mean(P_ref != 0) < 0.999 or kw["regularizer"] == "l1"
+
+
+# ---------------------------------------------------------------- squared-l1,2 band solve (psgd_solve_kernel)
+def _sorted_rule(vals, strength):
+    """utils.py:26-70 restated with a sort: the largest theta with v_(theta) > 2 s S_theta / (1 + 2 s theta)."""
+    v = np.sort(np.asarray(vals, dtype=np.float64))[::-1]
+    cs = np.cumsum(v)
+    tq = 2.0 * strength * cs / (1.0 + 2.0 * strength * np.arange(1, v.size + 1))
+    ok = np.nonzero(v > tq)[0]
+    m = int(ok.max()) + 1 if ok.size else 0
+    return (2.0 * strength * cs[m - 1] / (1.0 + 2.0 * strength * m)) if m else 0.0, m
+
+
+def test_band_exact_sum_is_order_independent_and_correctly_rounded():
+    import math
+    rng = np.random.RandomState(3)
+    for trial in range(200):
+        hi = 10.0 ** rng.uniform(-9, 3)
+        E = int(np.floor(np.log2(hi))) + 1
+        n = rng.randint(1, 2049)
+        vals = hi * (1.0 - 0.18 * rng.rand(n))                       # inside (0.82 hi, hi]: the widest band (+-10 %)
+        s0 = M.band_exact_sum(vals, E)
+        assert s0 == M.band_exact_sum(vals[rng.permutation(n)], E)   # any order: the same bits
+        assert s0 == math.fsum(vals)                                 # the exactly rounded sum
+
+
+def test_band_solve_matches_the_sorted_rule():
+    rng = np.random.RandomState(4)
+    hits = 0
+    for trial in range(400):
+        n_all = rng.randint(5, 400)
+        strength = 10.0 ** rng.uniform(-3, 1)
+        vals = np.abs(rng.randn(n_all)) * 10.0 ** rng.uniform(-4, 1)
+        tau_ref, theta = _sorted_rule(vals, strength)
+        delta = rng.choice([0.002, 0.01, 0.02, 0.1])
+        tp = tau_ref * (1.0 + 0.6 * delta * (2.0 * rng.rand() - 1.0))  # a prediction a little off the true threshold
+        b_lo, b_hi = tp * (1.0 - delta), tp * (1.0 + delta)
+        above = vals[vals > b_hi]
+        band = vals[(vals > b_lo) & ~(vals > b_hi)]
+        tau = M.band_solve(band[rng.permutation(band.size)], float(np.sum(above)), float(above.size), strength, b_lo, b_hi)
+        assert tau is not None                                        # the true threshold is inside the band
+        assert abs(tau - tau_ref) <= 1e-13 * tau_ref
+        assert int(np.sum(vals > tau)) == theta
+        hits += 1
+    assert hits == 400
+
+
+def test_band_solve_reports_a_miss():
+    vals = np.array([1.0, 0.9, 0.8, 0.05, 0.04])
+    strength = 0.3
+    tau_ref, _ = _sorted_rule(vals, strength)
+    for tp in (tau_ref * 1.5, tau_ref * 0.6):                          # prediction far off: the band does not hold tau
+        b_lo, b_hi = tp * 0.98, tp * 1.02
+        above = vals[vals > b_hi]
+        band = vals[(vals > b_lo) & ~(vals > b_hi)]
+        assert M.band_solve(band, float(above.sum()), float(above.size), strength, b_lo, b_hi) is None
