@@ -151,3 +151,28 @@ def test_fitted_estimators_pickle_without_device_state():
     assert np.array_equal(est2.P_, est.P_) and est2.n_iter_ == 4 and not hasattr(est2, "_dev_state")
     est3 = copy.deepcopy(est)
     assert not hasattr(est3, "_dev_state") and est3.get_params() == est.get_params()
+
+
+def test_binary_label_fast_path_equals_label_binarizer():
+    """Classifier._binary_labels (a few streaming passes) must give what the reference's
+    type_of_target + LabelBinarizer(pos_label=1, neg_label=-1) give (base.py:126-142), and must step aside
+    for everything else."""
+    from sklearn.preprocessing import LabelBinarizer
+
+    from sparsepoly_b200.estimators import SparsePolyClassifierMixin as Mixin
+    rng = np.random.RandomState(0)
+    for y in (rng.randint(0, 2, 64), np.where(rng.rand(64) < 0.3, 1.0, -1.0), rng.randint(0, 2, 64) * 3 + 2,
+              rng.randint(0, 2, 64).astype(np.uint8), rng.randint(0, 2, 64).astype(np.float32)):
+        fast = Mixin._binary_labels(y)
+        lb = LabelBinarizer(pos_label=1, neg_label=-1)
+        want = lb.fit_transform(y).ravel().astype(np.double)
+        assert fast is not None and np.array_equal(fast[1], want) and np.array_equal(fast[0], lb.classes_)
+        lb2 = LabelBinarizer(pos_label=1, neg_label=-1)
+        lb2.classes_, lb2.y_type_, lb2.sparse_input_ = fast[0], "binary", False
+        yp = rng.rand(64) > 0.5
+        assert np.array_equal(lb2.inverse_transform(yp), lb.inverse_transform(yp))
+        assert lb2.inverse_transform(yp).dtype == lb.inverse_transform(yp).dtype
+    for y in (rng.rand(16), rng.randint(0, 3, 64), np.array([1.0, 1.0]), np.array([0.5, 1.5, 0.5]),
+              np.array(["a", "b"]), np.array([0.0, np.nan, 1.0]), np.array([0.0, np.inf]), np.zeros((4, 1)),
+              [0, 1, 0], np.array([True, False])):
+        assert Mixin._binary_labels(y) is None
