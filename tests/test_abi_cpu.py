@@ -176,3 +176,24 @@ def test_binary_label_fast_path_equals_label_binarizer():
               np.array(["a", "b"]), np.array([0.0, np.nan, 1.0]), np.array([0.0, np.inf]), np.zeros((4, 1)),
               [0, 1, 0], np.array([True, False])):
         assert Mixin._binary_labels(y) is None
+
+
+def test_upload_thread_errors_reach_the_caller():
+    """fit() moves X to the device on a helper thread (estimators._start_upload); whatever goes wrong there must be
+    raised by the joining thread, not swallowed.  Without a GPU the helper fails at once: exactly that case."""
+    import scipy.sparse as sp
+    import torch
+
+    import sparsepoly_b200 as S
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA")
+    est = S.SparseFactorizationMachineClassifier(solver="psgd", regularizer="squaredl12", n_components=2)
+    X = sp.random(20, 5, density=0.5, format="csr", random_state=0)
+    y = np.where(np.arange(20) % 2 == 0, 1.0, -1.0)
+    dev = torch.device("cuda", 0)
+    upload = est._start_upload(X, dev)
+    upload[0].join()
+    assert "error" in upload[1] and "ds" not in upload[1]
+    est.P_, est.w_, est.lams_, est.it_ = np.zeros((1, 2, 5)), np.zeros(5), np.ones(2), 1
+    with pytest.raises(type(upload[1]["error"])):
+        est._psgd_setup(X, y, np.random.RandomState(0), dev, upload)
