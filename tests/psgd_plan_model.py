@@ -145,6 +145,7 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
     bL = ranks[0].plan.batch_local
     degs = [degree - o for o in range(n_orders)]
     sum_loss = 0.0
+    early = {}                                          # rank -> RAW rows of its next minibatch, pulled before the prox
     for _ in range(epochs):
         for m in range(M):
             eta_P, eta_w = get_eta(lr, eta0, alpha, beta, power_t, it)
@@ -161,14 +162,19 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                 e0, e1 = pl.mb_eptr[m], pl.mb_eptr[m + 1]
                 u0, u1 = pl.mb_uptr[m], pl.mb_uptr[m + 1]
                 b0, b1 = m * bL, min((m + 1) * bL, pl.n_local)
-                # ---- pull (sharded) / direct reads: true rows of the minibatch's columns
+                # ---- pull (sharded) / direct reads: RAW rows of the minibatch's columns -- for every minibatch but the
+                #      first of an epoch they were fetched right after the owners' update of the previous one, i.e.
+                #      BEFORE its prox moved the frame (psgd_pull_kernel on the context's own stream); the readers apply
+                #      the frame of THIS minibatch
                 feats = R.u_feat[u0:u1]
-                stage = np.zeros((u1 - u0, n_orders, k))
-                stage_w = np.zeros(u1 - u0)
-                for su, j in enumerate(feats):
-                    own, q = ranks[j % G], j // G
-                    stage[su] = st_true(own.P[:, q, :], thr, invC)
-                    stage_w[su] = own.w[q] * invCw
+                if r in early:
+                    raw_stage, raw_w = early.pop(r)
+                else:
+                    raw_stage = np.stack([ranks[j % G].P[:, j // G, :] for j in feats]) if len(feats) else np.zeros((0, n_orders, k))
+                    raw_w = np.array([ranks[j % G].w[j // G] for j in feats])
+                assert raw_stage.shape[0] == u1 - u0
+                stage = st_true(raw_stage, thr, invC)
+                stage_w = raw_w * invCw
                 slot_of = {int(j): su for su, j in enumerate(feats)}
                 # ---- rows pass
                 bufA = {}
@@ -309,6 +315,13 @@ def run_model(ranks, d, n_orders, k, degree, reg, loss, fit_linear, lams, alpha,
                         if fit_linear:
                             R.w[q] = ((R.w[q] * invCw - gw * cw) / denw) * Cnw
             C, Cw = CnP, Cnw
+            # ---- early pull of the next minibatch's raw rows (every owner's rows are final; the prox below only
+            #      moves thr)
+            if m + 1 < M:
+                for r, R in enumerate(ranks):
+                    nf = R.u_feat[R.plan.mb_uptr[m + 1]:R.plan.mb_uptr[m + 2]]
+                    early[r] = (np.stack([ranks[j % G].P[:, j // G, :].copy() for j in nf]) if len(nf) else np.zeros((0, n_orders, k)),
+                                np.array([ranks[j % G].w[j // G] for j in nf]))
             # ---- prox as a lazily applied column threshold
             if reg == "l1":
                 thr = thr + C * strength
